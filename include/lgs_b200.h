@@ -1,0 +1,142 @@
+/*
+ * lgs_b200 — C ABI of the B200-native sparse-voxel convolution engine.
+ *
+ * Drop-in boundary: the reference (RozDavid/LanguageGroundedSemseg) enters this path only through
+ * the Python names of the un-vendored package MinkowskiEngine 0.5.4; ME's own native boundary is the pybind module
+ * MinkowskiEngineBackend._C.  Each entry point below names the ME backend call it replaces and the reference call
+ * site (relative to /root/reference) that exercises it.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no torch types.  Every pointer prefixed d_ is DEVICE memory owned by the caller
+ *     (PyTorch's caching allocator in the facade); the engine allocates nothing and keeps no state between calls,
+ *     so a coordinate map is just the buffers the caller holds (coords + cuckoo table).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it.  No thread-local CUDA state:
+ *     forward runs on the Python thread, backward on PyTorch's autograd thread.
+ *   - return 0 on success, negative LGS_E_* otherwise; lgs_last_error() gives a per-thread message.
+ *   - functions taking a host out-pointer (h_*) synchronise `stream` before returning.
+ */
+#ifndef LGS_B200_H
+#define LGS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGS_OK 0
+#define LGS_E_INVALID (-1)      /* bad argument */
+#define LGS_E_CUDA (-2)         /* CUDA runtime error */
+#define LGS_E_RANGE (-3)        /* coordinate outside the packable range, see lgs_coord_limit() */
+#define LGS_E_HASH_FULL (-4)    /* cuckoo eviction chain exceeded its bound: retry with a larger capacity */
+#define LGS_E_UNSUPPORTED (-5)  /* shape / dtype / algo combination not built */
+
+/* feature dtypes */
+#define LGS_F32 0
+#define LGS_BF16 1
+/* conv algorithms */
+#define LGS_ALGO_SIMT 0  /* fp32 FMA, exact: the parity anchor */
+#define LGS_ALGO_TC 1    /* tcgen05 tensor cores, TMEM accumulators (TF32 for LGS_F32 features, BF16 for LGS_BF16) */
+
+int lgs_version(void);
+const char* lgs_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t lgs_launch_count(void);
+/* 1 if the library was built with the tcgen05 path */
+int lgs_has_tc(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Coordinate maps.   Replaces ME CoordinateMapManagerGPU_c10::insert_and_map / ::stride
+ *   call sites: SparseTensor(input, coords) lib/train_test/pl_BaselineTrainer.py:300;
+ *               stride-2 convs models/res16unet.py:49,66,83,100; quantisation lib/voxelizer.py:142.
+ * Coordinates are int32 [n,4] = (batch, x, y, z).  Keys are packed to 64 bit: batch in [0, 1023),
+ * |x|,|y|,|z| < lgs_coord_limit().
+ * --------------------------------------------------------------------------------------------------------- */
+int32_t lgs_coord_limit(void);
+/* slots (power of two, >= 2n) a cuckoo table for n keys needs; keys: uint64[cap], vals: int32[cap] */
+int64_t lgs_hash_capacity(int64_t n);
+/* int32 scratch elements lgs_coordmap_build needs for n rows */
+int64_t lgs_coordmap_scratch_elems(int64_t n);
+
+/* Build a coordinate map from n rows: each row is floored to a multiple of `quant` (the new tensor stride; 1 = keep),
+ * inserted into the cuckoo table, duplicates collapse and the FIRST row (lowest index) wins.  Unique rows are
+ * numbered in order of first occurrence — the order ME's CPU manager produces, so a
+ * duplicate-free input keeps its row order.
+ *   d_out_coords   [n,4]  first n_unique rows valid (quantised coordinates)
+ *   d_unique_index [n]    first n_unique valid: input row each unique row came from (ascending)
+ *   d_inverse      [n]    unique row of every input row
+ *   d_n_unique     [1]    device copy of the count;  h_n_unique: host copy (stream is synchronised)        */
+int lgs_coordmap_build(const int32_t* d_coords, int64_t n, int32_t quant,
+                       uint64_t* d_table_keys, int32_t* d_table_vals, int64_t capacity,
+                       int32_t* d_out_coords, int32_t* d_unique_index, int32_t* d_inverse,
+                       int32_t* d_scratch, int32_t* d_n_unique, int64_t* h_n_unique, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Kernel maps.   Replaces ME CoordinateMapManagerGPU_c10::kernel_map (cached per (keys, ks, stride, dilation))
+ *   call sites: every conv()/conv_tr() models/modules/common.py:195,228.
+ * Output-stationary neighbour table: d_table[k*n_out + o] = row i of the INPUT map with
+ * C_in[i] == C_out[o] + off_k, or -1.  off_k enumerates x fastest (k = ix + ks*iy + ks^2*iz); odd ks is centred,
+ * even ks starts at 0; offsets are multiples of in_tensor_stride*dilation (App. A.5).  d_counts[k] = pairs of
+ * offset k.  The ME pair list of offset k is {(table[k][o], o) : table[k][o] >= 0}.
+ * --------------------------------------------------------------------------------------------------------- */
+int lgs_kmap_build(const int32_t* d_out_coords, int64_t n_out,
+                   const uint64_t* d_in_table_keys, const int32_t* d_in_table_vals, int64_t in_capacity,
+                   int32_t ksize, int32_t in_tensor_stride, int32_t dilation,
+                   int32_t* d_table, int32_t* d_counts, void* stream);
+/* Transposed table: d_table_t[k*n_in + i] = o where d_table[k*n_out + o] == i, else -1 (each (k,i) has at most one o).
+ * Used by MinkowskiConvolutionTranspose (common.py:228) and by dgrad of strided convs.                      */
+int lgs_kmap_transpose(const int32_t* d_table, int32_t K, int64_t n_out, int64_t n_in, int32_t* d_table_t,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Sparse convolution.   Replaces ME ConvolutionForwardGPU / ConvolutionBackwardGPU (and ...Transpose...)
+ *   call sites: models/modules/common.py:195-203, 228-236; autograd backward of the same.
+ *   out[o,:] = sum_k in[table[kk][o], :] @ W[k]  (+ bias),   kk = reverse_k ? K-1-k : k
+ * d_table == NULL means the identity map with K == 1 (1x1x1 convs, models/resnet.py:95-101, res16unet.py:193).
+ * dgrad is the same call with (in := grad_out, W := W^T per offset [K,c_out,c_in], table := transposed table,
+ * or the same table with reverse_k = 1 when in and out maps coincide and ks is odd).
+ * W is fp32 [K,c_in,c_out] for LGS_F32, bf16 for LGS_BF16; out has the feature dtype; accumulation is fp32.
+ * --------------------------------------------------------------------------------------------------------- */
+int lgs_conv_fwd(const void* d_in, int64_t n_in, int32_t c_in,
+                 const void* d_weight, int32_t K, int32_t c_out,
+                 const int32_t* d_table, int64_t n_out, int32_t reverse_k,
+                 const float* d_bias, void* d_out, int32_t dtype, int32_t algo, void* stream);
+
+/* grad_w[k] = sum_o in[table[k][o], :]^T (outer) grad_out[o, :]   -> fp32 [K,c_in,c_out], overwritten. */
+int lgs_conv_wgrad(const void* d_in, int64_t n_in, int32_t c_in,
+                   const void* d_grad_out, int64_t n_out, int32_t c_out,
+                   const int32_t* d_table, int32_t K,
+                   float* d_grad_w, int32_t dtype, int32_t algo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * CLIP text-anchor loss.   Replaces lib/losses/ContrastiveLanguageLoss.py:224-237 (+ feat_dist :206-222) and
+ * lib/losses/utils.py:99-103 (feature_sim argmax), fused:
+ *   S = normalize(F) @ An^T  (An already L2-normalised, [a,c]);  loss_i = CE(S_i, y_i), 0 where y_i == ignore;
+ *   d_grad_feats[i] = d loss_i / d F_i;  d_pred[i] = argmax_j S_ij;  optional d_grad_logits [n,a] = softmax - onehot
+ *   (for the learned anchor projection, models/clip_models.py:197-200).  Any output pointer may be NULL.
+ * --------------------------------------------------------------------------------------------------------- */
+int lgs_clip_ce(const float* d_feats, int64_t n, int32_t c, const float* d_anchors_n, int32_t a,
+                const int64_t* d_labels, int64_t ignore_label,
+                float* d_loss, float* d_grad_feats, int32_t* d_pred, float* d_grad_logits, void* stream);
+
+/* Hinge variant (ContrastiveLanguageLoss.py:184-192, 'cos' distance :87-93): negatives' anchor ids are an input
+ * [n,n_neg] (the reference draws them on the host, :131-138).
+ *   pos_i = relu(1 - S[i,y_i] - pos_thresh);  neg_i = relu(neg_thresh - (1 - mean_j S[i,neg_ij]));  0 where ignored. */
+int lgs_clip_hinge(const float* d_feats, int64_t n, int32_t c, const float* d_anchors_n, int32_t a,
+                   const int64_t* d_labels, const int32_t* d_neg_ids, int32_t n_neg, int64_t ignore_label,
+                   float pos_thresh, float neg_thresh, float neg_weight,
+                   float* d_pos_loss, float* d_neg_loss, float* d_grad_feats, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Voxelisation.   Replaces lib/voxelizer.py:138-139 (float64 affine + floor); the de-duplication of :142
+ * (ME.utils.sparse_quantize) is lgs_coordmap_build with quant = 1 on the result.
+ *   d_coords[i] = (batch, floor(((x*M[j][0] + y*M[j][1]) + z*M[j][2]) + M[j][3]) for j = 0..2), float64, no FMA.
+ * h_M: 12 doubles (row-major 3x4) on the HOST.
+ * --------------------------------------------------------------------------------------------------------- */
+int lgs_voxelize_affine(const float* d_xyz, int64_t n, const double* h_M, int32_t batch, int32_t* d_coords,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGS_B200_H */

@@ -1,0 +1,70 @@
+"""ctypes binding of the C-ABI library (include/lgs_b200.h).  The product path has no CPU fallback:
+if the CUDA library is missing or a call fails this module raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liblgs_b200.so")
+
+OK, E_INVALID, E_CUDA, E_RANGE, E_HASH_FULL, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+F32, BF16 = 0, 1
+ALGO_SIMT, ALGO_TC = 0, 1
+
+_p, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+
+# name -> (restype, argtypes); mirrors include/lgs_b200.h one to one
+SIGNATURES = {
+    "lgs_version": (C.c_int, []),
+    "lgs_last_error": (C.c_char_p, []),
+    "lgs_launch_count": (C.c_uint64, []),
+    "lgs_has_tc": (C.c_int, []),
+    "lgs_coord_limit": (_i32, []),
+    "lgs_hash_capacity": (_i64, [_i64]),
+    "lgs_coordmap_scratch_elems": (_i64, [_i64]),
+    "lgs_coordmap_build": (C.c_int, [_p, _i64, _i32, _p, _p, _i64, _p, _p, _p, _p, _p, C.POINTER(_i64), _p]),
+    "lgs_kmap_build": (C.c_int, [_p, _i64, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p]),
+    "lgs_kmap_transpose": (C.c_int, [_p, _i32, _i64, _i64, _p, _p]),
+    "lgs_conv_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _p, _i64, _i32, _p, _p, _i32, _i32, _p]),
+    "lgs_conv_wgrad": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _p, _i32, _p, _i32, _i32, _p]),
+    "lgs_clip_ce": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _i64, _p, _p, _p, _p, _p]),
+    "lgs_clip_hinge": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _p, _i32, _i64, _f32, _f32, _f32, _p, _p, _p, _p]),
+    "lgs_voxelize_affine": (C.c_int, [_p, _i64, C.POINTER(C.c_double), _i32, _p, _p]),
+}
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"lgs_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load():
+    """Load liblgs_b200.so (built in-tree by csrc/build.py).  Raises if it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m languagegroundedsemseg_b200.csrc.build` "
+                "(or __graft_entry__.build()).  There is no CPU fallback for the engine.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise EngineError(rc, load().lgs_last_error().decode(errors="replace"))
+
+
+def ptr(t):
+    """Raw device pointer of a (contiguous) tensor, or NULL."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def launch_count():
+    return int(load().lgs_launch_count())

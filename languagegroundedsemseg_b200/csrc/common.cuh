@@ -1,0 +1,88 @@
+// Shared host/device helpers of the lgs_b200 engine (error slot, launch counter, key packing, cuckoo probes).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <cstdio>
+#include <cstdarg>
+
+#include "../../include/lgs_b200.h"
+
+namespace lgs {
+
+// ---- host-side plumbing ------------------------------------------------------------------------------
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define LGS_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return ::lgs::fail(LGS_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+// every kernel launch goes through here so lgs_launch_count() is the library's own claim
+#define LGS_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \
+  do {                                                                                              \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                     \
+    ::lgs::g_launches.fetch_add(1, std::memory_order_relaxed);                                      \
+    LGS_CUDA(cudaGetLastError());                                                                   \
+  } while (0)
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- coordinate keys ---------------------------------------------------------------------------------
+// 64-bit key: batch 10 bit | x 18 bit | y 18 bit | z 18 bit (two's complement fields).
+constexpr int kCoordBits = 18;
+constexpr int32_t kCoordLimit = (1 << (kCoordBits - 1)) - 64;  // margin so +-offset probes never wrap
+constexpr int32_t kBatchLimit = 1023;
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr int kNumHashes = 4;
+constexpr int kMaxEvictions = 256;
+
+__host__ __device__ __forceinline__ uint64_t pack_key(int32_t b, int32_t x, int32_t y, int32_t z) {
+  const uint64_t m = (1ull << kCoordBits) - 1;
+  return (uint64_t(uint32_t(b)) << (3 * kCoordBits)) | ((uint64_t(uint32_t(x)) & m) << (2 * kCoordBits)) |
+         ((uint64_t(uint32_t(y)) & m) << kCoordBits) | (uint64_t(uint32_t(z)) & m);
+}
+
+__host__ __device__ __forceinline__ bool key_in_range(int32_t b, int32_t x, int32_t y, int32_t z) {
+  return b >= 0 && b < kBatchLimit && x > -kCoordLimit && x < kCoordLimit && y > -kCoordLimit &&
+         y < kCoordLimit && z > -kCoordLimit && z < kCoordLimit;
+}
+
+// murmur3 finaliser over key ^ per-function seed
+__host__ __device__ __forceinline__ uint32_t hash_slot(uint64_t key, int j, uint32_t mask) {
+  const uint64_t seeds[kNumHashes] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull,
+                                      0xD6E8FEB86659FD93ull};
+  uint64_t h = key ^ seeds[j];
+  h ^= h >> 33;
+  h *= 0xff51afd7ed558ccdull;
+  h ^= h >> 33;
+  h *= 0xc4ceb9fe1a85ec53ull;
+  h ^= h >> 33;
+  return uint32_t(h) & mask;
+}
+
+// Slot holding `key`, or -1.  Probe order j = 0..3; an EMPTY first-choice slot proves absence (slots are never
+// emptied once filled and every key's first placement attempt is its j = 0 slot).
+__device__ __forceinline__ int32_t cuckoo_find(const uint64_t* __restrict__ keys, uint32_t mask, uint64_t key) {
+#pragma unroll
+  for (int j = 0; j < kNumHashes; ++j) {
+    const uint32_t s = hash_slot(key, j, mask);
+    const uint64_t k = __ldg(keys + s);
+    if (k == key) return int32_t(s);
+    if (j == 0 && k == kEmptyKey) return -1;
+  }
+  return -1;
+}
+
+}  // namespace lgs

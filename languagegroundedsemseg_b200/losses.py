@@ -1,0 +1,155 @@
+"""CLIP text-anchor losses through the fused CUDA kernels (include/lgs_b200.h: lgs_clip_ce / lgs_clip_hinge).
+
+Mirrors the reference classes' call signature — ``criterion(features, labels, anchor_feats)``:
+  ContrastiveLanguageCELoss   lib/losses/ContrastiveLanguageLoss.py:197-237
+  ContrastiveLanguageLoss     lib/losses/ContrastiveLanguageLoss.py:13-194 (hinge; 'cos' distance)
+  feature_sim (argmax preds)  lib/losses/utils.py:80-103
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _ClipCEFn(torch.autograd.Function):
+    """per-row loss; gradient w.r.t. features computed in the same launch; anchors' gradient (learned projection,
+    models/clip_models.py:197-200) through the optional [n,a] grad-logits output and one plain GEMM."""
+
+    @staticmethod
+    def forward(ctx, feats, anchors_n, labels, ignore_label):
+        lib = _lib.load()
+        feats = feats.float().contiguous()
+        anchors_n = anchors_n.float().contiguous()
+        labels = labels.long().contiguous()
+        n, c = feats.shape
+        a = anchors_n.shape[0]
+        loss = torch.empty(n, dtype=torch.float32, device=feats.device)
+        pred = torch.empty(n, dtype=torch.int32, device=feats.device)
+        need_f = ctx.needs_input_grad[0]
+        need_a = ctx.needs_input_grad[1]
+        gf = torch.empty_like(feats) if need_f else None
+        gl = torch.empty((n, a), dtype=torch.float32, device=feats.device) if need_a else None
+        _lib.check(lib.lgs_clip_ce(_lib.ptr(feats), n, c, _lib.ptr(anchors_n), a, _lib.ptr(labels), int(ignore_label),
+                                   _lib.ptr(loss), _lib.ptr(gf), _lib.ptr(pred), _lib.ptr(gl), _stream()))
+        ctx.save_for_backward(gf, gl, feats if need_a else None)
+        ctx.mark_non_differentiable(pred)
+        return loss, pred
+
+    @staticmethod
+    def backward(ctx, gloss, _gpred):
+        gf, gl, feats = ctx.saved_tensors
+        g_feats = gf * gloss[:, None] if gf is not None else None
+        g_anch = None
+        if gl is not None:
+            g_anch = (gl * gloss[:, None]).t() @ F.normalize(feats, p=2, dim=1)
+        return g_feats, g_anch, None, None
+
+
+def clip_ce(feats, labels, anchor_feats, ignore_label=-1):
+    """-> (per-point loss [n], argmax prediction [n]); anchors are L2-normalised here (tiny [a,c] op)."""
+    return _ClipCEFn.apply(feats, F.normalize(anchor_feats.float(), p=2, dim=1), labels, ignore_label)
+
+
+class ContrastiveLanguageCELoss(nn.Module):
+    def __init__(self, config=None, num_labels=200, reduction="mean", ignore_label=None):
+        super().__init__()
+        self.ignore_label = ignore_label if ignore_label is not None else getattr(config, "ignore_label", -1)
+        self.num_labels, self.reduction = num_labels, reduction
+        self.last_pred = None
+
+    def forward(self, features, labels, anchor_feats, preds=None):
+        if features.dim() != 2:
+            raise ValueError("`features` needs to be [n_points, feat_dim]")
+        loss, self.last_pred = clip_ce(features, labels, anchor_feats, self.ignore_label)
+        if self.reduction == "mean":   # nn.CrossEntropyLoss(ignore_index): mean over non-ignored points
+            loss = loss.sum() / (labels != self.ignore_label).sum().clamp(min=1)
+        elif self.reduction == "sum":
+            loss = loss.sum()
+        return loss, torch.zeros(1), loss   # same 3-tuple as the reference (:239)
+
+
+class _ClipHingeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, anchors_n, labels, neg_ids, ignore_label, pos_thresh, neg_thresh, neg_weight):
+        lib = _lib.load()
+        feats = feats.float().contiguous()
+        anchors_n = anchors_n.float().contiguous()
+        labels = labels.long().contiguous()
+        neg_ids = neg_ids.to(torch.int32).contiguous()
+        n, c = feats.shape
+        pos = torch.empty(n, dtype=torch.float32, device=feats.device)
+        neg = torch.empty_like(pos)
+        gf = torch.empty_like(feats) if ctx.needs_input_grad[0] else None
+        _lib.check(lib.lgs_clip_hinge(_lib.ptr(feats), n, c, _lib.ptr(anchors_n), anchors_n.shape[0], _lib.ptr(labels),
+                                      _lib.ptr(neg_ids), neg_ids.shape[1], int(ignore_label), float(pos_thresh),
+                                      float(neg_thresh), float(neg_weight), _lib.ptr(pos), _lib.ptr(neg),
+                                      _lib.ptr(gf), _stream()))
+        ctx.save_for_backward(gf, pos, neg)
+        ctx.neg_weight = float(neg_weight)
+        return pos, neg
+
+    @staticmethod
+    def backward(ctx, gpos, gneg):
+        # the kernel's gradient is d(pos + neg_weight*neg)/dF; callers combine the two outputs that way
+        gf, pos, neg = ctx.saved_tensors
+        if gf is None:
+            return (None,) * 8
+        # d pos/dF and d neg/dF are both folded into gf with weights (1, neg_weight); rescale by upstream grads
+        # when they are the uniform weights of the reference's reductions (mean / none).
+        w = gpos[:, None]
+        return gf * w, None, None, None, None, None, None, None
+
+
+class ContrastiveLanguageLoss(nn.Module):
+    """Hinge variant.  Negatives are drawn on the device (uniform over anchors != label, the reference's
+    clip_uniform_sampling branch :131-134) unless `neg_ids` is given."""
+
+    def __init__(self, config=None, num_labels=200, reduction="mean", ignore_label=None, num_negative_samples=3,
+                 pos_thresh=0.0, neg_thresh=0.6, neg_weight=1.0):
+        super().__init__()
+        g = lambda k, d: getattr(config, k, d) if config is not None else d
+        self.ignore_label = ignore_label if ignore_label is not None else g("ignore_label", -1)
+        self.num_labels, self.reduction = num_labels, reduction
+        self.num_negative_samples = g("num_negative_samples", num_negative_samples)
+        self.pos_thresh = g("contrast_pos_thresh", pos_thresh)
+        self.neg_thresh = g("contrast_neg_thresh", neg_thresh)
+        self.neg_weight = g("contrast_neg_weight", neg_weight)
+
+    def sample_negatives(self, labels, generator=None):
+        n, a = labels.shape[0], self.num_labels
+        r = torch.randint(0, a - 1, (n, self.num_negative_samples), device=labels.device, generator=generator)
+        y = labels.long().clamp(min=0)[:, None]
+        return (r + (r >= y).long()).to(torch.int32)   # uniform over {0..a-1} \ {y}
+
+    def forward(self, features, labels, anchor_feats, preds=None, neg_ids=None):
+        if features.dim() != 2:
+            raise ValueError("`features` needs to be [n_points, feat_dim]")
+        if anchor_feats.dim() == 3:
+            anchor_feats = anchor_feats[:, 0, :]
+        if neg_ids is None:
+            neg_ids = self.sample_negatives(labels)
+        an = F.normalize(anchor_feats.float(), p=2, dim=1)
+        pos, neg = _ClipHingeFn.apply(features, an, labels, neg_ids, self.ignore_label, self.pos_thresh,
+                                      self.neg_thresh, self.neg_weight)
+        if self.reduction == "mean":
+            # loss = pos.mean() + w*neg.mean(): route the whole gradient through `pos` (see _ClipHingeFn.backward)
+            loss = pos.mean() + (neg.detach() * self.neg_weight).mean()
+        else:
+            loss = pos + neg.detach() * self.neg_weight
+        return loss, pos, neg
+
+
+def feature_sim_argmax(feats, anchor_feats):
+    """argmax_c cos(F_i, A_c) (lib/losses/utils.py:99-103 + the argmax at pl_RepresentationTrainer.py:238-239)."""
+    n = feats.shape[0]
+    labels = torch.full((n,), -1, dtype=torch.long, device=feats.device)
+    with torch.no_grad():
+        _, pred = clip_ce(feats.detach(), labels, anchor_feats, -1)
+    return pred.long()

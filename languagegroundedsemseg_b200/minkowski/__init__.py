@@ -1,0 +1,583 @@
+"""Host-side mirror of the reference-facing interface: the Python names of package ``MinkowskiEngine`` that
+RozDavid/LanguageGroundedSemseg uses, backed by the lgs_b200 C-ABI CUDA engine.
+
+    import languagegroundedsemseg_b200 as lgs
+    lgs.install_as_minkowski()          # `import MinkowskiEngine as ME` in the reference now resolves here
+    import models                        # /root/reference/models, unchanged
+
+Reference call sites served (relative to /root/reference):
+  SparseTensor                      lib/train_test/pl_BaselineTrainer.py:300, pl_RepresentationTrainer.py:183
+  KernelGenerator, RegionType       models/modules/common.py:55-64, 192-193
+  MinkowskiConvolution(/Transpose)  models/modules/common.py:195-203, 228-236
+  MinkowskiBatchNorm (.bn)          models/modules/common.py:17-19, models/resnet.py:78-82
+  MinkowskiReLU, cat, +=            models/res16unet.py:5-6,194,237; models/modules/resnet_block.py:54
+  MinkowskiSyncBatchNorm            main.py:122-123
+  utils.sparse_quantize / collate   lib/voxelizer.py:142, lib/transforms.py:421
+
+All arithmetic runs in the CUDA library; there is no CPU path behind these names.
+"""
+from __future__ import annotations
+
+import collections
+import collections.abc
+import ctypes
+import sys
+import types
+from enum import Enum
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+# Python-3.12 compatibility for the 2021-era reference callers (models/modules/common.py:81, lib/voxelizer.py:53)
+for _n in ("Sequence", "Iterable"):
+    if not hasattr(collections, _n):
+        setattr(collections, _n, getattr(collections.abc, _n))
+
+# ----------------------------------------------------------------------------------------------------------
+# engine-wide settings
+# ----------------------------------------------------------------------------------------------------------
+_ALGO = {"simt": _lib.ALGO_SIMT, "tc": _lib.ALGO_TC}
+_state = {"algo": _lib.ALGO_TC}
+
+
+def set_conv_algo(name: str):
+    """'simt' = exact fp32 FMA kernels (parity anchor); 'tc' = tcgen05 tensor-core kernels (default)."""
+    _state["algo"] = _ALGO[name]
+
+
+def get_conv_algo() -> str:
+    return {v: k for k, v in _ALGO.items()}[_state["algo"]]
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _lib.F32
+    if t.dtype == torch.bfloat16:
+        return _lib.BF16
+    raise TypeError(f"engine features must be float32 or bfloat16, got {t.dtype}")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# enums / kernel generator
+# ----------------------------------------------------------------------------------------------------------
+class RegionType(Enum):
+    HYPER_CUBE = 0
+    HYPER_CROSS = 1
+    CUSTOM = 2
+
+
+def _as_list(v, D):
+    if isinstance(v, torch.Tensor):
+        v = v.tolist()
+    if isinstance(v, (list, tuple)):
+        if len(v) != D:
+            raise ValueError(f"expected {D} values, got {v}")
+        return [int(x) for x in v]
+    return [int(v)] * D
+
+
+def _uniform(v, what):
+    if any(x != v[0] for x in v):
+        raise NotImplementedError(f"anisotropic {what} {v} is outside the hot path (SURVEY.md App. B: all isotropic)")
+    return v[0]
+
+
+class KernelGenerator:
+    def __init__(self, kernel_size=-1, stride=1, dilation=1, is_transpose=False,
+                 region_type=RegionType.HYPER_CUBE, region_offsets=None, expand_coordinates=False,
+                 axis_types=None, dimension=-1):
+        if dimension != 3:
+            raise NotImplementedError("lgs_b200 implements D = 3 (all in-scope call sites)")
+        if region_type != RegionType.HYPER_CUBE:
+            raise NotImplementedError("lgs_b200 implements RegionType.HYPER_CUBE (SURVEY.md App. B)")
+        self.dimension = dimension
+        self.kernel_size = _as_list(kernel_size, dimension)
+        self.kernel_stride = _as_list(stride, dimension)
+        self.kernel_dilation = _as_list(dilation, dimension)
+        self.region_type, self.region_offsets, self.axis_types = region_type, region_offsets, axis_types
+        self.kernel_volume = int(np.prod(self.kernel_size))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# coordinate manager
+# ----------------------------------------------------------------------------------------------------------
+class CoordinateMapKey:
+    def __init__(self, tensor_stride, tag=""):
+        self.tensor_stride = tuple(int(t) for t in tensor_stride)
+        self.tag = tag
+
+    def get_tensor_stride(self):
+        return list(self.tensor_stride)
+
+    def __eq__(self, o):
+        return isinstance(o, CoordinateMapKey) and (self.tensor_stride, self.tag) == (o.tensor_stride, o.tag)
+
+    def __hash__(self):
+        return hash((self.tensor_stride, self.tag))
+
+    def __repr__(self):
+        return f"CoordinateMapKey(stride={list(self.tensor_stride)}, tag={self.tag!r})"
+
+
+class _CoordMap:
+    """One coordinate map: rows (device int32 [n,4]) + its cuckoo table.  All buffers are torch tensors."""
+    __slots__ = ("coords", "tkeys", "tvals", "n", "capacity")
+
+
+class KernelMap:
+    """Output-stationary neighbour tables of one (in map, out map, kernel) triple.
+    fwd_table [K, n_out] rows of the input map; bwd_table [K, n_in] rows of the output map (dgrad)."""
+    __slots__ = ("K", "n_in", "n_out", "fwd_table", "bwd_table", "bwd_reverse", "counts")
+
+
+def _build_coordmap(coords: torch.Tensor, quant: int, want_maps: bool):
+    lib = _lib.load()
+    n = coords.shape[0]
+    dev = coords.device
+    cap = lib.lgs_hash_capacity(n)
+    cm = _CoordMap()
+    for attempt in range(3):
+        cm.tkeys = torch.empty(cap, dtype=torch.int64, device=dev)
+        cm.tvals = torch.empty(cap, dtype=torch.int32, device=dev)
+        out_coords = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        uidx = torch.empty(n, dtype=torch.int32, device=dev) if want_maps else None
+        inv = torch.empty(n, dtype=torch.int32, device=dev) if want_maps else None
+        scratch = torch.empty(lib.lgs_coordmap_scratch_elems(n), dtype=torch.int32, device=dev)
+        d_n = torch.empty(1, dtype=torch.int32, device=dev)
+        h_n = ctypes.c_int64(0)
+        rc = lib.lgs_coordmap_build(_lib.ptr(coords), n, quant, _lib.ptr(cm.tkeys), _lib.ptr(cm.tvals), cap,
+                                    _lib.ptr(out_coords), _lib.ptr(uidx), _lib.ptr(inv), _lib.ptr(scratch),
+                                    _lib.ptr(d_n), ctypes.byref(h_n), _stream())
+        if rc == _lib.E_HASH_FULL and attempt < 2:
+            cap *= 2
+            continue
+        _lib.check(rc)
+        break
+    cm.n, cm.capacity = int(h_n.value), cap
+    cm.coords = out_coords[: cm.n]
+    if want_maps:
+        return cm, uidx[: cm.n], inv
+    return cm
+
+
+class CoordinateManager:
+    def __init__(self, D=3):
+        if D != 3:
+            raise NotImplementedError("lgs_b200 implements D = 3")
+        self.D = D
+        self._maps = {}
+        self._kmaps = {}
+
+    # -- coordinate maps --------------------------------------------------------------------------------
+    def insert_and_map(self, coords: torch.Tensor, tensor_stride=(1, 1, 1)):
+        key = CoordinateMapKey(tensor_stride)
+        cm, uidx, inv = _build_coordmap(coords, 1, True)
+        self._maps[key] = cm
+        return key, uidx, inv
+
+    def stride(self, key, stride):
+        s = _as_list(stride, self.D)
+        nkey = CoordinateMapKey([t * q for t, q in zip(key.tensor_stride, s)])
+        if nkey not in self._maps:
+            self._maps[nkey] = _build_coordmap(self._maps[key].coords, _uniform(list(nkey.tensor_stride), "stride"),
+                                               False)
+        return nkey
+
+    def key_with_stride(self, tensor_stride):
+        k = CoordinateMapKey(tensor_stride)
+        if k not in self._maps:
+            raise RuntimeError(f"no coordinate map with tensor stride {list(tensor_stride)} in this manager")
+        return k
+
+    def get_coordinates(self, key):
+        return self._maps[key].coords
+
+    def size(self, key):
+        return self._maps[key].n
+
+    # -- kernel maps ------------------------------------------------------------------------------------
+    def _table(self, in_key, out_key, ks, dil):
+        lib = _lib.load()
+        cin, cout = self._maps[in_key], self._maps[out_key]
+        K = ks ** 3
+        table = torch.empty((K, cout.n), dtype=torch.int32, device=cout.coords.device)
+        counts = torch.empty(K, dtype=torch.int32, device=cout.coords.device)
+        _lib.check(lib.lgs_kmap_build(_lib.ptr(cout.coords), cout.n, _lib.ptr(cin.tkeys), _lib.ptr(cin.tvals),
+                                      cin.capacity, ks, _uniform(list(in_key.tensor_stride), "tensor stride"), dil,
+                                      _lib.ptr(table), _lib.ptr(counts), _stream()))
+        return table, counts
+
+    def _transpose(self, table, n_in):
+        lib = _lib.load()
+        K, n_out = table.shape
+        tt = torch.empty((K, n_in), dtype=torch.int32, device=table.device)
+        _lib.check(lib.lgs_kmap_transpose(_lib.ptr(table), K, n_out, n_in, _lib.ptr(tt), _stream()))
+        return tt
+
+    def kernel_map(self, in_key, out_key, kernel_size, dilation, is_transpose=False) -> KernelMap:
+        ks, dil = _uniform(list(kernel_size), "kernel size"), _uniform(list(dilation), "dilation")
+        ck = (in_key, out_key, ks, dil, bool(is_transpose))
+        km = self._kmaps.get(ck)
+        if km is not None:
+            return km
+        km = KernelMap()
+        km.K = ks ** 3
+        if is_transpose:
+            # map of the forward conv fine(out_key) -> coarse(in_key) with (in, out) swapped (App. A.7)
+            down = self.kernel_map(out_key, in_key, kernel_size, dilation, False)
+            km.n_in, km.n_out = down.n_out, down.n_in
+            km.fwd_table, km.bwd_table, km.bwd_reverse, km.counts = down.bwd_table, down.fwd_table, False, down.counts
+        else:
+            km.n_in, km.n_out = self._maps[in_key].n, self._maps[out_key].n
+            km.fwd_table, km.counts = self._table(in_key, out_key, ks, dil)
+            if in_key == out_key and ks % 2 == 1:
+                # C_in[i] = C[o] + off_k  <=>  C[o] = C_in[i] + off_{K-1-k}: dgrad reads the same table mirrored
+                km.bwd_table, km.bwd_reverse = km.fwd_table, True
+            else:
+                km.bwd_table, km.bwd_reverse = self._transpose(km.fwd_table, km.n_in), False
+        self._kmaps[ck] = km
+        return km
+
+    def kernel_map_pairs(self, km: KernelMap):
+        """ME-style pair lists [(in_idx, out_idx)] per offset, derived from the table (for inspection / tests)."""
+        res = []
+        for k in range(km.K):
+            o = torch.nonzero(km.fwd_table[k] >= 0).squeeze(1)
+            res.append((km.fwd_table[k][o].long(), o))
+        return res
+
+
+# ----------------------------------------------------------------------------------------------------------
+# SparseTensor
+# ----------------------------------------------------------------------------------------------------------
+class SparseTensor:
+    def __init__(self, features, coordinates=None, coordinate_map_key=None, coordinate_manager=None,
+                 tensor_stride=1, device=None, **_ignored):
+        if coordinate_map_key is None:
+            if coordinates is None:
+                raise ValueError("SparseTensor needs coordinates or a coordinate_map_key")
+            dev = features.device if features.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            if device is not None:
+                dev = torch.device(device)
+            if dev.type != "cuda":
+                raise RuntimeError("lgs_b200 has no CPU path: SparseTensor needs a CUDA device")
+            c = torch.as_tensor(coordinates)
+            if c.is_floating_point():
+                c = torch.floor(c)
+            c = c.to(device=dev, dtype=torch.int32).contiguous()
+            features = features.to(dev)
+            mgr = coordinate_manager or CoordinateManager(D=c.shape[1] - 1)
+            key, uidx, inv = mgr.insert_and_map(c, _as_list(tensor_stride, c.shape[1] - 1))
+            if uidx.shape[0] != c.shape[0]:  # duplicates: one row per coordinate, first occurrence kept
+                features = features.index_select(0, uidx.long())
+            self.unique_index, self.inverse_mapping = uidx, inv
+            coordinate_map_key, coordinate_manager = key, mgr
+        self._F = features
+        self.coordinate_map_key = coordinate_map_key
+        self.coordinate_manager = coordinate_manager
+
+    @property
+    def F(self):
+        return self._F
+
+    feats = F
+
+    @property
+    def C(self):
+        return self.coordinate_manager.get_coordinates(self.coordinate_map_key)
+
+    coordinates = C
+
+    @property
+    def tensor_stride(self):
+        return list(self.coordinate_map_key.tensor_stride)
+
+    @property
+    def device(self):
+        return self._F.device
+
+    @property
+    def D(self):
+        return self.coordinate_manager.D
+
+    @property
+    def shape(self):
+        return self._F.shape
+
+    def __len__(self):
+        return self._F.shape[0]
+
+    def _same(self, o):
+        if o.coordinate_map_key != self.coordinate_map_key or o.coordinate_manager is not self.coordinate_manager:
+            raise RuntimeError("SparseTensor arithmetic needs identical coordinate_map_key")
+
+    def _like(self, F):
+        return SparseTensor(F, coordinate_map_key=self.coordinate_map_key, coordinate_manager=self.coordinate_manager)
+
+    def __add__(self, o):
+        self._same(o)
+        return self._like(self._F + o._F)
+
+    def __iadd__(self, o):  # models/modules/resnet_block.py:54
+        self._same(o)
+        self._F = self._F + o._F
+        return self
+
+
+def cat(*sts):
+    for s in sts[1:]:
+        sts[0]._same(s)
+    return sts[0]._like(torch.cat([s.F for s in sts], 1))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# convolution
+# ----------------------------------------------------------------------------------------------------------
+class _SparseConvFn(torch.autograd.Function):
+    """out = conv(feats, W) through the C ABI; backward = dgrad (same kernel, W^T, mirrored/transposed table) + wgrad."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, bias, km, algo):
+        lib = _lib.load()
+        feats = feats.contiguous()
+        w3 = weight.view(1, *weight.shape) if weight.dim() == 2 else weight
+        wk = w3.to(feats.dtype).contiguous()
+        K, c_in, c_out = wk.shape
+        n_in = feats.shape[0]
+        n_out = km.n_out if km is not None else n_in
+        out = torch.empty((n_out, c_out), dtype=feats.dtype, device=feats.device)
+        b32 = bias.detach().float().contiguous().view(-1) if bias is not None else None
+        _lib.check(lib.lgs_conv_fwd(_lib.ptr(feats), n_in, c_in, _lib.ptr(wk), K, c_out,
+                                    _lib.ptr(km.fwd_table) if km is not None else None, n_out, 0, _lib.ptr(b32),
+                                    _lib.ptr(out), _dtype_code(feats), algo, _stream()))
+        ctx.save_for_backward(feats, wk)
+        ctx.km, ctx.algo, ctx.w_shape, ctx.w_dtype, ctx.has_bias = km, algo, weight.shape, weight.dtype, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        feats, wk = ctx.saved_tensors
+        km, algo = ctx.km, ctx.algo
+        gout = gout.contiguous()
+        K, c_in, c_out = wk.shape
+        n_in, n_out = feats.shape[0], gout.shape[0]
+        dt = _dtype_code(feats)
+        gin = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            wt = wk.transpose(1, 2).contiguous()  # [K, c_out, c_in]
+            gin = torch.empty((n_in, c_in), dtype=feats.dtype, device=feats.device)
+            _lib.check(lib.lgs_conv_fwd(_lib.ptr(gout), n_out, c_out, _lib.ptr(wt), K, c_in,
+                                        _lib.ptr(km.bwd_table) if km is not None else None, n_in,
+                                        1 if (km is not None and km.bwd_reverse) else 0, None, _lib.ptr(gin), dt, algo,
+                                        _stream()))
+        if ctx.needs_input_grad[1]:
+            gw = torch.empty((K, c_in, c_out), dtype=torch.float32, device=feats.device)
+            _lib.check(lib.lgs_conv_wgrad(_lib.ptr(feats), n_in, c_in, _lib.ptr(gout), n_out, c_out,
+                                          _lib.ptr(km.fwd_table) if km is not None else None, K, _lib.ptr(gw), dt,
+                                          algo, _stream()))
+            gw = gw.view(ctx.w_shape).to(ctx.w_dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gout.float().sum(0, keepdim=True)
+        return gin, gw, gb, None, None
+
+
+def sparse_conv(feats, weight, bias, km, algo=None):
+    return _SparseConvFn.apply(feats, weight, bias, km, _state["algo"] if algo is None else algo)
+
+
+class MinkowskiNetwork(nn.Module):
+    def __init__(self, D):
+        super().__init__()
+        self.D = D
+
+
+class _ConvBase(nn.Module):
+    TRANSPOSE = False
+
+    def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False,
+                 kernel_generator=None, expand_coordinates=False, dimension=None):
+        super().__init__()
+        if dimension is None or dimension <= 0:
+            raise ValueError("dimension must be given")
+        if expand_coordinates:
+            raise NotImplementedError("expand_coordinates is outside the hot path")
+        if kernel_generator is None:
+            kernel_generator = KernelGenerator(kernel_size, stride, dilation, dimension=dimension)
+        self.kernel_generator = kernel_generator
+        self.in_channels, self.out_channels, self.dimension = in_channels, out_channels, dimension
+        self.use_mm = (not self.TRANSPOSE) and kernel_generator.kernel_volume == 1 and \
+            all(s == 1 for s in kernel_generator.kernel_stride)
+        K = kernel_generator.kernel_volume
+        # state-dict ABI of ME 0.5.4: kernel [K,Cin,Cout] ([Cin,Cout] for 1x1), bias [1,Cout]
+        self.kernel = nn.Parameter(torch.empty((in_channels, out_channels) if self.use_mm
+                                               else (K, in_channels, out_channels)))
+        self.bias = nn.Parameter(torch.empty(1, out_channels)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        with torch.no_grad():
+            K = self.kernel_generator.kernel_volume
+            n = (self.out_channels if self.TRANSPOSE else self.in_channels) * K
+            stdv = 1.0 / np.sqrt(n)
+            self.kernel.uniform_(-stdv, stdv)
+            if self.bias is not None:
+                self.bias.uniform_(-stdv, stdv)
+
+    def forward(self, x: SparseTensor):
+        mgr, kg = x.coordinate_manager, self.kernel_generator
+        in_key = x.coordinate_map_key
+        if self.use_mm:
+            return x._like(sparse_conv(x.F, self.kernel, self.bias, None))
+        if self.TRANSPOSE:
+            out_key = mgr.key_with_stride([t // s for t, s in zip(in_key.tensor_stride, kg.kernel_stride)])
+        else:
+            out_key = mgr.stride(in_key, kg.kernel_stride) if any(s > 1 for s in kg.kernel_stride) else in_key
+        km = mgr.kernel_map(in_key, out_key, kg.kernel_size, kg.kernel_dilation, self.TRANSPOSE)
+        out = sparse_conv(x.F, self.kernel, self.bias, km)
+        return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=mgr)
+
+    def extra_repr(self):
+        kg = self.kernel_generator
+        return (f"in={self.in_channels}, out={self.out_channels}, kernel_size={kg.kernel_size}, "
+                f"stride={kg.kernel_stride}, dilation={kg.kernel_dilation}")
+
+
+class MinkowskiConvolution(_ConvBase):
+    TRANSPOSE = False
+
+
+class MinkowskiConvolutionTranspose(_ConvBase):
+    TRANSPOSE = True
+
+
+# ----------------------------------------------------------------------------------------------------------
+# row-wise layers (ATen on .F; fusion into the conv epilogue is SURVEY.md §8f rank 1)
+# ----------------------------------------------------------------------------------------------------------
+class MinkowskiBatchNorm(nn.Module):
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
+        super().__init__()
+        self.bn = nn.BatchNorm1d(num_features, eps=eps, momentum=momentum, affine=affine,
+                                 track_running_stats=track_running_stats)
+
+    def forward(self, x: SparseTensor):
+        return x._like(self.bn(x.F))
+
+
+class MinkowskiSyncBatchNorm(MinkowskiBatchNorm):
+    @classmethod
+    def convert_sync_batchnorm(cls, module, process_group=None):  # main.py:122-123
+        for _, child in list(module.named_children()):
+            if isinstance(child, MinkowskiBatchNorm):
+                child.bn = nn.SyncBatchNorm.convert_sync_batchnorm(child.bn, process_group)
+            else:
+                cls.convert_sync_batchnorm(child, process_group)
+        return module
+
+
+class MinkowskiReLU(nn.Module):
+    def __init__(self, inplace=False):
+        super().__init__()
+        self.inplace = inplace
+
+    def forward(self, x: SparseTensor):
+        return x._like(torch.relu(x.F))
+
+
+def _stub(name):
+    class _S(nn.Module):
+        def __init__(self, *a, **k):
+            raise NotImplementedError(f"{name}: outside the hot path (SURVEY.md §8b, import-surface row)")
+    _S.__name__ = _S.__qualname__ = name
+    return _S
+
+
+for _n in ("MinkowskiInstanceNorm", "MinkowskiSumPooling", "MinkowskiAvgPooling", "MinkowskiAvgUnpooling",
+           "MinkowskiPoolingTranspose", "MinkowskiGlobalPooling", "MinkowskiBroadcastAddition",
+           "MinkowskiBroadcastMultiplication", "MinkowskiLinear", "MinkowskiSigmoid", "MinkowskiMaxPooling",
+           "MinkowskiGlobalMaxPooling", "MinkowskiDropout", "MinkowskiBroadcast", "MinkowskiConvolutionFunction"):
+    globals()[_n] = _stub(_n)
+
+
+def convert_to_int_tensor(arg, dimension):
+    return torch.IntTensor(_as_list(arg, dimension))
+
+
+def convert_region_type(*a, **k):
+    raise NotImplementedError("ME 0.4-era API, outside the hot path")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# utils
+# ----------------------------------------------------------------------------------------------------------
+def sparse_quantize(coordinates, features=None, labels=None, ignore_label=-100, return_index=False,
+                    return_inverse=False, quantization_size=None, device=None, **_):
+    """First-occurrence voxel de-duplication on the GPU (lib/voxelizer.py:142).  numpy in -> numpy out."""
+    if labels is not None:
+        raise NotImplementedError("label-voting mode of sparse_quantize is not used by the reference path")
+    is_np = isinstance(coordinates, np.ndarray)
+    c = torch.as_tensor(coordinates)
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    c = c.to(dev)
+    if quantization_size is not None:
+        c = c / quantization_size
+    if c.is_floating_point():
+        c = torch.floor(c)
+    c4 = torch.cat([torch.zeros((c.shape[0], 1), dtype=torch.int32, device=dev), c.to(torch.int32)], 1).contiguous()
+    cm, uidx, inv = _build_coordmap(c4, 1, True)
+    conv = (lambda t: t.cpu().numpy()) if is_np else (lambda t: t.to(torch.as_tensor(coordinates).device))
+    ret = [conv(cm.coords[:, 1:])]
+    if features is not None:
+        ret.append(features[conv(uidx.long())])
+    if return_index:
+        ret.append(conv(uidx.long()))
+    if return_inverse:
+        ret.append(conv(inv.long()))
+    return ret[0] if len(ret) == 1 else tuple(ret)
+
+
+def batched_coordinates(coords_list, dtype=torch.int32, device=None):
+    out = []
+    for b, c in enumerate(coords_list):
+        c = torch.as_tensor(c)
+        if c.is_floating_point():
+            c = torch.floor(c)
+        out.append(torch.cat([torch.full((c.shape[0], 1), b, dtype=dtype), c.to(dtype)], 1))
+    r = torch.cat(out, 0)
+    return r.to(device) if device is not None else r
+
+
+def sparse_collate(coords, feats, labels=None, dtype=torch.int32, device=None):
+    """(int32 [sum N, 1+D] with the batch column prepended, cat(feats), cat(labels))  (lib/transforms.py:421)."""
+    bc = batched_coordinates(coords, dtype, device)
+    f = torch.cat([torch.as_tensor(x) for x in feats], 0)
+    if labels is None:
+        return bc, f
+    return bc, f, torch.cat([torch.as_tensor(x) for x in labels], 0)
+
+
+utils = types.ModuleType(__name__ + ".utils")
+utils.sparse_quantize = sparse_quantize
+utils.sparse_collate = sparse_collate
+utils.batched_coordinates = batched_coordinates
+
+MinkowskiOps = types.ModuleType(__name__ + ".MinkowskiOps")
+MinkowskiOps.cat = cat
+
+__version__ = "0.5.4+lgs_b200"
+
+
+def install(name="MinkowskiEngine"):
+    """Register this facade under the package name the reference imports."""
+    me = sys.modules[__name__]
+    sys.modules[name] = me
+    sys.modules[name + ".MinkowskiOps"] = MinkowskiOps
+    sys.modules[name + ".utils"] = utils
+    return me
