@@ -303,7 +303,7 @@ int lgs_coordmap_build(const int32_t* d_coords, int64_t n, int32_t quant, uint64
     return fail(LGS_E_INVALID, "lgs_coordmap_build: n=%lld quant=%d capacity=%lld (need pow2 >= 2n)", (long long)n,
                 quant, (long long)capacity);
   if (n > (int64_t(1) << 30)) return fail(LGS_E_INVALID, "lgs_coordmap_build: n too large (max 2^30 rows)");
-  if (!d_table_keys || !d_table_vals || !d_out_coords || !d_scratch || !d_n_unique || (n && !d_coords))
+  if (!d_table_keys || !d_table_vals || !d_scratch || !d_n_unique || (n && (!d_coords || !d_out_coords)))
     return fail(LGS_E_INVALID, "lgs_coordmap_build: null pointer");
   LGS_CUDA(cudaMemsetAsync(d_table_keys, 0xFF, size_t(capacity) * 8, stream));
   LGS_CUDA(cudaMemsetAsync(d_table_vals, 0x7F, size_t(capacity) * 4, stream));

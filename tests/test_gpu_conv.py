@@ -1,0 +1,158 @@
+"""-m gpu: sparse convolution forward / dgrad / wgrad of the CUDA engine vs the oracle (same seeded inputs).
+Tolerances: LGS_ALGO_SIMT is fp32 FMA -> 2e-5 relative (summation order only);
+            LGS_ALGO_TC uses TF32 tensor cores -> 2e-3 relative per layer (north_star's 1e-3 is on whole-net logits,
+            checked in test_gpu_nets.py)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import random_sparse_coords, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"simt": 2e-5, "tc": 2e-3}
+
+
+@pytest.fixture(scope="module")
+def E(lib):
+    from languagegroundedsemseg_b200 import minkowski
+    return minkowski
+
+
+def _run_pair(E, algo, c, cin, cout, ks, stride, transpose, bias, seed, pre=None):
+    """build identical layers on both engines, run fwd + bwd with a random upstream gradient"""
+    from oracle import me_cpu
+    E.set_conv_algo(algo)
+    torch.manual_seed(seed)
+    res = {}
+    f0 = torch.randn(c.shape[0], pre or cin)
+    for name, eng, dev in (("oracle", me_cpu, "cpu"), ("cuda", E, "cuda")):
+        torch.manual_seed(seed + 1)
+        cls = eng.MinkowskiConvolutionTranspose if transpose else eng.MinkowskiConvolution
+        layers = []
+        if transpose or pre:
+            # go down first so the transposed conv has an encoder map to land on
+            layers.append(eng.MinkowskiConvolution(pre or cin, cin, kernel_size=2, stride=2, dimension=3))
+        layers.append(cls(cin, cout, kernel_size=ks, stride=stride, bias=bias, dimension=3))
+        net = torch.nn.Sequential(*layers).to(dev)
+        f = f0.clone().to(dev).requires_grad_(True)
+        x = eng.SparseTensor(f, torch.from_numpy(c).to(dev))
+        y = net(x)
+        torch.manual_seed(seed + 2)
+        gy = torch.randn(y.F.shape)
+        y.F.backward(gy.to(dev))
+        res[name] = dict(out=y.F.detach().cpu(), gin=f.grad.cpu(), gw=layers[-1].kernel.grad.cpu(),
+                         gb=layers[-1].bias.grad.cpu() if bias else None, C=y.C.cpu())
+    return res
+
+
+CASES = [
+    # cin, cout, ks, stride, transpose, bias
+    (3, 32, 3, 1, False, False),      # conv0p1s1
+    (32, 32, 3, 1, False, False),
+    (32, 64, 3, 1, False, False),
+    (128, 96, 3, 1, False, False),    # block8 first conv
+    (96, 96, 3, 1, False, False),
+    (256, 256, 3, 1, False, False),
+    (32, 32, 2, 2, False, False),     # conv1p1s2
+    (96, 96, 2, 2, True, False),      # convtr7p2s2
+    (256, 128, 2, 2, True, False),
+    (96, 200, 1, 1, False, True),     # final
+    (128, 96, 1, 1, False, False),    # block downsample branch
+    (5, 7, 3, 1, False, True),        # ragged channel counts
+]
+
+
+@pytest.mark.parametrize("algo", ["simt", "tc"])
+@pytest.mark.parametrize("cin,cout,ks,stride,transpose,bias", CASES)
+def test_conv_layer_parity(E, algo, cin, cout, ks, stride, transpose, bias):
+    rng = np.random.default_rng(cin * 1000 + cout)
+    c = random_sparse_coords(rng, 6000, extent=28, batches=2)
+    r = _run_pair(E, algo, c, cin, cout, ks, stride, transpose, bias, seed=cin + cout)
+    o, g = r["oracle"], r["cuda"]
+    assert torch.equal(o["C"], g["C"])
+    tol = TOL[algo]
+    assert rel_err(g["out"], o["out"]) < tol
+    assert rel_err(g["gin"], o["gin"]) < tol
+    assert rel_err(g["gw"], o["gw"]) < tol
+    if bias:
+        assert rel_err(g["gb"], o["gb"]) < tol
+
+
+@pytest.mark.parametrize("algo", ["simt", "tc"])
+def test_conv_kats(E, algo):
+    """closed-form answers through the CUDA path"""
+    from tests.helpers import dense_cube
+    E.set_conv_algo(algo)
+    n = 6
+    c = dense_cube(n)
+    x = E.SparseTensor(torch.ones(n ** 3, 16).cuda(), torch.from_numpy(c).cuda())
+    conv = E.MinkowskiConvolution(16, 16, kernel_size=3, dimension=3).cuda()
+    with torch.no_grad():
+        conv.kernel.fill_(1.0 / 16)
+        out = conv(x).F[:, 0].cpu().numpy()
+    border = ((c[:, 1:] == 0) | (c[:, 1:] == n - 1)).sum(1)
+    assert np.allclose(out, np.array([27, 18, 12, 8])[border], rtol=1e-5)
+    # centre identity and one-hot offsets
+    rng = np.random.default_rng(1)
+    c = random_sparse_coords(rng, 900, extent=10, batches=1)
+    f = torch.randn(c.shape[0], 16)
+    f = (f * 64).round() / 64      # exactly representable in tf32/bf16 so the KAT is exact on every path
+    x = E.SparseTensor(f.cuda(), torch.from_numpy(c).cuda())
+    lut = {tuple(r): i for i, r in enumerate(c)}
+    for k in (13, 0, 5, 14, 26):
+        with torch.no_grad():
+            conv.kernel.zero_()
+            conv.kernel[k] = torch.eye(16)
+            out = conv(x).F.cpu()
+        off = np.array([k % 3 - 1, (k // 3) % 3 - 1, k // 9 - 1])
+        exp = torch.zeros_like(f)
+        for o in range(c.shape[0]):
+            q = c[o].copy()
+            q[1:] += off
+            i = lut.get(tuple(q))
+            if i is not None:
+                exp[o] = f[i]
+        assert torch.equal(out, exp), k
+
+
+@pytest.mark.parametrize("algo", ["simt", "tc"])
+def test_linearity_full_size(E, algo):
+    """size-independent property at BASELINE config-2 size: conv(a*x + y) == a*conv(x) + conv(y)"""
+    from languagegroundedsemseg_b200 import scenes
+    E.set_conv_algo(algo)
+    c, _, _ = scenes.synthetic_voxel_scene(0, 150000)
+    torch.manual_seed(0)
+    a, b = torch.randn(c.shape[0], 96).cuda(), torch.randn(c.shape[0], 96).cuda()
+    conv = E.MinkowskiConvolution(96, 96, kernel_size=3, dimension=3).cuda()
+    cc = torch.from_numpy(c).cuda()
+    with torch.no_grad():
+        xa = E.SparseTensor(a, cc)
+        mgr = xa.coordinate_manager
+        mk = lambda f: E.SparseTensor(f, coordinate_map_key=xa.coordinate_map_key, coordinate_manager=mgr)
+        ya, yb, yab = conv(xa).F, conv(mk(b)).F, conv(mk(2 * a + b)).F
+    assert rel_err(yab, 2 * ya + yb) < (1e-5 if algo == "simt" else 3e-3)
+    # isolated-voxel property: rows with no neighbours other than themselves equal F @ W[13]
+    t = mgr.kernel_map(xa.coordinate_map_key, xa.coordinate_map_key, [3, 3, 3], [1, 1, 1]).fwd_table
+    iso = torch.nonzero((t >= 0).sum(0) == 1).squeeze(1)
+    if iso.numel():
+        assert rel_err(ya[iso], a[iso] @ conv.kernel[13]) < TOL[algo]
+
+
+def test_bf16_features(E):
+    from oracle import me_cpu
+    rng = np.random.default_rng(9)
+    c = random_sparse_coords(rng, 5000, extent=24, batches=1)
+    torch.manual_seed(3)
+    f = torch.randn(c.shape[0], 64)
+    w = torch.randn(27, 64, 96) * 0.05
+    x = me_cpu.SparseTensor(f.bfloat16().float(), torch.from_numpy(c))
+    km = x.coordinate_manager.kernel_map(x.coordinate_map_key, x.coordinate_map_key, [3, 3, 3], [1, 1, 1])
+    ref = me_cpu.sparse_conv(x.F, w.bfloat16().float(), km, c.shape[0])
+    for algo in ("simt", "tc"):
+        E.set_conv_algo(algo)
+        g = E.SparseTensor(f.cuda().bfloat16(), torch.from_numpy(c).cuda())
+        gk = g.coordinate_manager.kernel_map(g.coordinate_map_key, g.coordinate_map_key, [3, 3, 3], [1, 1, 1])
+        out = E.sparse_conv(g.F, w.cuda(), None, gk)
+        assert out.dtype == torch.bfloat16
+        assert rel_err(out.float().cpu(), ref) < 1e-2     # one bf16 rounding of the output
