@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — active voxels/sec of Res16UNet34C forward+backward (BASELINE.json metric, config 2) on N x B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--algo tc|simt] [--dtype f32|bf16]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N
+
+A step = one pass of the hot path over one batch: SparseTensor construction (cuckoo coordinate-map build),
+lazy build of the 4 strided maps + 9 kernel maps, Res16UNet34C forward, CrossEntropy(ignore -1), backward,
+SGD step.  One synthetic ScanNet-shaped scene (~150 K voxels @ 2 cm) per GPU; the only collective is DDP's NCCL
+gradient all-reduce (weak scaling).
+  value  = voxels of all ranks / step time, inputs resident in HBM.
+  e2e    = same step through the reference-facing API with pinned HOST inputs (H2D inside) and loss.item() (D2H).
+  roofline = conv fwd/dgrad kernel: SURVEY.md §8(d) per-offset HBM-gather bytes / CUDA-event time of its launches.
+  cpu_baseline = the CPU oracle (restatement of MinkowskiEngine's CPU algorithm) on this box's host cores.
+--impl reference times that CPU restatement alone (MinkowskiEngine itself is not installable here).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "active voxels/sec Res16UNet34C fwd+bwd"
+UNIT = "voxels/s"
+MODEL = "Res16UNet34C"
+TARGET_VOXELS = 150_000
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_scene(seed, target=TARGET_VOXELS, voxel_size=0.02):
+    from languagegroundedsemseg_b200 import scenes
+    return scenes.synthetic_voxel_scene(seed=seed, target_voxels=target, voxel_size=voxel_size)
+
+
+def build_net(engine, device, dtype):
+    from languagegroundedsemseg_b200 import nets
+    torch.manual_seed(42)
+    net = nets.build_model(MODEL, 3, 200, nets.DefaultConfig(), engine=engine).to(device).train()
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, dampening=0.1, weight_decay=1e-4)  # lib/solvers.py:58-63
+    return net, opt
+
+
+def train_step(ST, net, opt, coords, feats, labels):
+    st = ST(feats, coords)                                   # pl_BaselineTrainer.py:300
+    out, _ = net(st)                                         # res16unet.py:196
+    loss = torch.nn.functional.cross_entropy(out.F.float(), labels, ignore_index=-1)   # :350
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    opt.step()
+    return loss
+
+
+# ------------------------------------------------------------------------------------------------------------
+# work model: per conv launch with P pairs, K offsets, element size s
+# ------------------------------------------------------------------------------------------------------------
+def launch_work(meta, pair_cache):
+    kind, K, c_in, c_out, n_in, n_out, km, dtype = meta
+    s = 2 if dtype == torch.bfloat16 else 4
+    if km is None:
+        P = n_out
+        idx = 0
+    else:
+        if id(km) not in pair_cache:
+            pair_cache[id(km)] = int(km.counts.sum().item())
+        P = pair_cache[id(km)]
+        idx = 8 * P
+    flops = 2.0 * P * c_in * c_out
+    if kind == "wgrad":
+        byts = P * (c_in + c_out) * s + idx + K * c_in * c_out * 4
+    else:
+        byts = P * (c_in + c_out) * s + idx + K * c_in * c_out * s
+    return flops, byts, P
+
+
+def run_engine(args, rank, world, local_rank):
+    from languagegroundedsemseg_b200 import _lib, minkowski as E
+    from languagegroundedsemseg_b200.csrc import build as _build
+    if rank == 0:
+        _build.build()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    _lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    E.set_conv_algo(args.algo)
+    fdtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+
+    coords_np, feats_np, labels_np = make_scene(seed=rank)
+    n_vox = coords_np.shape[0]
+    # host (pinned) copies for the e2e leg; device-resident copies for `value`
+    h_coords = torch.from_numpy(coords_np).pin_memory()
+    h_feats = torch.from_numpy(feats_np).pin_memory()
+    h_labels = torch.from_numpy(labels_np).pin_memory()
+    d_coords, d_feats, d_labels = h_coords.to(dev), h_feats.to(dev).to(fdtype), h_labels.to(dev)
+
+    net, opt = build_net(None, dev, fdtype)
+    if args.dtype == "bf16":
+        # bf16 features; parameters stay fp32 (master weights), BN in fp32 statistics via autocast-free mixed dtype
+        pass
+    model = net
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        model = DDP(net, device_ids=[local_rank], find_unused_parameters=False, gradient_as_bucket_view=True)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step():
+        flush.fill_(0.0)
+        return train_step(E.SparseTensor, model, opt, d_coords, d_feats, d_labels)
+
+    def e2e_step():
+        flush.fill_(0.0)
+        c = h_coords.to(dev, non_blocking=True)
+        f = h_feats.to(dev, non_blocking=True).to(fdtype)
+        lab = h_labels.to(dev, non_blocking=True)
+        return train_step(E.SparseTensor, model, opt, c, f, lab).item()
+
+    for _ in range(args.warmup):
+        resident_step()
+    barrier()
+
+    # ---- timed region: `value` --------------------------------------------------------------------------
+    E.profile_begin()
+    l0 = _lib.launch_count()
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            loss = resident_step()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - l0
+    prof = E.profile_end()
+    loss_val = float(loss.item())
+
+    # ---- e2e leg -----------------------------------------------------------------------------------------
+    e2e_step()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+
+    # ---- kernel-map build time (coordinate map + 4 strided maps + 9 kernel maps of one scene) -------------
+    def build_maps():
+        st = E.SparseTensor(d_feats[:, :1], d_coords)
+        m, k = st.coordinate_manager, st.coordinate_map_key
+        for lvl in range(5):
+            m.kernel_map(k, k, [3, 3, 3], [1, 1, 1])
+            if lvl < 4:
+                k2 = m.stride(k, 2)
+                m.kernel_map(k, k2, [2, 2, 2], [1, 1, 1])
+                k = k2
+        return m
+    build_maps()
+    torch.cuda.synchronize()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record()
+    for _ in range(5):
+        build_maps()
+    m1.record()
+    torch.cuda.synchronize()
+    kmap_ms = m0.elapsed_time(m1) / 5
+
+    # ---- reduce over ranks ---------------------------------------------------------------------------------
+    tot_vox = n_vox
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms, ms_e2e, kmap_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, kmap_ms = t.tolist()
+        v = torch.tensor([n_vox], device=dev, dtype=torch.float64)
+        dist.all_reduce(v)
+        tot_vox = int(v.item())
+    if rank != 0:
+        return None
+
+    # ---- roofline of the dominant kernel (conv fwd/dgrad launches) ----------------------------------------
+    hbm_gbs, tf_peak, peak_src = load_peaks()
+    pair_cache = {}
+    agg = {}
+    for meta, (a, b) in prof:
+        fl, by, _ = launch_work(meta, pair_cache)
+        kname = "wgrad" if meta[0] == "wgrad" else "conv"
+        d = agg.setdefault(kname, [0.0, 0.0, 0.0, 0])
+        d[0] += a.elapsed_time(b)
+        d[1] += by
+        d[2] += fl
+        d[3] += 1
+    step_flops = sum(v[2] for v in agg.values()) / args.steps
+    step_bytes = sum(v[1] for v in agg.values()) / args.steps
+    conv_ms, conv_bytes, conv_flops, conv_n = agg["conv"]
+    achieved = conv_bytes / (conv_ms * 1e-3) / 1e9
+    wg = agg.get("wgrad", [0, 0, 0, 0])
+    roofline = {"bound": "hbm", "kernel": "conv fwd/dgrad (output-stationary gather-GEMM)", "achieved": round(achieved, 1),
+                "peak": hbm_gbs, "unit": "GB/s", "frac": round(achieved / hbm_gbs, 4), "traffic": None,
+                "peak_source": peak_src, "launches": conv_n, "avg_launch_ms": round(conv_ms / conv_n, 4),
+                "share_of_step": round(conv_ms / ms, 3),
+                "tflops": round(conv_flops / (conv_ms * 1e-3) / 1e12, 2),
+                "wgrad": {"share_of_step": round(wg[0] / ms, 3), "achieved_gbs": round(wg[1] / max(wg[0], 1e-9) / 1e6, 1),
+                          "tflops": round(wg[2] / max(wg[0], 1e-9) / 1e9, 2)},
+                "step_model": {"gflop": round(step_flops / 1e9, 1), "gbyte": round(step_bytes / 1e9, 2),
+                               "hbm_floor_ms": round(step_bytes / hbm_gbs / 1e6, 3)}}
+
+    value = tot_vox * args.steps / (ms * 1e-3)
+    e2e_value = tot_vox * args.steps / (ms_e2e * 1e-3)
+    h2d = h_coords.numel() * 4 + h_feats.numel() * 4 + h_labels.numel() * 8
+    res = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if args.dtype == "f32" else "bf16", "data": "synthetic",
+        "config": {"workload": f"{MODEL} fwd+bwd+SGD, 1 synthetic ScanNet-shaped scene/GPU, {n_vox} voxels @2cm, 200 classes "
+                               "(BASELINE configs[1])", "voxels_per_gpu": n_vox, "algo": args.algo,
+                   "math": ("tf32 tensor cores, fp32 accumulate" if args.algo == "tc" else "fp32 FMA") if args.dtype == "f32"
+                   else "bf16 tensor cores, fp32 accumulate",
+                   "l2": "256 MB buffer written between steps (L2 flush); per-step activations >> 126 MB L2",
+                   "parallelism": f"dp{world}", "step": "coordinate+kernel maps, fwd, CE loss, bwd, SGD"},
+        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": int(launches),
+        "kernel_map_build_ms": round(kmap_ms, 3),
+        "roofline": roofline,
+        "clocks": clk.summary(),
+        "loss": round(loss_val, 5),
+    }
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of MinkowskiEngine's CPU algorithm) on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_arm(steps, warmup, sample_voxels, seed=0):
+    from oracle import me_cpu
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    coords, feats, labels = make_scene(seed=seed, target=sample_voxels)
+    net, opt = build_net(me_cpu, "cpu", torch.float32)
+    c, f, lab = torch.from_numpy(coords), torch.from_numpy(feats), torch.from_numpy(labels)
+    for _ in range(warmup):
+        train_step(me_cpu.SparseTensor, net, opt, c, f, lab)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        train_step(me_cpu.SparseTensor, net, opt, c, f, lab)
+    dt = time.perf_counter() - t0
+    n = coords.shape[0]
+    return {"value": round(n * steps / dt, 1), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{MODEL} fwd+bwd+SGD on a {n}-voxel scene from the same generator, {steps} step(s) after "
+                      f"{warmup} warm-up; ME-CPU-algorithm restatement (torch index_select->mm->index_add_, "
+                      f"{cores} threads)",
+            "seconds": round(dt, 2)}, n, dt
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--algo", default="tc", choices=["tc", "simt"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--cpu-sample-voxels", type=int, default=60_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, min(args.steps, 3))
+        cb, n, dt = cpu_arm(steps, min(args.warmup, 1), args.cpu_sample_voxels)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt / steps * 1e3, 1),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{MODEL} fwd+bwd+SGD; CPU restatement of MinkowskiEngine 0.5.4's CPU algorithm "
+                                       f"(the reference's own ME is not installable here) on a bounded {n}-voxel sample",
+                           "cpu": cpu_model_name()},
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    res = run_engine(args, rank, world, local_rank)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _, _ = cpu_arm(1, 0, args.cpu_sample_voxels)
+            cb["cpu"] = cpu_model_name()
+            res["cpu_baseline"] = cb
+        print(json.dumps(res), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

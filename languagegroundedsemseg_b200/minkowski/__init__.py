@@ -40,7 +40,38 @@ for _n in ("Sequence", "Iterable"):
 # engine-wide settings
 # ----------------------------------------------------------------------------------------------------------
 _ALGO = {"simt": _lib.ALGO_SIMT, "tc": _lib.ALGO_TC}
-_state = {"algo": _lib.ALGO_TC}
+_state = {"algo": _lib.ALGO_TC, "profile": None}
+
+
+def profile_begin():
+    """Start recording one (kind, shape, kernel map, start/end CUDA events) entry per engine convolution launch —
+    bench.py's live per-kernel timing.  Events are recorded on the launching stream."""
+    _state["profile"] = []
+
+
+def profile_end():
+    rec, _state["profile"] = _state["profile"], None
+    return rec
+
+
+class _Timed:
+    """context manager: CUDA events around one C-ABI launch when profiling is on"""
+    __slots__ = ("meta", "ev")
+
+    def __init__(self, kind, K, c_in, c_out, n_in, n_out, km, dtype):
+        self.meta = (kind, K, c_in, c_out, n_in, n_out, km, dtype)
+
+    def __enter__(self):
+        if _state["profile"] is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *a):
+        if _state["profile"] is not None:
+            self.ev[1].record()
+            _state["profile"].append((self.meta, self.ev))
+        return False
 
 
 def set_conv_algo(name: str):
@@ -354,9 +385,10 @@ class _SparseConvFn(torch.autograd.Function):
         n_out = km.n_out if km is not None else n_in
         out = torch.empty((n_out, c_out), dtype=feats.dtype, device=feats.device)
         b32 = bias.detach().float().contiguous().view(-1) if bias is not None else None
-        _lib.check(lib.lgs_conv_fwd(_lib.ptr(feats), n_in, c_in, _lib.ptr(wk), K, c_out,
-                                    _lib.ptr(km.fwd_table) if km is not None else None, n_out, 0, _lib.ptr(b32),
-                                    _lib.ptr(out), _dtype_code(feats), algo, _stream()))
+        with _Timed("fwd", K, c_in, c_out, n_in, n_out, km, feats.dtype):
+            _lib.check(lib.lgs_conv_fwd(_lib.ptr(feats), n_in, c_in, _lib.ptr(wk), K, c_out,
+                                        _lib.ptr(km.fwd_table) if km is not None else None, n_out, 0, _lib.ptr(b32),
+                                        _lib.ptr(out), _dtype_code(feats), algo, _stream()))
         ctx.save_for_backward(feats, wk)
         ctx.km, ctx.algo, ctx.w_shape, ctx.w_dtype, ctx.has_bias = km, algo, weight.shape, weight.dtype, bias is not None
         return out
@@ -374,15 +406,17 @@ class _SparseConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wt = wk.transpose(1, 2).contiguous()  # [K, c_out, c_in]
             gin = torch.empty((n_in, c_in), dtype=feats.dtype, device=feats.device)
-            _lib.check(lib.lgs_conv_fwd(_lib.ptr(gout), n_out, c_out, _lib.ptr(wt), K, c_in,
-                                        _lib.ptr(km.bwd_table) if km is not None else None, n_in,
-                                        1 if (km is not None and km.bwd_reverse) else 0, None, _lib.ptr(gin), dt, algo,
-                                        _stream()))
+            with _Timed("dgrad", K, c_out, c_in, n_out, n_in, km, feats.dtype):
+                _lib.check(lib.lgs_conv_fwd(_lib.ptr(gout), n_out, c_out, _lib.ptr(wt), K, c_in,
+                                            _lib.ptr(km.bwd_table) if km is not None else None, n_in,
+                                            1 if (km is not None and km.bwd_reverse) else 0, None, _lib.ptr(gin), dt,
+                                            algo, _stream()))
         if ctx.needs_input_grad[1]:
             gw = torch.empty((K, c_in, c_out), dtype=torch.float32, device=feats.device)
-            _lib.check(lib.lgs_conv_wgrad(_lib.ptr(feats), n_in, c_in, _lib.ptr(gout), n_out, c_out,
-                                          _lib.ptr(km.fwd_table) if km is not None else None, K, _lib.ptr(gw), dt,
-                                          algo, _stream()))
+            with _Timed("wgrad", K, c_in, c_out, n_in, n_out, km, feats.dtype):
+                _lib.check(lib.lgs_conv_wgrad(_lib.ptr(feats), n_in, c_in, _lib.ptr(gout), n_out, c_out,
+                                              _lib.ptr(km.fwd_table) if km is not None else None, K, _lib.ptr(gw), dt,
+                                              algo, _stream()))
             gw = gw.view(ctx.w_shape).to(ctx.w_dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gout.float().sum(0, keepdim=True)
