@@ -37,6 +37,9 @@ extern "C" {
 /* conv algorithms */
 #define LGS_ALGO_SIMT 0  /* fp32 FMA, exact: the parity anchor */
 #define LGS_ALGO_TC 1    /* tcgen05 tensor cores, TMEM accumulators (TF32 for LGS_F32 features, BF16 for LGS_BF16) */
+/* weight layouts */
+#define LGS_W_KCN 0      /* [K, c_in, c_out]: MinkowskiEngine's parameter layout */
+#define LGS_W_KNC 1      /* [K, c_out, c_in]: per-offset transpose (the K-major B operand the tensor-core path loads by TMA) */
 
 int lgs_version(void);
 const char* lgs_last_error(void);
@@ -93,12 +96,15 @@ int lgs_kmap_transpose(const int32_t* d_table, int32_t K, int64_t n_out, int64_t
  *   call sites: models/modules/common.py:195-203, 228-236; autograd backward of the same.
  *   out[o,:] = sum_k in[table[kk][o], :] @ W[k]  (+ bias),   kk = reverse_k ? K-1-k : k
  * d_table == NULL means the identity map with K == 1 (1x1x1 convs, models/resnet.py:95-101, res16unet.py:193).
- * dgrad is the same call with (in := grad_out, W := W^T per offset [K,c_out,c_in], table := transposed table,
- * or the same table with reverse_k = 1 when in and out maps coincide and ks is odd).
- * W is fp32 [K,c_in,c_out] for LGS_F32, bf16 for LGS_BF16; out has the feature dtype; accumulation is fp32.
+ * dgrad is the same call on the transposed problem: in := grad_out, the SAME weight buffer read as LGS_W_KNC
+ * (W[k] is [c_in,c_out] = [c_out',c_in']), table := transposed table, or the same table with reverse_k = 1 when the
+ * in and out maps coincide and ks is odd.
+ * W has the feature dtype (fp32 for LGS_F32, bf16 for LGS_BF16); out too; accumulation is fp32.
+ * LGS_ALGO_SIMT reads either layout.  LGS_ALGO_TC needs LGS_W_KNC, 16-byte-multiple feature rows and c_out % 4 == 0;
+ * any other request is served by the SIMT kernel (still on the GPU; there is no CPU path).
  * --------------------------------------------------------------------------------------------------------- */
 int lgs_conv_fwd(const void* d_in, int64_t n_in, int32_t c_in,
-                 const void* d_weight, int32_t K, int32_t c_out,
+                 const void* d_weight, int32_t weight_layout, int32_t K, int32_t c_out,
                  const int32_t* d_table, int64_t n_out, int32_t reverse_k,
                  const float* d_bias, void* d_out, int32_t dtype, int32_t algo, void* stream);
 

@@ -2,8 +2,9 @@
 #include "common.cuh"
 
 namespace lgs {
-int conv_fwd_simt(const void* in, int64_t n_in, int c_in, const void* w, int K, int c_out, const int32_t* table,
-                  int64_t n_out, int reverse_k, const float* bias, void* out, int dtype, cudaStream_t stream);
+int conv_fwd_simt(const void* in, int64_t n_in, int c_in, const void* w, int w_layout, int K, int c_out,
+                  const int32_t* table, int64_t n_out, int reverse_k, const float* bias, void* out, int dtype,
+                  cudaStream_t stream);
 int conv_wgrad_simt(const void* in, int c_in, const void* gout, int64_t n_out, int c_out, const int32_t* table, int K,
                     float* gw, int dtype, cudaStream_t stream);
 // tcgen05 path (conv_tc.cu): returns LGS_E_UNSUPPORTED when the shape is outside what it was built for
@@ -20,7 +21,8 @@ extern "C" {
 
 int lgs_has_tc(void) { return tc_built() ? 1 : 0; }
 
-int lgs_conv_fwd(const void* d_in, int64_t n_in, int32_t c_in, const void* d_weight, int32_t K, int32_t c_out,
+int lgs_conv_fwd(const void* d_in, int64_t n_in, int32_t c_in, const void* d_weight, int32_t weight_layout, int32_t K,
+                 int32_t c_out,
                  const int32_t* d_table, int64_t n_out, int32_t reverse_k, const float* d_bias, void* d_out,
                  int32_t dtype, int32_t algo, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -30,16 +32,21 @@ int lgs_conv_fwd(const void* d_in, int64_t n_in, int32_t c_in, const void* d_wei
   if (!d_table && (K != 1 || n_in != n_out))
     return fail(LGS_E_INVALID, "lgs_conv_fwd: NULL table needs K == 1 and n_in == n_out");
   if (dtype != LGS_F32 && dtype != LGS_BF16) return fail(LGS_E_INVALID, "lgs_conv_fwd: dtype %d", dtype);
+  if (weight_layout != LGS_W_KCN && weight_layout != LGS_W_KNC)
+    return fail(LGS_E_INVALID, "lgs_conv_fwd: weight_layout %d", weight_layout);
   if ((n_out && (!d_in && n_in)) || !d_weight || (n_out && !d_out)) return fail(LGS_E_INVALID, "lgs_conv_fwd: null pointer");
   if (algo == LGS_ALGO_TC) {
-    const int rc = conv_fwd_tc(d_in, n_in, c_in, d_weight, K, c_out, d_table, n_out, reverse_k, d_bias, d_out, dtype,
-                               stream);
+    const int rc = weight_layout == LGS_W_KNC
+                       ? conv_fwd_tc(d_in, n_in, c_in, d_weight, K, c_out, d_table, n_out, reverse_k, d_bias, d_out,
+                                     dtype, stream)
+                       : LGS_E_UNSUPPORTED;
     if (rc != LGS_E_UNSUPPORTED) return rc;
     // shape outside the tensor-core kernel's envelope (e.g. c_in = 3): the SIMT kernel takes it
   } else if (algo != LGS_ALGO_SIMT) {
     return fail(LGS_E_INVALID, "lgs_conv_fwd: algo %d", algo);
   }
-  return conv_fwd_simt(d_in, n_in, c_in, d_weight, K, c_out, d_table, n_out, reverse_k, d_bias, d_out, dtype, stream);
+  return conv_fwd_simt(d_in, n_in, c_in, d_weight, weight_layout, K, c_out, d_table, n_out, reverse_k, d_bias, d_out,
+                       dtype, stream);
 }
 
 int lgs_conv_wgrad(const void* d_in, int64_t n_in, int32_t c_in, const void* d_grad_out, int64_t n_out, int32_t c_out,

@@ -49,7 +49,7 @@ __device__ __forceinline__ float4 load4(const T* __restrict__ p, int valid, bool
   return r;
 }
 
-template <typename T>
+template <typename T, bool W_KNC>
 __global__ void __launch_bounds__(256)
 conv_simt_kernel(const T* __restrict__ in, int c_in, const T* __restrict__ w, int K, int c_out,
                  const int32_t* __restrict__ table, int64_t n_out, int reverse_k, const float* __restrict__ bias,
@@ -88,14 +88,25 @@ conv_simt_kernel(const T* __restrict__ in, int c_in, const T* __restrict__ w, in
       const int ca = c0 + a_chunk * 4;
       const float4 av = (r >= 0) ? load4<T>(in + size_t(r) * c_in + ca, c_in - ca, vec_in)
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-      const int cb = c0 + b_kk, nb = n0 + b_n4 * 4;
-      const float4 bv = (cb < c_in) ? load4<T>(wk + size_t(cb) * c_out + nb, c_out - nb, vec_w)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
       As[a_chunk * 4 + 0][a_row] = av.x;
       As[a_chunk * 4 + 1][a_row] = av.y;
       As[a_chunk * 4 + 2][a_row] = av.z;
       As[a_chunk * 4 + 3][a_row] = av.w;
-      *reinterpret_cast<float4*>(&Bs[b_kk][b_n4 * 4]) = bv;
+      if constexpr (W_KNC) {
+        // weights stored [K, c_out, c_in]: same access pattern as the A loader (row = output channel)
+        const int n = n0 + a_row;
+        const float4 bv = (n < c_out) ? load4<T>(wk + size_t(n) * c_in + ca, c_in - ca, vec_in)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        Bs[a_chunk * 4 + 0][a_row] = bv.x;
+        Bs[a_chunk * 4 + 1][a_row] = bv.y;
+        Bs[a_chunk * 4 + 2][a_row] = bv.z;
+        Bs[a_chunk * 4 + 3][a_row] = bv.w;
+      } else {
+        const int cb = c0 + b_kk, nb = n0 + b_n4 * 4;
+        const float4 bv = (cb < c_in) ? load4<T>(wk + size_t(cb) * c_out + nb, c_out - nb, vec_w)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(&Bs[b_kk][b_n4 * 4]) = bv;
+      }
       __syncthreads();
 #pragma unroll
       for (int kk = 0; kk < BK; ++kk) {
@@ -185,20 +196,29 @@ wgrad_simt_kernel(const T* __restrict__ in, int c_in, const T* __restrict__ gout
   }
 }
 
-int conv_fwd_simt(const void* in, int64_t n_in, int c_in, const void* w, int K, int c_out, const int32_t* table,
-                  int64_t n_out, int reverse_k, const float* bias, void* out, int dtype, cudaStream_t stream) {
-  (void)n_in;
-  if (n_out == 0) return LGS_OK;
+template <typename T>
+static int launch_conv_simt(const void* in, int c_in, const void* w, int w_layout, int K, int c_out,
+                            const int32_t* table, int64_t n_out, int reverse_k, const float* bias, void* out,
+                            cudaStream_t stream) {
   dim3 grid(unsigned(cdiv(n_out, BM)), unsigned(cdiv(c_out, BN)));
-  if (dtype == LGS_F32) {
-    LGS_LAUNCH(conv_simt_kernel<float>, grid, 256, 0, stream, static_cast<const float*>(in), c_in,
-               static_cast<const float*>(w), K, c_out, table, n_out, reverse_k, bias, static_cast<float*>(out));
+  if (w_layout == LGS_W_KNC) {
+    LGS_LAUNCH((conv_simt_kernel<T, true>), grid, 256, 0, stream, static_cast<const T*>(in), c_in,
+               static_cast<const T*>(w), K, c_out, table, n_out, reverse_k, bias, static_cast<T*>(out));
   } else {
-    LGS_LAUNCH(conv_simt_kernel<__nv_bfloat16>, grid, 256, 0, stream, static_cast<const __nv_bfloat16*>(in), c_in,
-               static_cast<const __nv_bfloat16*>(w), K, c_out, table, n_out, reverse_k, bias,
-               static_cast<__nv_bfloat16*>(out));
+    LGS_LAUNCH((conv_simt_kernel<T, false>), grid, 256, 0, stream, static_cast<const T*>(in), c_in,
+               static_cast<const T*>(w), K, c_out, table, n_out, reverse_k, bias, static_cast<T*>(out));
   }
   return LGS_OK;
+}
+
+int conv_fwd_simt(const void* in, int64_t n_in, int c_in, const void* w, int w_layout, int K, int c_out,
+                  const int32_t* table, int64_t n_out, int reverse_k, const float* bias, void* out, int dtype,
+                  cudaStream_t stream) {
+  (void)n_in;
+  if (n_out == 0) return LGS_OK;
+  if (dtype == LGS_F32)
+    return launch_conv_simt<float>(in, c_in, w, w_layout, K, c_out, table, n_out, reverse_k, bias, out, stream);
+  return launch_conv_simt<__nv_bfloat16>(in, c_in, w, w_layout, K, c_out, table, n_out, reverse_k, bias, out, stream);
 }
 
 int conv_wgrad_simt(const void* in, int c_in, const void* gout, int64_t n_out, int c_out, const int32_t* table, int K,

@@ -1,9 +1,451 @@
-// tcgen05 path — placeholder until the tensor-core kernel lands (returns UNSUPPORTED so the SIMT kernel runs).
+// LGS_ALGO_TC: output-stationary sparse convolution on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// One CTA owns a tile of 128 output rows and up to 256 output channels.  For every kernel offset k that has at least
+// one neighbour in the tile, and every 128-byte block of input channels:
+//   * 4 producer warps gather the neighbour rows  in[table[k][o]]  with 16-byte cp.async (zero-fill for missing
+//     neighbours) straight into a 128B-swizzled K-major shared-memory tile  A[128 rows][128 B];
+//   * one thread TMA-loads the matching weight block  W^T[k][n][128 B]  (K-major, 128B swizzle) — the B operand;
+//   * one thread issues tcgen05.mma (M=128, N=c_out, K=32 B per instruction) accumulating into TMEM over ALL offsets
+//     and channel blocks, so the [128 x c_out] fp32 accumulator never leaves the SM until the tile is done;
+//   * the producer warps then drain TMEM (tcgen05.ld) and store each output row once — no atomics, deterministic.
+// The stages form an mbarrier ring (full: 128 producer arrivals + TMA transaction bytes; empty: tcgen05.commit).
+//
+// Math modes: fp32 features -> kind::tf32 (operands are read as TF32, fp32 accumulate); bf16 features -> kind::f16.
+// Shapes outside the envelope (row bytes not a multiple of 16, e.g. c_in = 3) return LGS_E_UNSUPPORTED and the caller
+// falls back to the exact SIMT kernel.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+
 #include "common.cuh"
+
 namespace lgs {
-bool tc_built() { return false; }
-int conv_fwd_tc(const void*, int64_t, int, const void*, int, int, const int32_t*, int64_t, int, const float*, void*,
-                int, cudaStream_t) { return LGS_E_UNSUPPORTED; }
+
+namespace tc {
+
+constexpr int BM = 128;          // output rows per CTA (UMMA M)
+constexpr int THREADS = 192;     // warps 0-3: gather producers + epilogue; warp 4: MMA issuer; warp 5: weight TMA
+constexpr int KBLOCK_BYTES = 128;
+constexpr int A_STAGE_BYTES = BM * KBLOCK_BYTES;  // 16 KB
+constexpr int LAG = 3;           // cp.async groups a producer thread keeps in flight
+constexpr int MAX_STAGES = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100): rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= uint64_t((saddr >> 4) & 0x3FFF);        // start address  [0,14)
+  d |= uint64_t(1) << 16;                       // LBO (unused for swizzled K-major) [16,30)
+  d |= uint64_t(1024 >> 4) << 32;               // SBO = 1024 B  [32,46)
+  d |= uint64_t(1) << 46;                       // descriptor version (Blackwell) [46,48)
+  d |= uint64_t(2) << 61;                       // layout type SWIZZLE_128B [61,64)
+  return d;
+}
+
+template <bool BF16>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (BF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Params {
+  const uint8_t* in;        // [n_in, c_in] features (fp32 or bf16)
+  int64_t n_in;
+  int32_t row_bytes;        // c_in * elem size
+  int32_t K;
+  int32_t c_out;            // total output channels
+  const int32_t* table;     // [K, n_out] or nullptr (identity, K == 1)
+  int64_t n_out;
+  int32_t reverse_k;
+  const float* bias;
+  void* out;                // [n_out, c_out]
+  int32_t num_kb;           // 128-byte channel blocks per offset
+  int32_t n_tile;           // MMA N of one CTA (multiple of 16, <= 256)
+  int32_t stages;
+  int32_t tmem_cols;
+  int32_t b_stage_bytes;    // n_tile * 128
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A 16 KB | B n_tile*128)] [idx K*128 int32] [klist 32] [barriers] [tmem ptr]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
+  int32_t* sidx = reinterpret_cast<int32_t*>(smem + size_t(p.stages) * stage_bytes);
+  int32_t* klist = sidx + p.K * BM;
+  int32_t* kflag = klist + 32;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(kflag + 32);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* acc_bar = empty_bar + MAX_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  int32_t* nk_smem = reinterpret_cast<int32_t*>(tmem_ptr_smem + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = int64_t(blockIdx.x) * BM;
+  const int n0 = blockIdx.y * 256;
+
+  // ---- prologue -----------------------------------------------------------------------------------------
+  for (int e = tid; e < p.K * BM; e += THREADS) {
+    const int k = e / BM, r = e - k * BM;
+    const int64_t o = m0 + r;
+    int32_t v = -1;
+    if (o < p.n_out) v = p.table ? __ldg(p.table + int64_t(p.reverse_k ? p.K - 1 - k : k) * p.n_out + o) : int32_t(o);
+    sidx[e] = v;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar + s, 128 + 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(uint32_t(p.tmem_cols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 5 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+  }
+  __syncthreads();
+  // which offsets have any neighbour in this tile
+  for (int k = warp; k < p.K; k += THREADS / 32) {
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < BM / 32; ++j) any |= sidx[k * BM + lane + 32 * j] >= 0;
+    const uint32_t b = __ballot_sync(0xffffffffu, any);
+    if (lane == 0) kflag[k] = b != 0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    int nk = 0;
+    for (int k = 0; k < p.K; ++k)
+      if (kflag[k]) klist[nk++] = k;
+    *nk_smem = nk;
+  }
+  __syncthreads();
+  const int nk = *nk_smem;
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int total = nk * p.num_kb;
+
+  if (warp < 4) {
+    // =================================== gather producers ===================================
+    const int chunk = tid & 7, rbase = tid >> 3;  // 8 lanes cover one 128-byte row segment; 16 rows per pass
+    int it = 0;
+    for (int a = 0; a < nk; ++a) {
+      const int k = klist[a];
+      const int32_t* idx = sidx + k * BM;
+      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        const uint32_t a_base = smem_u32(smem + size_t(s) * stage_bytes);
+        const int col = kb * KBLOCK_BYTES + chunk * 16;
+        const bool col_ok = col < p.row_bytes;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = rbase + 16 * i;
+          const int32_t src_row = idx[r];
+          const bool ok = col_ok && src_row >= 0;
+          const uint8_t* src = ok ? p.in + size_t(src_row) * p.row_bytes + col : p.in;
+          cp_async16(a_base + r * KBLOCK_BYTES + ((chunk ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        if (it >= LAG) {
+          cp_async_wait<LAG>();
+          fence_proxy_async();
+          mbar_arrive(full_bar + (it - LAG) % p.stages);
+        }
+      }
+    }
+    // drain the last LAG groups
+    if (total > 2) { cp_async_wait<2>(); fence_proxy_async(); mbar_arrive(full_bar + (total - 3) % p.stages); }
+    if (total > 1) { cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(full_bar + (total - 2) % p.stages); }
+    if (total > 0) { cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(full_bar + (total - 1) % p.stages); }
+
+    // =================================== epilogue ===================================
+    if (total > 0) {
+      mbar_wait(acc_bar, 0);
+      tc_fence_after();
+    }
+    const int64_t o = m0 + warp * 32 + lane;
+    const int ncols = min(p.n_tile, p.c_out - n0);
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+      uint32_t v[32];
+      if (total > 0) {
+        tmem_ld32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(c0), v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (o < p.n_out) {
+        if constexpr (BF16) {
+          __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out) + size_t(o) * p.c_out + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            if (c0 + j + 1 < ncols) {
+              const float x0 = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
+              const float x1 = __uint_as_float(v[j + 1]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 1) : 0.f);
+              *reinterpret_cast<__nv_bfloat162*>(orow + j) = __floats2bfloat162_rn(x0, x1);
+            } else if (c0 + j < ncols) {
+              orow[j] = __float2bfloat16(__uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f));
+            }
+          }
+        } else {
+          float* orow = static_cast<float*>(p.out) + size_t(o) * p.c_out + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (c0 + j + 3 < ncols) {
+              float4 x;
+              x.x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
+              x.y = __uint_as_float(v[j + 1]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 1) : 0.f);
+              x.z = __uint_as_float(v[j + 2]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 2) : 0.f);
+              x.w = __uint_as_float(v[j + 3]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 3) : 0.f);
+              *reinterpret_cast<float4*>(orow + j) = x;
+            } else {
+              for (int jj = j; jj < j + 4; ++jj)
+                if (c0 + jj < ncols) orow[jj] = __uint_as_float(v[jj]) + (p.bias ? __ldg(p.bias + n0 + c0 + jj) : 0.f);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // =================================== MMA issuer (one thread) ===================================
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B tf32 (or bf16), both K-major, N = n_tile, M = 128
+      const uint32_t fmt = BF16 ? 1u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(p.n_tile >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+      int it = 0;
+      for (int a = 0; a < nk; ++a) {
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(full_bar + s, ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + size_t(s) * stage_bytes);
+          const uint32_t b_base = a_base + A_STAGE_BYTES;
+          const int valid = min(KBLOCK_BYTES, p.row_bytes - kb * KBLOCK_BYTES);
+          const int ksteps = (valid + 31) / 32;  // 32 bytes of K per instruction (8 tf32 / 16 bf16)
+          for (int j = 0; j < ksteps; ++j) {
+            umma<BF16>(tmem_base, make_kmajor_sw128_desc(a_base + j * 32), make_kmajor_sw128_desc(b_base + j * 32), idesc,
+                       (it > 0 || j > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + s);  // frees the stage once these MMAs have read it
+        }
+      }
+      if (total > 0) umma_commit(acc_bar);
+    }
+    __syncwarp();
+  } else {
+    // =================================== weight TMA producer (one thread) ===================================
+    if (lane == 0) {
+      const int kelems = KBLOCK_BYTES / (BF16 ? 2 : 4);
+      int it = 0;
+      for (int a = 0; a < nk; ++a) {
+        const int k = klist[a];
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          mbar_expect_tx(full_bar + s, uint32_t(p.b_stage_bytes));
+          tma_load_2d(smem_u32(smem + size_t(s) * stage_bytes + A_STAGE_BYTES), &tmap_w, full_bar + s, kb * kelems,
+                      k * p.c_out + n0);
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(p.tmem_cols))
+                 : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+}  // namespace tc
+
+bool tc_built() { return true; }
+
+// Weights arrive K-major for this path: d_weight_nk = [K, c_out, c_in] (c_in contiguous).
+int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K, int c_out, const int32_t* table,
+                int64_t n_out, int reverse_k, const float* bias, void* out, int dtype, cudaStream_t stream) {
+  using namespace tc;
+  const int es = dtype == LGS_BF16 ? 2 : 4;
+  const int row_bytes = c_in * es;
+  if (row_bytes % 16 != 0 || row_bytes < 16) return LGS_E_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(w_nk) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 15))
+    return LGS_E_UNSUPPORTED;
+  if (dtype == LGS_BF16 ? (c_out % 2 != 0) : (c_out % 4 != 0)) return LGS_E_UNSUPPORTED;  // vector stores
+  if (int64_t(K) * c_out >= (int64_t(1) << 31)) return LGS_E_UNSUPPORTED;
+  if (n_out == 0) return LGS_OK;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return fail(LGS_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+
+  Params p;
+  p.in = static_cast<const uint8_t*>(in);
+  p.n_in = n_in;
+  p.row_bytes = row_bytes;
+  p.K = K;
+  p.c_out = c_out;
+  p.table = table;
+  p.n_out = n_out;
+  p.reverse_k = reverse_k;
+  p.bias = bias;
+  p.out = out;
+  p.num_kb = (row_bytes + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
+  const int n_tiles = (c_out + 255) / 256;
+  const int c_pad = ((c_out + 15) / 16) * 16;
+  p.n_tile = n_tiles == 1 ? c_pad : 256;
+  if (n_tiles > 1 && c_out % 256 != 0) {
+    // keep every N tile the same width: only multiples of 256 beyond 256 channels
+    return LGS_E_UNSUPPORTED;
+  }
+  p.b_stage_bytes = p.n_tile * KBLOCK_BYTES;
+  int cols = 32;
+  while (cols < p.n_tile) cols <<= 1;
+  p.tmem_cols = cols;
+  const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
+  const int fixed = K * BM * 4 + 64 * 4 + (2 * MAX_STAGES + 1) * 8 + 16 + 1024;  // idx + klist/kflag + barriers + align
+  int stages = (100 * 1024 - fixed) / stage_bytes;            // try to leave room for two CTAs per SM
+  if (stages < LAG + 1) stages = (227 * 1024 - fixed) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < LAG + 1) return LGS_E_UNSUPPORTED;
+  p.stages = stages;
+  const size_t smem_bytes = size_t(stages) * stage_bytes + fixed;
+
+  // tensor map over W^T viewed as [K * c_out rows, c_in] with box {128 B of channels, n_tile rows}, 128B swizzle
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {cuuint64_t(c_in), cuuint64_t(K) * cuuint64_t(c_out)};
+  const cuuint64_t gstride[1] = {cuuint64_t(row_bytes)};
+  const cuuint32_t box[2] = {cuuint32_t(KBLOCK_BYTES / es), cuuint32_t(p.n_tile)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult cr = encode(&tmap, dtype == LGS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                             2, const_cast<void*>(w_nk), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(LGS_E_CUDA, "cuTensorMapEncodeTiled failed (%d) c_in=%d c_out=%d K=%d", int(cr), c_in, c_out, K);
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) return fail(LGS_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+
+  dim3 grid(unsigned(cdiv(n_out, BM)), unsigned(n_tiles));
+  if (dtype == LGS_BF16) {
+    LGS_LAUNCH(conv_tc_kernel<true>, grid, THREADS, smem_bytes, stream, tmap, p);
+  } else {
+    LGS_LAUNCH(conv_tc_kernel<false>, grid, THREADS, smem_bytes, stream, tmap, p);
+  }
+  return LGS_OK;
+}
+
 int conv_wgrad_tc(const void*, int64_t, int, const void*, int64_t, int, const int32_t*, int, float*, int,
-                  cudaStream_t) { return LGS_E_UNSUPPORTED; }
+                  cudaStream_t) {
+  return LGS_E_UNSUPPORTED;
+}
+
 }  // namespace lgs

@@ -379,14 +379,18 @@ class _SparseConvFn(torch.autograd.Function):
         lib = _lib.load()
         feats = feats.contiguous()
         w3 = weight.view(1, *weight.shape) if weight.dim() == 2 else weight
-        wk = w3.to(feats.dtype).contiguous()
+        wk = w3.detach().to(feats.dtype).contiguous()            # [K, c_in, c_out]  (LGS_W_KCN)
         K, c_in, c_out = wk.shape
         n_in = feats.shape[0]
         n_out = km.n_out if km is not None else n_in
         out = torch.empty((n_out, c_out), dtype=feats.dtype, device=feats.device)
         b32 = bias.detach().float().contiguous().view(-1) if bias is not None else None
+        if algo == _lib.ALGO_TC:
+            w_fwd, layout = wk.transpose(1, 2).contiguous(), _lib.W_KNC   # K-major B operand for the TMA/tcgen05 path
+        else:
+            w_fwd, layout = wk, _lib.W_KCN
         with _Timed("fwd", K, c_in, c_out, n_in, n_out, km, feats.dtype):
-            _lib.check(lib.lgs_conv_fwd(_lib.ptr(feats), n_in, c_in, _lib.ptr(wk), K, c_out,
+            _lib.check(lib.lgs_conv_fwd(_lib.ptr(feats), n_in, c_in, _lib.ptr(w_fwd), layout, K, c_out,
                                         _lib.ptr(km.fwd_table) if km is not None else None, n_out, 0, _lib.ptr(b32),
                                         _lib.ptr(out), _dtype_code(feats), algo, _stream()))
         ctx.save_for_backward(feats, wk)
@@ -404,10 +408,10 @@ class _SparseConvFn(torch.autograd.Function):
         dt = _dtype_code(feats)
         gin = gw = gb = None
         if ctx.needs_input_grad[0]:
-            wt = wk.transpose(1, 2).contiguous()  # [K, c_out, c_in]
+            # dgrad = the same kernel on the transposed problem; W[k] ([c_in,c_out]) read as LGS_W_KNC needs no copy
             gin = torch.empty((n_in, c_in), dtype=feats.dtype, device=feats.device)
             with _Timed("dgrad", K, c_out, c_in, n_out, n_in, km, feats.dtype):
-                _lib.check(lib.lgs_conv_fwd(_lib.ptr(gout), n_out, c_out, _lib.ptr(wt), K, c_in,
+                _lib.check(lib.lgs_conv_fwd(_lib.ptr(gout), n_out, c_out, _lib.ptr(wk), _lib.W_KNC, K, c_in,
                                             _lib.ptr(km.bwd_table) if km is not None else None, n_in,
                                             1 if (km is not None and km.bwd_reverse) else 0, None, _lib.ptr(gin), dt,
                                             algo, _stream()))

@@ -35,7 +35,7 @@ def test_host_only_entry_points(lib):
 
 def test_argument_validation_without_gpu(lib):
     # invalid arguments are rejected before any CUDA call
-    rc = lib.lgs_conv_fwd(None, 10, 0, None, 27, 8, None, 10, 0, None, None, 0, 0, None)
+    rc = lib.lgs_conv_fwd(None, 10, 0, None, 0, 27, 8, None, 10, 0, None, None, 0, 0, None)
     assert rc == _lib.E_INVALID and b"lgs_conv_fwd" in lib.lgs_last_error()
     rc = lib.lgs_kmap_build(None, 10, None, None, 1024, 5, 1, 1, None, None, None)
     assert rc == _lib.E_INVALID
