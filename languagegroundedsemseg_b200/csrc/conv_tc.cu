@@ -8,7 +8,8 @@
 //   * one thread issues tcgen05.mma (M=128, N=c_out, K=32 B per instruction) accumulating into TMEM over ALL offsets
 //     and channel blocks, so the [128 x c_out] fp32 accumulator never leaves the SM until the tile is done;
 //   * the producer warps then drain TMEM (tcgen05.ld) and store each output row once — no atomics, deterministic.
-// The stages form an mbarrier ring (full: 128 producer arrivals + TMA transaction bytes; empty: tcgen05.commit).
+// The stages form an mbarrier ring (full: 128 cp.async-completion arrivals + TMA transaction bytes; empty:
+// tcgen05.commit).
 //
 // Math modes: fp32 features -> kind::tf32 (operands are read as TF32, fp32 accumulate); bf16 features -> kind::f16.
 // Shapes outside the envelope (row bytes not a multiple of 16, e.g. c_in = 3) return LGS_E_UNSUPPORTED and the caller
@@ -28,7 +29,7 @@ constexpr int BM = 128;          // output rows per CTA (UMMA M)
 constexpr int THREADS = 192;     // warps 0-3: gather producers + epilogue; warp 4: MMA issuer; warp 5: weight TMA
 constexpr int KBLOCK_BYTES = 128;
 constexpr int A_STAGE_BYTES = BM * KBLOCK_BYTES;  // 16 KB
-constexpr int LAG = 3;           // cp.async groups a producer thread keeps in flight
+constexpr int MIN_STAGES = 3;
 constexpr int MAX_STAGES = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -63,9 +64,8 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, uint64_t* bar, int32_t c0, int32_t c1) {
@@ -227,18 +227,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
           const uint8_t* src = ok ? p.in + size_t(src_row) * p.row_bytes + col : p.in;
           cp_async16(a_base + r * KBLOCK_BYTES + ((chunk ^ (r & 7)) << 4), src, ok ? 16u : 0u);
         }
-        cp_async_commit();
-        if (it >= LAG) {
-          cp_async_wait<LAG>();
-          fence_proxy_async();
-          mbar_arrive(full_bar + (it - LAG) % p.stages);
-        }
+        // hardware arrives on full[s] when this thread's copies have landed: nothing blocks, every free stage of the
+        // ring is in flight.  The generic->async proxy fence is issued by the consumer after it observes the barrier.
+        cp_async_mbar_arrive_noinc(full_bar + s);
       }
     }
-    // drain the last LAG groups
-    if (total > 2) { cp_async_wait<2>(); fence_proxy_async(); mbar_arrive(full_bar + (total - 3) % p.stages); }
-    if (total > 1) { cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(full_bar + (total - 2) % p.stages); }
-    if (total > 0) { cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(full_bar + (total - 1) % p.stages); }
 
     // =================================== epilogue ===================================
     if (total > 0) {
@@ -300,6 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(full_bar + s, ph);
+          fence_proxy_async();  // cp.async (generic proxy) writes of the producers -> visible to the tensor core's reads
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + size_t(s) * stage_bytes);
           const uint32_t b_base = a_base + A_STAGE_BYTES;
@@ -407,9 +401,9 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
   const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
   const int fixed = K * BM * 4 + 64 * 4 + (2 * MAX_STAGES + 1) * 8 + 16 + 1024;  // idx + klist/kflag + barriers + align
   int stages = (100 * 1024 - fixed) / stage_bytes;            // try to leave room for two CTAs per SM
-  if (stages < LAG + 1) stages = (227 * 1024 - fixed) / stage_bytes;
+  if (stages < MIN_STAGES + 1) stages = (227 * 1024 - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages < LAG + 1) return LGS_E_UNSUPPORTED;
+  if (stages < MIN_STAGES) return LGS_E_UNSUPPORTED;
   p.stages = stages;
   const size_t smem_bytes = size_t(stages) * stage_bytes + fixed;
 
@@ -443,9 +437,334 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
   return LGS_OK;
 }
 
-int conv_wgrad_tc(const void*, int64_t, int, const void*, int64_t, int, const int32_t*, int, float*, int,
-                  cudaStream_t) {
-  return LGS_E_UNSUPPORTED;
+// =============================================================================================================
+// wgrad on tensor cores:  dW[k] (c_in x c_out) = sum_o  X[table[k][o], :]^T (outer) dY[o, :]
+//
+// The reduction dimension of the GEMM is the (gathered) row index, so both operands are "MN-major": a shared-memory
+// tile [rows][128 B of channels] with the 128B swizzle is exactly the canonical MN-major layout (rows = K, 8-row
+// groups 1024 B apart, channel blocks LBO apart) — the same tiles the forward kernel gathers, read through a
+// different descriptor.  One MMA consumes 8 rows (tf32) / 16 rows (bf16).
+//
+// CTA = (chunk of rows, group of G offsets).  Per tile of R rows: TMA loads the dY tile once (shared by the G offsets),
+// the producers gather X for each offset, the MMA thread accumulates into G*MC accumulators in TMEM (MC = c_in/128
+// lane chunks).  At the end the accumulators are reduced into global dW with vector red.add.
+// =============================================================================================================
+namespace tcw {
+using namespace tc;
+
+constexpr int A_STAGES = 2;
+
+struct WParams {
+  const uint8_t* in;       // X [n_in, c_in]
+  int32_t in_row_bytes;
+  const int32_t* table;    // [K, n_out] or nullptr
+  int64_t n_out;
+  int32_t K, c_in, c_out;
+  float* gw;               // [K, c_in, c_out] fp32, pre-zeroed
+  int32_t R;               // rows per tile (32 / 64 / 128)
+  int32_t nb_in, nb_out;   // 128-byte channel blocks of X / dY
+  int32_t G;               // offsets per CTA
+  int32_t MC;              // 128-lane chunks of c_in
+  int32_t n_cols;          // accumulator columns (c_out padded to 16)
+  int32_t tmem_cols;
+  int64_t rows_per_chunk;  // multiple of R
+};
+
+// MN-major operand descriptor over a tile [rows][128 B of channels].
+//   16-bit types: SWIZZLE_128B (16-byte chunks XOR row%8), swizzle atom = 8 rows  -> SBO 1024 B
+//   32-bit types: SWIZZLE_128B_BASE32B (32-byte chunks XOR row%4), atom = 4 rows   -> SBO  512 B
+// (CuTe: Layout_MN_SW128_Atom / Layout_MN_SW128_32B_Atom; the transposing read of 32-bit elements needs the 32 B base.)
+template <bool BF16>
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((saddr >> 4) & 0x3FFF);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;            // LBO: stride between 128-byte channel blocks
+  d |= uint64_t((BF16 ? 1024 : 512) >> 4) << 32;              // SBO: stride between swizzle atoms along the rows
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(BF16 ? 2 : 1) << 61;
+  return d;
+}
+// position of 16-byte chunk c of row r inside the 128-byte row
+template <bool BF16>
+__device__ __forceinline__ uint32_t mn_chunk_pos(uint32_t c, uint32_t r) {
+  if constexpr (BF16) return c ^ (r & 7);
+  return ((((c >> 1) ^ (r & 3)) << 1) | (c & 1));
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int blk_bytes = p.R * KBLOCK_BYTES;             // one channel block of one tile
+  const int a_stage_bytes = p.nb_in * blk_bytes;
+  const int b_buf_bytes = p.nb_out * blk_bytes;
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = smem + size_t(A_STAGES) * a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + 2 * size_t(b_buf_bytes));
+  uint64_t* afull = bars;               // [A_STAGES]
+  uint64_t* aempty = bars + 2;          // [A_STAGES]
+  uint64_t* bfull = bars + 4;           // [2]
+  uint64_t* bempty = bars + 6;          // [2]
+  uint64_t* acc_bar = bars + 8;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t r_begin = int64_t(blockIdx.x) * p.rows_per_chunk;
+  const int64_t r_end = min(p.n_out, r_begin + p.rows_per_chunk);
+  const int k0 = blockIdx.y * p.G;
+  const int g_count = min(p.G, p.K - k0);
+  const int n_tiles = int((r_end - r_begin + p.R - 1) / p.R);
+
+  if (tid == 0) {
+    for (int s = 0; s < A_STAGES; ++s) {
+      mbar_init(afull + s, 128);
+      mbar_init(aempty + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bfull + s, 1);
+      mbar_init(bempty + s, 1);
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(uint32_t(p.tmem_cols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 5 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_gy) : "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < 4) {
+    // =================================== gather producers ===================================
+    const int chunk = tid & 7, rbase = tid >> 3;
+    const int passes = p.R / 16;
+    int it = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int64_t row0 = r_begin + int64_t(t) * p.R;
+      for (int g = 0; g < g_count; ++g, ++it) {
+        const int s = it & (A_STAGES - 1);
+        const uint32_t ph = (it / A_STAGES) & 1;
+        const int32_t* trow = p.table ? p.table + int64_t(k0 + g) * p.n_out : nullptr;
+        int32_t src_rows[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t o = row0 + rbase + 16 * i;
+          src_rows[i] = (i < passes && o < r_end) ? (trow ? __ldg(trow + o) : int32_t(o)) : -1;
+        }
+        mbar_wait(aempty + s, ph ^ 1);
+        const uint32_t a_base = smem_u32(a_smem + size_t(s) * a_stage_bytes);
+        for (int kb = 0; kb < p.nb_in; ++kb) {
+          const int col = kb * KBLOCK_BYTES + chunk * 16;
+          const bool col_ok = col < p.in_row_bytes;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < passes) {
+              const int r = rbase + 16 * i;
+              const bool ok = col_ok && src_rows[i] >= 0;
+              const uint8_t* src = ok ? p.in + size_t(src_rows[i]) * p.in_row_bytes + col : p.in;
+              cp_async16(a_base + kb * blk_bytes + r * KBLOCK_BYTES + (mn_chunk_pos<BF16>(chunk, r) << 4), src, ok ? 16u : 0u);
+            }
+          }
+        }
+        cp_async_mbar_arrive_noinc(afull + s);
+      }
+    }
+    // =================================== epilogue: TMEM -> red.add into dW ===================================
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    for (int g = 0; g < (n_tiles > 0 ? g_count : 0); ++g) {
+      for (int mc = 0; mc < p.MC; ++mc) {
+        const int ci = mc * 128 + warp * 32 + lane;
+        const uint32_t col_base = uint32_t((g * p.MC + mc) * p.n_cols);
+        for (int c0 = 0; c0 < p.c_out; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (uint32_t(warp * 32) << 16) + col_base + uint32_t(c0), v);
+          if (ci < p.c_in) {
+            float* dst = p.gw + (size_t(k0 + g) * p.c_in + ci) * p.c_out + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (c0 + j + 3 < p.c_out) {
+                red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                           __uint_as_float(v[j + 3]));
+              } else {
+                for (int jj = j; jj < j + 4; ++jj)
+                  if (c0 + jj < p.c_out) atomicAdd(dst + jj, __uint_as_float(v[jj]));
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // =================================== MMA issuer ===================================
+    if (lane == 0) {
+      const uint32_t fmt = BF16 ? 1u : 2u;
+      const int m_dim = 128;  // always whole 128-lane chunks (channels beyond c_in are zero-filled by the gather)
+      // D fp32, A/B tf32|bf16, BOTH MN-major (bits 15, 16), N = n_cols, M = m_dim
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) |
+                             (uint32_t(p.n_cols >> 3) << 17) | (uint32_t(m_dim >> 4) << 24);
+      const int rows_per_mma = BF16 ? 16 : 8;
+      const int mmas = p.R / rows_per_mma;
+      const int mma_stride = rows_per_mma * KBLOCK_BYTES;           // bytes of one K step (8 or 16 rows)
+      const int mc_blocks = 128 * (BF16 ? 2 : 4) / KBLOCK_BYTES;     // channel blocks per 128-lane chunk (4 fp32 / 2 bf16)
+      int it = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int bs = t & 1;
+        mbar_wait(bfull + bs, (t >> 1) & 1);
+        const uint32_t b_base = smem_u32(b_smem + size_t(bs) * b_buf_bytes);
+        for (int g = 0; g < g_count; ++g, ++it) {
+          const int s = it & (A_STAGES - 1);
+          mbar_wait(afull + s, (it / A_STAGES) & 1);
+          fence_proxy_async();
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(a_smem + size_t(s) * a_stage_bytes);
+          for (int mc = 0; mc < p.MC; ++mc) {
+            const uint32_t d_addr = tmem_base + uint32_t((g * p.MC + mc) * p.n_cols);
+            const uint32_t a_mc = a_base + mc * mc_blocks * blk_bytes;
+            for (int j = 0; j < mmas; ++j) {
+              umma<BF16>(d_addr, make_mnmajor_desc<BF16>(a_mc + j * mma_stride, blk_bytes),
+                         make_mnmajor_desc<BF16>(b_base + j * mma_stride, blk_bytes), idesc, (t > 0 || j > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(aempty + s);
+        }
+        umma_commit(bempty + bs);
+      }
+      umma_commit(acc_bar);
+    }
+    __syncwarp();
+  } else {
+    // =================================== dY tile TMA producer ===================================
+    if (lane == 0) {
+      const int kelems = KBLOCK_BYTES / (BF16 ? 2 : 4);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int bs = t & 1;
+        mbar_wait(bempty + bs, ((t >> 1) & 1) ^ 1);
+        mbar_expect_tx(bfull + bs, uint32_t(b_buf_bytes));
+        const int64_t row0 = r_begin + int64_t(t) * p.R;
+        for (int kb = 0; kb < p.nb_out; ++kb)
+          tma_load_2d(smem_u32(b_smem + size_t(bs) * b_buf_bytes + kb * blk_bytes), &tmap_gy, bfull + bs, kb * kelems,
+                      int32_t(row0));
+      }
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(p.tmem_cols))
+                 : "memory");
+  }
+}
+
+}  // namespace tcw
+
+int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int64_t n_out, int c_out,
+                  const int32_t* table, int K, float* gw, int dtype, cudaStream_t stream) {
+  using namespace tcw;
+  (void)n_in;
+  const int es = dtype == LGS_BF16 ? 2 : 4;
+  const int in_row_bytes = c_in * es, out_row_bytes = c_out * es;
+  if (in_row_bytes % 16 != 0 || out_row_bytes % 16 != 0) return LGS_E_UNSUPPORTED;
+  if (c_out % 4 != 0 || c_out > 256 || c_in > 512) return LGS_E_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(gout) & 15) ||
+      (reinterpret_cast<uintptr_t>(gw) & 15))
+    return LGS_E_UNSUPPORTED;
+  if (n_out >= (int64_t(1) << 31)) return LGS_E_UNSUPPORTED;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return fail(LGS_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+
+  WParams p;
+  p.in = static_cast<const uint8_t*>(in);
+  p.in_row_bytes = in_row_bytes;
+  p.table = table;
+  p.n_out = n_out;
+  p.K = K;
+  p.c_in = c_in;
+  p.c_out = c_out;
+  p.gw = gw;
+  p.nb_in = (in_row_bytes + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
+  p.nb_out = (out_row_bytes + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
+  p.MC = (c_in + 127) / 128;
+  p.n_cols = ((c_out + 15) / 16) * 16;
+  // the MMA reads whole 128-lane chunks (and, for M = 64, 64 lanes) of channel blocks: make the stage cover them
+  const int blocks_per_mc = 128 * es / KBLOCK_BYTES;   // 4 (fp32) / 2 (bf16)
+  const int nb_in_alloc = p.MC * blocks_per_mc;
+  const int nb_out_alloc = (p.n_cols * es + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
+  int R = 128;
+  while (R >= 32 && size_t(A_STAGES * nb_in_alloc + 2 * nb_out_alloc) * R * KBLOCK_BYTES > 200 * 1024) R >>= 1;
+  if (R < 32) return LGS_E_UNSUPPORTED;
+  p.R = R;
+  int G = 512 / (p.MC * p.n_cols);
+  if (G < 1) return LGS_E_UNSUPPORTED;
+  if (G > K) G = K;
+  // balance the offset groups (27 offsets, G = 5 -> 6 groups of 4/5)
+  const int groups = (K + G - 1) / G;
+  G = (K + groups - 1) / groups;
+  p.G = G;
+  int cols = 32;
+  while (cols < G * p.MC * p.n_cols) cols <<= 1;
+  p.tmem_cols = cols;
+
+  LGS_CUDA(cudaMemsetAsync(gw, 0, size_t(K) * c_in * c_out * sizeof(float), stream));
+  if (n_out == 0) return LGS_OK;
+
+  int64_t chunks = (148 * 2) / groups;   // <= two CTAs' worth of work per SM, one resident at a time (TMEM)
+  const int64_t max_chunks = cdiv(n_out, int64_t(R) * 4);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  p.rows_per_chunk = cdiv(cdiv(n_out, chunks), R) * R;
+  chunks = cdiv(n_out, p.rows_per_chunk);
+
+  // kernel-side sizes use nb_in (gathered) for the producer loop but the stage stride must cover what the MMA reads
+  WParams q = p;
+  const int blk_bytes = R * KBLOCK_BYTES;
+  // encode stage strides through nb_in/nb_out: the kernel computes a_stage_bytes = nb_in * blk_bytes, so pass the
+  // allocation counts and keep the number of gathered blocks implicit in in_row_bytes (col_ok masks the rest)
+  q.nb_in = nb_in_alloc;
+  q.nb_out = nb_out_alloc;
+  const size_t smem_bytes = size_t(A_STAGES * nb_in_alloc + 2 * nb_out_alloc) * blk_bytes + 16 * 8 + 1024;
+
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {cuuint64_t(c_out), cuuint64_t(n_out)};
+  const cuuint64_t gstride[1] = {cuuint64_t(out_row_bytes)};
+  const cuuint32_t box[2] = {cuuint32_t(KBLOCK_BYTES / es), cuuint32_t(R)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult cr = encode(&tmap, dtype == LGS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                             2, const_cast<void*>(gout), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             dtype == LGS_BF16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(LGS_E_CUDA, "cuTensorMapEncodeTiled (wgrad) failed (%d)", int(cr));
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) return fail(LGS_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+
+  const dim3 grid{unsigned(chunks), unsigned(groups), 1u};
+  if (dtype == LGS_BF16) {
+    LGS_LAUNCH(wgrad_tc_kernel<true>, grid, THREADS, smem_bytes, stream, tmap, q);
+  } else {
+    LGS_LAUNCH(wgrad_tc_kernel<false>, grid, THREADS, smem_bytes, stream, tmap, q);
+  }
+  return LGS_OK;
 }
 
 }  // namespace lgs

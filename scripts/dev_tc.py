@@ -28,10 +28,12 @@ def check(name, c, cin, cout, ks=3, dtype=torch.float32, nscale=1.0):
         y = run(algo, f, w, km)
         y.backward(gy)
         torch.cuda.synchronize()
-        res[algo] = (y.detach().float(), f.grad.detach().float())
+        res[algo] = (y.detach().float(), f.grad.detach().float(), w.grad.detach().float().clone())
+        w.grad = None
     e_out = ((res["tc"][0] - res["simt"][0]).abs().max() / res["simt"][0].abs().max()).item()
     e_gin = ((res["tc"][1] - res["simt"][1]).abs().max() / res["simt"][1].abs().max()).item()
-    print(f"{name:28s} n={c.shape[0]:7d} {cin:4d}->{cout:4d} ks={ks} {str(dtype)[6:]:9s} rel err out={e_out:.2e} dgrad={e_gin:.2e}", flush=True)
+    e_gw = ((res["tc"][2] - res["simt"][2]).abs().max() / res["simt"][2].abs().max()).item()
+    print(f"{name:28s} n={c.shape[0]:7d} {cin:4d}->{cout:4d} ks={ks} {str(dtype)[6:]:9s} rel err out={e_out:.2e} dgrad={e_gin:.2e} wgrad={e_gw:.2e}", flush=True)
     return km, f, w
 
 rng = np.random.default_rng(0)
@@ -64,3 +66,17 @@ for cin, cout, dtype in [(96, 96, torch.float32), (128, 96, torch.float32), (32,
         s = 2 if dtype == torch.bfloat16 else 4
         byts = P * (cin + cout) * s + 8 * P + 27 * cin * cout * s
         print(f"   {algo:5s} fwd {ms:8.3f} ms  {2*P*cin*cout/ms/1e9:8.2f} TFLOP/s  gather-model {byts/ms/1e6:8.1f} GB/s  (P={P})", flush=True)
+        gw = torch.empty(27, cin, cout, device="cuda")
+        a = _lib.ALGO_TC if algo == "tc" else _lib.ALGO_SIMT
+        fd, gyd = f.detach().contiguous(), torch.randn(c.shape[0], cout, device="cuda").to(dtype)
+        st = E._stream()
+        def wg():
+            _lib.check(lib.lgs_conv_wgrad(_lib.ptr(fd), fd.shape[0], cin, _lib.ptr(gyd), gyd.shape[0], cout, _lib.ptr(km.fwd_table), 27, _lib.ptr(gw), E._dtype_code(fd), a, st))
+        for _ in range(2): wg()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5): wg()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"   {algo:5s} wgrad {ms:8.3f} ms  {2*P*cin*cout/ms/1e9:8.2f} TFLOP/s", flush=True)
