@@ -53,6 +53,8 @@ class ClockSampler:
 
     def __enter__(self):
         try:
+            if self.index < 0:
+                raise RuntimeError('disabled')
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -183,7 +185,6 @@ def run_engine(args, rank, world, local_rank):
     barrier()
 
     # ---- timed region: `value` --------------------------------------------------------------------------
-    E.profile_begin()
     l0 = _lib.launch_count()
     with ClockSampler(local_rank) as clk:
         barrier()
@@ -195,8 +196,16 @@ def run_engine(args, rank, world, local_rank):
         barrier()
     ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - l0
-    prof = E.profile_end()
     loss_val = float(loss.item())
+
+    # ---- per-launch CUDA-event timing of the engine's conv kernels (same process, same data, right after the timed
+    # region; kept out of it because ~380 event records per step starve the launch queue and double the step time)
+    PROF_STEPS = 2
+    E.profile_begin()
+    for _ in range(PROF_STEPS):
+        resident_step()
+    torch.cuda.synchronize()
+    prof = E.profile_end() or []
 
     # ---- e2e leg -----------------------------------------------------------------------------------------
     e2e_step()
@@ -256,17 +265,18 @@ def run_engine(args, rank, world, local_rank):
         d[1] += by
         d[2] += fl
         d[3] += 1
-    step_flops = sum(v[2] for v in agg.values()) / args.steps
-    step_bytes = sum(v[1] for v in agg.values()) / args.steps
-    conv_ms, conv_bytes, conv_flops, conv_n = agg["conv"]
+    step_flops = sum(v[2] for v in agg.values()) / PROF_STEPS
+    step_bytes = sum(v[1] for v in agg.values()) / PROF_STEPS
+    conv_ms, conv_bytes, conv_flops, conv_n = agg.get("conv", [1e-9, 0, 0, 1])
     achieved = conv_bytes / (conv_ms * 1e-3) / 1e9
     wg = agg.get("wgrad", [0, 0, 0, 0])
     roofline = {"bound": "hbm", "kernel": "conv fwd/dgrad (output-stationary gather-GEMM)", "achieved": round(achieved, 1),
                 "peak": hbm_gbs, "unit": "GB/s", "frac": round(achieved / hbm_gbs, 4), "traffic": None,
                 "peak_source": peak_src, "launches": conv_n, "avg_launch_ms": round(conv_ms / conv_n, 4),
-                "share_of_step": round(conv_ms / ms, 3),
+                "share_of_step": round((conv_ms / PROF_STEPS) / (ms / args.steps), 3),
+                "timed_over": f"{PROF_STEPS} extra steps right after the timed region, CUDA events around every launch",
                 "tflops": round(conv_flops / (conv_ms * 1e-3) / 1e12, 2),
-                "wgrad": {"share_of_step": round(wg[0] / ms, 3), "achieved_gbs": round(wg[1] / max(wg[0], 1e-9) / 1e6, 1),
+                "wgrad": {"share_of_step": round((wg[0] / PROF_STEPS) / (ms / args.steps), 3), "achieved_gbs": round(wg[1] / max(wg[0], 1e-9) / 1e6, 1),
                           "tflops": round(wg[2] / max(wg[0], 1e-9) / 1e9, 2)},
                 "step_model": {"gflop": round(step_flops / 1e9, 1), "gbyte": round(step_bytes / 1e9, 2),
                                "hbm_floor_ms": round(step_bytes / hbm_gbs / 1e6, 3)}}
@@ -280,8 +290,9 @@ def run_engine(args, rank, world, local_rank):
         "vs_baseline": None, "dtype": "f32" if args.dtype == "f32" else "bf16", "data": "synthetic",
         "config": {"workload": f"{MODEL} fwd+bwd+SGD, 1 synthetic ScanNet-shaped scene/GPU, {n_vox} voxels @2cm, 200 classes "
                                "(BASELINE configs[1])", "voxels_per_gpu": n_vox, "algo": args.algo,
-                   "math": ("tf32 tensor cores, fp32 accumulate" if args.algo == "tc" else "fp32 FMA") if args.dtype == "f32"
-                   else "bf16 tensor cores, fp32 accumulate",
+                   "math": {"tc": "tcgen05 3xTF32 products (fp32-grade) fwd/dgrad, TF32 wgrad, fp32 accumulate in TMEM",
+                            "tf32": "tcgen05 single-pass TF32, fp32 accumulate", "simt": "fp32 FMA"}[args.algo]
+                   if args.dtype == "f32" else "tcgen05 bf16 products, fp32 accumulate in TMEM",
                    "l2": "256 MB buffer written between steps (L2 flush); per-step activations >> 126 MB L2",
                    "parallelism": f"dp{world}", "step": "coordinate+kernel maps, fwd, CE loss, bwd, SGD"},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -332,10 +343,10 @@ def cpu_model_name():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--algo", default="tc", choices=["tc", "simt"])
+    ap.add_argument("--algo", default="tc", choices=["tc", "tf32", "simt"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--cpu-sample-voxels", type=int, default=60_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")

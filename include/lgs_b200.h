@@ -37,9 +37,11 @@ extern "C" {
 /* conv algorithms */
 #define LGS_ALGO_SIMT 0  /* fp32 FMA, exact: the parity anchor */
 #define LGS_ALGO_TC 1    /* tcgen05 tensor cores, TMEM accumulators (TF32 for LGS_F32 features, BF16 for LGS_BF16) */
+#define LGS_ALGO_TC3 2   /* tcgen05, 3xTF32 error-compensated products (hi*hi + lo*hi + hi*lo): fp32-grade, LGS_F32 only */
 /* weight layouts */
 #define LGS_W_KCN 0      /* [K, c_in, c_out]: MinkowskiEngine's parameter layout */
 #define LGS_W_KNC 1      /* [K, c_out, c_in]: per-offset transpose (the K-major B operand the tensor-core path loads by TMA) */
+#define LGS_W_KNC_SPLIT 2 /* [2, K, c_out, c_in]: TF32 hi / lo halves of LGS_W_KNC, for LGS_ALGO_TC3 (see lgs_weight_prep) */
 
 int lgs_version(void);
 const char* lgs_last_error(void);
@@ -91,6 +93,16 @@ int lgs_kmap_build(const int32_t* d_out_coords, int64_t n_out,
 int lgs_kmap_transpose(const int32_t* d_table, int32_t K, int64_t n_out, int64_t n_in, int32_t* d_table_t,
                        void* stream);
 
+/* 1 if the tensor-core kernels (LGS_ALGO_TC / TC3) take a c_in -> c_out layer of this feature dtype */
+int lgs_conv_tc_supported(int32_t c_in, int32_t c_out, int32_t dtype);
+
+/* Tensor-core operand forms of one layer's weights W [K,c_in,c_out] (fp32 parameter), one launch:
+ *   d_fwd [nsplit,K,c_out,c_in] for the forward GEMM, d_bwd [nsplit,K,c_in,c_out] for dgrad (either may be NULL).
+ *   nsplit 1: cast/transposed copy (LGS_W_KNC);  nsplit 2: hi = RN_tf32(w), lo = RN_tf32(w - hi) (LGS_W_KNC_SPLIT).
+ * Outputs have the feature dtype.  (ME keeps one fp32 [K,Cin,Cout] kernel and re-reads it per offset.) */
+int lgs_weight_prep(const float* d_weight, int32_t K, int32_t c_in, int32_t c_out, int32_t nsplit,
+                    void* d_fwd, void* d_bwd, int32_t dtype, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Sparse convolution.   Replaces ME ConvolutionForwardGPU / ConvolutionBackwardGPU (and ...Transpose...)
  *   call sites: models/modules/common.py:195-203, 228-236; autograd backward of the same.
@@ -100,8 +112,9 @@ int lgs_kmap_transpose(const int32_t* d_table, int32_t K, int64_t n_out, int64_t
  * (W[k] is [c_in,c_out] = [c_out',c_in']), table := transposed table, or the same table with reverse_k = 1 when the
  * in and out maps coincide and ks is odd.
  * W has the feature dtype (fp32 for LGS_F32, bf16 for LGS_BF16); out too; accumulation is fp32.
- * LGS_ALGO_SIMT reads either layout.  LGS_ALGO_TC needs LGS_W_KNC, 16-byte-multiple feature rows and c_out % 4 == 0;
- * any other request is served by the SIMT kernel (still on the GPU; there is no CPU path).
+ * LGS_ALGO_SIMT reads LGS_W_KCN or LGS_W_KNC.  LGS_ALGO_TC needs LGS_W_KNC and a shape lgs_conv_tc_supported()
+ * accepts; any other LGS_ALGO_TC request is served by the SIMT kernel (still on the GPU; there is no CPU path).
+ * LGS_ALGO_TC3 needs LGS_W_KNC_SPLIT weights, LGS_F32 features and a supported shape, and fails otherwise.
  * --------------------------------------------------------------------------------------------------------- */
 int lgs_conv_fwd(const void* d_in, int64_t n_in, int32_t c_in,
                  const void* d_weight, int32_t weight_layout, int32_t K, int32_t c_out,

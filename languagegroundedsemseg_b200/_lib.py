@@ -8,8 +8,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liblgs_b200.so")
 
 OK, E_INVALID, E_CUDA, E_RANGE, E_HASH_FULL, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 F32, BF16 = 0, 1
-ALGO_SIMT, ALGO_TC = 0, 1
-W_KCN, W_KNC = 0, 1
+ALGO_SIMT, ALGO_TC, ALGO_TC3 = 0, 1, 2
+W_KCN, W_KNC, W_KNC_SPLIT = 0, 1, 2
 
 _p, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 
@@ -25,6 +25,8 @@ SIGNATURES = {
     "lgs_coordmap_build": (C.c_int, [_p, _i64, _i32, _p, _p, _i64, _p, _p, _p, _p, _p, C.POINTER(_i64), _p]),
     "lgs_kmap_build": (C.c_int, [_p, _i64, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p]),
     "lgs_kmap_transpose": (C.c_int, [_p, _i32, _i64, _i64, _p, _p]),
+    "lgs_conv_tc_supported": (C.c_int, [_i32, _i32, _i32]),
+    "lgs_weight_prep": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _i32, _p]),
     "lgs_conv_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i32, _p, _i64, _i32, _p, _p, _i32, _i32, _p]),
     "lgs_conv_wgrad": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _p, _i32, _p, _i32, _i32, _p]),
     "lgs_clip_ce": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _i64, _p, _p, _p, _p, _p]),

@@ -9,7 +9,10 @@ int conv_wgrad_simt(const void* in, int c_in, const void* gout, int64_t n_out, i
                     float* gw, int dtype, cudaStream_t stream);
 // tcgen05 path (conv_tc.cu): returns LGS_E_UNSUPPORTED when the shape is outside what it was built for
 int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w, int K, int c_out, const int32_t* table,
-                int64_t n_out, int reverse_k, const float* bias, void* out, int dtype, cudaStream_t stream);
+                int64_t n_out, int reverse_k, const float* bias, void* out, int dtype, int precise, cudaStream_t stream);
+int conv_tc_shape_ok(int c_in, int c_out, int dtype);
+int weight_prep(const float* w, int K, int c_in, int c_out, int nsplit, void* fwd, void* bwd, int dtype,
+                cudaStream_t stream);
 int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int64_t n_out, int c_out,
                   const int32_t* table, int K, float* gw, int dtype, cudaStream_t stream);
 bool tc_built();
@@ -20,6 +23,16 @@ using namespace lgs;
 extern "C" {
 
 int lgs_has_tc(void) { return tc_built() ? 1 : 0; }
+
+int lgs_conv_tc_supported(int32_t c_in, int32_t c_out, int32_t dtype) { return conv_tc_shape_ok(c_in, c_out, dtype); }
+
+int lgs_weight_prep(const float* d_weight, int32_t K, int32_t c_in, int32_t c_out, int32_t nsplit, void* d_fwd,
+                    void* d_bwd, int32_t dtype, void* stream_) {
+  if (K < 1 || c_in < 1 || c_out < 1 || (nsplit != 1 && nsplit != 2) || !d_weight || (!d_fwd && !d_bwd))
+    return fail(LGS_E_INVALID, "lgs_weight_prep: bad arguments");
+  if (dtype != LGS_F32 && dtype != LGS_BF16) return fail(LGS_E_INVALID, "lgs_weight_prep: dtype %d", dtype);
+  return weight_prep(d_weight, K, c_in, c_out, nsplit, d_fwd, d_bwd, dtype, static_cast<cudaStream_t>(stream_));
+}
 
 int lgs_conv_fwd(const void* d_in, int64_t n_in, int32_t c_in, const void* d_weight, int32_t weight_layout, int32_t K,
                  int32_t c_out,
@@ -32,13 +45,23 @@ int lgs_conv_fwd(const void* d_in, int64_t n_in, int32_t c_in, const void* d_wei
   if (!d_table && (K != 1 || n_in != n_out))
     return fail(LGS_E_INVALID, "lgs_conv_fwd: NULL table needs K == 1 and n_in == n_out");
   if (dtype != LGS_F32 && dtype != LGS_BF16) return fail(LGS_E_INVALID, "lgs_conv_fwd: dtype %d", dtype);
-  if (weight_layout != LGS_W_KCN && weight_layout != LGS_W_KNC)
+  if (weight_layout != LGS_W_KCN && weight_layout != LGS_W_KNC && weight_layout != LGS_W_KNC_SPLIT)
     return fail(LGS_E_INVALID, "lgs_conv_fwd: weight_layout %d", weight_layout);
+  if (algo == LGS_ALGO_TC3) {
+    // 3xTF32: hi/lo-split K-major weights only; the caller checks lgs_conv_tc_supported() before choosing this form
+    if (weight_layout != LGS_W_KNC_SPLIT || dtype != LGS_F32)
+      return fail(LGS_E_INVALID, "lgs_conv_fwd: LGS_ALGO_TC3 needs LGS_W_KNC_SPLIT weights and LGS_F32 features");
+    const int rc = conv_fwd_tc(d_in, n_in, c_in, d_weight, K, c_out, d_table, n_out, reverse_k, d_bias, d_out, dtype, 1,
+                               stream);
+    if (rc == LGS_E_UNSUPPORTED) return fail(rc, "lgs_conv_fwd: shape %d->%d not supported by LGS_ALGO_TC3", c_in, c_out);
+    return rc;
+  }
+  if (weight_layout == LGS_W_KNC_SPLIT) return fail(LGS_E_INVALID, "lgs_conv_fwd: split weights need LGS_ALGO_TC3");
   if ((n_out && (!d_in && n_in)) || !d_weight || (n_out && !d_out)) return fail(LGS_E_INVALID, "lgs_conv_fwd: null pointer");
   if (algo == LGS_ALGO_TC) {
     const int rc = weight_layout == LGS_W_KNC
                        ? conv_fwd_tc(d_in, n_in, c_in, d_weight, K, c_out, d_table, n_out, reverse_k, d_bias, d_out,
-                                     dtype, stream)
+                                     dtype, 0, stream)
                        : LGS_E_UNSUPPORTED;
     if (rc != LGS_E_UNSUPPORTED) return rc;
     // shape outside the tensor-core kernel's envelope (e.g. c_in = 3): the SIMT kernel takes it
@@ -59,6 +82,10 @@ int lgs_conv_wgrad(const void* d_in, int64_t n_in, int32_t c_in, const void* d_g
   if (dtype != LGS_F32 && dtype != LGS_BF16) return fail(LGS_E_INVALID, "lgs_conv_wgrad: dtype %d", dtype);
   if (!d_grad_w) return fail(LGS_E_INVALID, "lgs_conv_wgrad: null pointer");
   if (algo == LGS_ALGO_TC) {
+    const int rc = conv_wgrad_tc(d_in, n_in, c_in, d_grad_out, n_out, c_out, d_table, K, d_grad_w, dtype, stream);
+    if (rc != LGS_E_UNSUPPORTED) return rc;
+  } else if (algo == LGS_ALGO_TC3) {
+    // weight gradients: single-pass TF32 products with fp32 accumulation (sums over ~1e5 rows)
     const int rc = conv_wgrad_tc(d_in, n_in, c_in, d_grad_out, n_out, c_out, d_table, K, d_grad_w, dtype, stream);
     if (rc != LGS_E_UNSUPPORTED) return rc;
   } else if (algo != LGS_ALGO_SIMT) {

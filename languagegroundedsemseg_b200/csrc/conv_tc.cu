@@ -137,19 +137,26 @@ struct Params {
   int32_t b_stage_bytes;    // n_tile * 128
 };
 
-template <bool BF16>
-__global__ void __launch_bounds__(THREADS, 1)
+// PRECISE (fp32 features only): 3xTF32 error-compensated product.  Four extra warps split every landed A tile into
+// hi = tf32-truncated value (rewritten in place) and lo = a - hi (second tile); the weights arrive pre-split (hi, lo
+// stacked, see lgs_weight_prep); three MMAs per K step accumulate hi*hi + lo*hi + hi*lo, i.e. fp32-grade products
+// (relative error ~2^-21) with fp32 accumulation in TMEM.
+template <bool BF16, bool PRECISE>
+__global__ void __launch_bounds__(PRECISE ? THREADS + 128 : THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A 16 KB | B n_tile*128)] [idx K*128 int32] [klist 32] [barriers] [tmem ptr]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
+  constexpr int NSPLIT = PRECISE ? 2 : 1;
+  constexpr int NTHREADS = PRECISE ? THREADS + 128 : THREADS;
+  const int stage_bytes = NSPLIT * (A_STAGE_BYTES + p.b_stage_bytes);   // [A hi | A lo] [B hi | B lo]
   int32_t* sidx = reinterpret_cast<int32_t*>(smem + size_t(p.stages) * stage_bytes);
   int32_t* klist = sidx + p.K * BM;
   int32_t* kflag = klist + 32;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(kflag + 32);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* acc_bar = empty_bar + MAX_STAGES;
+  uint64_t* split_bar = empty_bar + MAX_STAGES;
+  uint64_t* acc_bar = split_bar + MAX_STAGES;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_bar + 1);
   int32_t* nk_smem = reinterpret_cast<int32_t*>(tmem_ptr_smem + 1);
 
@@ -158,7 +165,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
   const int n0 = blockIdx.y * 256;
 
   // ---- prologue -----------------------------------------------------------------------------------------
-  for (int e = tid; e < p.K * BM; e += THREADS) {
+  for (int e = tid; e < p.K * BM; e += NTHREADS) {
     const int k = e / BM, r = e - k * BM;
     const int64_t o = m0 + r;
     int32_t v = -1;
@@ -169,6 +176,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar + s, 128 + 1);
       mbar_init(empty_bar + s, 1);
+      mbar_init(split_bar + s, 128);
     }
     mbar_init(acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -184,7 +192,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
   }
   __syncthreads();
   // which offsets have any neighbour in this tile
-  for (int k = warp; k < p.K; k += THREADS / 32) {
+  for (int k = warp; k < p.K; k += NTHREADS / 32) {
     bool any = false;
 #pragma unroll
     for (int j = 0; j < BM / 32; ++j) any |= sidx[k * BM + lane + 32 * j] >= 0;
@@ -292,16 +300,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(full_bar + s, ph);
-          fence_proxy_async();  // cp.async (generic proxy) writes of the producers -> visible to the tensor core's reads
+          mbar_wait(full_bar + s, ph);          // gathered rows (cp.async) and weights (TMA) have landed
+          if constexpr (PRECISE) mbar_wait(split_bar + s, ph);   // ... and the hi/lo split of A is done
+          fence_proxy_async();  // generic-proxy writes (cp.async / splitters) -> visible to the tensor core's reads
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + size_t(s) * stage_bytes);
-          const uint32_t b_base = a_base + A_STAGE_BYTES;
+          const uint32_t b_base = a_base + NSPLIT * A_STAGE_BYTES;
           const int valid = min(KBLOCK_BYTES, p.row_bytes - kb * KBLOCK_BYTES);
           const int ksteps = (valid + 31) / 32;  // 32 bytes of K per instruction (8 tf32 / 16 bf16)
           for (int j = 0; j < ksteps; ++j) {
-            umma<BF16>(tmem_base, make_kmajor_sw128_desc(a_base + j * 32), make_kmajor_sw128_desc(b_base + j * 32), idesc,
-                       (it > 0 || j > 0) ? 1u : 0u);
+            const uint64_t a_hi = make_kmajor_sw128_desc(a_base + j * 32), b_hi = make_kmajor_sw128_desc(b_base + j * 32);
+            umma<BF16>(tmem_base, a_hi, b_hi, idesc, (it > 0 || j > 0) ? 1u : 0u);
+            if constexpr (PRECISE) {
+              umma<BF16>(tmem_base, make_kmajor_sw128_desc(a_base + A_STAGE_BYTES + j * 32), b_hi, idesc, 1u);
+              umma<BF16>(tmem_base, a_hi, make_kmajor_sw128_desc(b_base + p.b_stage_bytes + j * 32), idesc, 1u);
+            }
           }
           umma_commit(empty_bar + s);  // frees the stage once these MMAs have read it
         }
@@ -309,7 +322,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
       if (total > 0) umma_commit(acc_bar);
     }
     __syncwarp();
-  } else {
+  } else if (warp == 5) {
     // =================================== weight TMA producer (one thread) ===================================
     if (lane == 0) {
       const int kelems = KBLOCK_BYTES / (BF16 ? 2 : 4);
@@ -320,13 +333,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(empty_bar + s, ph ^ 1);
-          mbar_expect_tx(full_bar + s, uint32_t(p.b_stage_bytes));
-          tma_load_2d(smem_u32(smem + size_t(s) * stage_bytes + A_STAGE_BYTES), &tmap_w, full_bar + s, kb * kelems,
-                      k * p.c_out + n0);
+          mbar_expect_tx(full_bar + s, uint32_t(NSPLIT * p.b_stage_bytes));
+          const uint32_t b_dst = smem_u32(smem + size_t(s) * stage_bytes + NSPLIT * A_STAGE_BYTES);
+          tma_load_2d(b_dst, &tmap_w, full_bar + s, kb * kelems, k * p.c_out + n0);
+          if constexpr (PRECISE)   // lo halves are stacked after the K*c_out hi rows
+            tma_load_2d(b_dst + p.b_stage_bytes, &tmap_w, full_bar + s, kb * kelems, (p.K + k) * p.c_out + n0);
         }
       }
     }
     __syncwarp();
+  }
+  if constexpr (PRECISE) {
+    if (warp >= 6) {
+      // =================================== hi/lo splitters (128 threads) ===================================
+      const int st = tid - THREADS;
+      for (int it = 0; it < total; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(full_bar + s, ph);
+        float4* a_hi = reinterpret_cast<float4*>(smem + size_t(s) * stage_bytes);
+        float4* a_lo = reinterpret_cast<float4*>(smem + size_t(s) * stage_bytes + A_STAGE_BYTES);
+#pragma unroll
+        for (int i = 0; i < A_STAGE_BYTES / 16 / 128; ++i) {
+          const int e = st + 128 * i;
+          const float4 v = a_hi[e];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          l.x = v.x - h.x;
+          l.y = v.y - h.y;
+          l.z = v.z - h.z;
+          l.w = v.w - h.w;
+          a_hi[e] = h;
+          a_lo[e] = l;
+        }
+        fence_proxy_async();
+        mbar_arrive(split_bar + s);
+      }
+    }
   }
 
   __syncthreads();
@@ -359,10 +405,72 @@ static EncodeTiledFn get_encode() {
 
 bool tc_built() { return true; }
 
+// One launch per layer: from W [K, c_in, c_out] (fp32) produce the tensor-core operand forms
+//   fwd  [nsplit, K, c_out, c_in]  (per-offset transpose = K-major B of the forward GEMM)
+//   bwd  [nsplit, K, c_in, c_out]  (K-major B of the dgrad GEMM: W itself)
+// nsplit = 1: plain copy / transpose (bf16 or fp32 -> TF32 read by the hardware);
+// nsplit = 2: hi = RN_tf32(w), lo = RN_tf32(w - hi) for the 3xTF32 path.
+template <typename T>
+__global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ w, int K, int c_in, int c_out,
+                                                          int nsplit, T* __restrict__ fwd, T* __restrict__ bwd) {
+  const int64_t total = int64_t(K) * c_in * c_out;
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= total) return;
+  const int co = int(e % c_out);
+  const int ci = int((e / c_out) % c_in);
+  const int k = int(e / (int64_t(c_out) * c_in));
+  const float v = w[e];
+  const int64_t et = (int64_t(k) * c_out + co) * c_in + ci;
+  if constexpr (sizeof(T) == 2) {
+    const T b = __float2bfloat16(v);
+    if (fwd) fwd[et] = b;
+    if (bwd) bwd[e] = b;
+  } else {
+    if (nsplit == 1) {
+      if (fwd) fwd[et] = v;
+      if (bwd) bwd[e] = v;
+    } else {
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+      const float hi = __uint_as_float(hb);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
+      const float lo = __uint_as_float(lb);
+      if (fwd) { fwd[et] = hi; fwd[total + et] = lo; }
+      if (bwd) { bwd[e] = hi; bwd[total + e] = lo; }
+    }
+  }
+}
+
+int weight_prep(const float* w, int K, int c_in, int c_out, int nsplit, void* fwd, void* bwd, int dtype,
+                cudaStream_t stream) {
+  const int64_t total = int64_t(K) * c_in * c_out;
+  if (total == 0) return LGS_OK;
+  if (dtype == LGS_BF16) {
+    LGS_LAUNCH(weight_prep_kernel<__nv_bfloat16>, unsigned(cdiv(total, 256)), 256, 0, stream, w, K, c_in, c_out, 1,
+               static_cast<__nv_bfloat16*>(fwd), static_cast<__nv_bfloat16*>(bwd));
+  } else {
+    LGS_LAUNCH(weight_prep_kernel<float>, unsigned(cdiv(total, 256)), 256, 0, stream, w, K, c_in, c_out, nsplit,
+               static_cast<float*>(fwd), static_cast<float*>(bwd));
+  }
+  return LGS_OK;
+}
+
 // Weights arrive K-major for this path: d_weight_nk = [K, c_out, c_in] (c_in contiguous).
+// 0 if the tensor-core kernels take this shape (the facade asks before choosing the weight layout)
+int conv_tc_shape_ok(int c_in, int c_out, int dtype) {
+  const int es = dtype == LGS_BF16 ? 2 : 4;
+  const int row_bytes = c_in * es;
+  if (row_bytes % 16 != 0 || row_bytes < 16) return 0;
+  if (dtype == LGS_BF16 ? (c_out % 2 != 0) : (c_out % 4 != 0)) return 0;
+  if (c_out > 256 && c_out % 256 != 0) return 0;
+  return 1;
+}
+
 int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K, int c_out, const int32_t* table,
-                int64_t n_out, int reverse_k, const float* bias, void* out, int dtype, cudaStream_t stream) {
+                int64_t n_out, int reverse_k, const float* bias, void* out, int dtype, int precise, cudaStream_t stream) {
   using namespace tc;
+  if (dtype == LGS_BF16) precise = 0;
+  const int nsplit = precise ? 2 : 1;
   const int es = dtype == LGS_BF16 ? 2 : 4;
   const int row_bytes = c_in * es;
   if (row_bytes % 16 != 0 || row_bytes < 16) return LGS_E_UNSUPPORTED;
@@ -370,7 +478,8 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
       (reinterpret_cast<uintptr_t>(out) & 15))
     return LGS_E_UNSUPPORTED;
   if (dtype == LGS_BF16 ? (c_out % 2 != 0) : (c_out % 4 != 0)) return LGS_E_UNSUPPORTED;  // vector stores
-  if (int64_t(K) * c_out >= (int64_t(1) << 31)) return LGS_E_UNSUPPORTED;
+  if (int64_t(K) * c_out * 2 >= (int64_t(1) << 31)) return LGS_E_UNSUPPORTED;
+  if (!conv_tc_shape_ok(c_in, c_out, dtype)) return LGS_E_UNSUPPORTED;
   if (n_out == 0) return LGS_OK;
   EncodeTiledFn encode = get_encode();
   if (!encode) return fail(LGS_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -398,18 +507,18 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
   int cols = 32;
   while (cols < p.n_tile) cols <<= 1;
   p.tmem_cols = cols;
-  const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
-  const int fixed = K * BM * 4 + 64 * 4 + (2 * MAX_STAGES + 1) * 8 + 16 + 1024;  // idx + klist/kflag + barriers + align
+  const int stage_bytes = nsplit * (A_STAGE_BYTES + p.b_stage_bytes);
+  const int fixed = K * BM * 4 + 64 * 4 + (3 * MAX_STAGES + 1) * 8 + 16 + 1024;  // idx + klist/kflag + barriers + align
   int stages = (100 * 1024 - fixed) / stage_bytes;            // try to leave room for two CTAs per SM
   if (stages < MIN_STAGES + 1) stages = (227 * 1024 - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages < MIN_STAGES) return LGS_E_UNSUPPORTED;
+  if (stages < (precise ? 2 : MIN_STAGES)) return LGS_E_UNSUPPORTED;
   p.stages = stages;
   const size_t smem_bytes = size_t(stages) * stage_bytes + fixed;
 
   // tensor map over W^T viewed as [K * c_out rows, c_in] with box {128 B of channels, n_tile rows}, 128B swizzle
   CUtensorMap tmap;
-  const cuuint64_t gdim[2] = {cuuint64_t(c_in), cuuint64_t(K) * cuuint64_t(c_out)};
+  const cuuint64_t gdim[2] = {cuuint64_t(c_in), cuuint64_t(nsplit) * cuuint64_t(K) * cuuint64_t(c_out)};
   const cuuint64_t gstride[1] = {cuuint64_t(row_bytes)};
   const cuuint32_t box[2] = {cuuint32_t(KBLOCK_BYTES / es), cuuint32_t(p.n_tile)};
   const cuuint32_t estr[2] = {1, 1};
@@ -422,17 +531,21 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      attr_err = cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return fail(LGS_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
 
   dim3 grid(unsigned(cdiv(n_out, BM)), unsigned(n_tiles));
   if (dtype == LGS_BF16) {
-    LGS_LAUNCH(conv_tc_kernel<true>, grid, THREADS, smem_bytes, stream, tmap, p);
+    LGS_LAUNCH((conv_tc_kernel<true, false>), grid, THREADS, smem_bytes, stream, tmap, p);
+  } else if (precise) {
+    LGS_LAUNCH((conv_tc_kernel<false, true>), grid, THREADS + 128, smem_bytes, stream, tmap, p);
   } else {
-    LGS_LAUNCH(conv_tc_kernel<false>, grid, THREADS, smem_bytes, stream, tmap, p);
+    LGS_LAUNCH((conv_tc_kernel<false, false>), grid, THREADS, smem_bytes, stream, tmap, p);
   }
   return LGS_OK;
 }

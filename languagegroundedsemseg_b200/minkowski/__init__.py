@@ -39,8 +39,11 @@ for _n in ("Sequence", "Iterable"):
 # ----------------------------------------------------------------------------------------------------------
 # engine-wide settings
 # ----------------------------------------------------------------------------------------------------------
-_ALGO = {"simt": _lib.ALGO_SIMT, "tc": _lib.ALGO_TC}
-_state = {"algo": _lib.ALGO_TC, "profile": None}
+# 'simt'  exact fp32 FMA kernels (parity anchor, slow)
+# 'tc'    tcgen05 tensor cores, parity-grade: 3xTF32 products for fp32 features (bf16 MMA for bf16 features)  [default]
+# 'tf32'  tcgen05 single-pass TF32 (fast, ~7e-4 relative error per layer)
+_ALGO = {"simt": _lib.ALGO_SIMT, "tc": _lib.ALGO_TC3, "tf32": _lib.ALGO_TC}
+_state = {"algo": _lib.ALGO_TC3, "profile": None}
 
 
 def profile_begin():
@@ -75,7 +78,7 @@ class _Timed:
 
 
 def set_conv_algo(name: str):
-    """'simt' = exact fp32 FMA kernels (parity anchor); 'tc' = tcgen05 tensor-core kernels (default)."""
+    """'simt' exact fp32 FMA | 'tc' tcgen05 3xTF32 (default, fp32-grade) | 'tf32' tcgen05 single-pass TF32."""
     _state["algo"] = _ALGO[name]
 
 
@@ -379,42 +382,64 @@ class _SparseConvFn(torch.autograd.Function):
         lib = _lib.load()
         feats = feats.contiguous()
         w3 = weight.view(1, *weight.shape) if weight.dim() == 2 else weight
-        wk = w3.detach().to(feats.dtype).contiguous()            # [K, c_in, c_out]  (LGS_W_KCN)
-        K, c_in, c_out = wk.shape
+        K, c_in, c_out = w3.shape
+        dt = _dtype_code(feats)
+        if algo == _lib.ALGO_TC3 and dt == _lib.BF16:
+            algo = _lib.ALGO_TC                                   # bf16 features: plain bf16 tensor-core products
         n_in = feats.shape[0]
         n_out = km.n_out if km is not None else n_in
         out = torch.empty((n_out, c_out), dtype=feats.dtype, device=feats.device)
         b32 = bias.detach().float().contiguous().view(-1) if bias is not None else None
-        if algo == _lib.ALGO_TC:
-            w_fwd, layout = wk.transpose(1, 2).contiguous(), _lib.W_KNC   # K-major B operand for the TMA/tcgen05 path
+        need_dgrad = ctx.needs_input_grad[0]
+        # tensor-core operand forms of the weights (one launch); a direction the TC kernels do not take (e.g. c_in = 3)
+        # runs on the exact SIMT kernel with the parameter itself
+        fwd_tc = algo != _lib.ALGO_SIMT and bool(lib.lgs_conv_tc_supported(c_in, c_out, dt))
+        bwd_tc = algo != _lib.ALGO_SIMT and need_dgrad and bool(lib.lgs_conv_tc_supported(c_out, c_in, dt))
+        nsplit = 2 if algo == _lib.ALGO_TC3 else 1
+        w32 = w3.detach().float().contiguous()
+        w_fwd = w_bwd = None
+        if fwd_tc or bwd_tc:
+            if fwd_tc:
+                w_fwd = torch.empty((nsplit, K, c_out, c_in), dtype=feats.dtype, device=feats.device)
+            if bwd_tc:
+                w_bwd = torch.empty((nsplit, K, c_in, c_out), dtype=feats.dtype, device=feats.device)
+            _lib.check(lib.lgs_weight_prep(_lib.ptr(w32), K, c_in, c_out, nsplit, _lib.ptr(w_fwd), _lib.ptr(w_bwd), dt,
+                                           _stream()))
+        tc_layout = _lib.W_KNC_SPLIT if nsplit == 2 else _lib.W_KNC
+        if fwd_tc:
+            wf, layout, a = w_fwd, tc_layout, algo
         else:
-            w_fwd, layout = wk, _lib.W_KCN
+            wf, layout, a = w32.to(feats.dtype), _lib.W_KCN, _lib.ALGO_SIMT
         with _Timed("fwd", K, c_in, c_out, n_in, n_out, km, feats.dtype):
-            _lib.check(lib.lgs_conv_fwd(_lib.ptr(feats), n_in, c_in, _lib.ptr(w_fwd), layout, K, c_out,
+            _lib.check(lib.lgs_conv_fwd(_lib.ptr(feats), n_in, c_in, _lib.ptr(wf), layout, K, c_out,
                                         _lib.ptr(km.fwd_table) if km is not None else None, n_out, 0, _lib.ptr(b32),
-                                        _lib.ptr(out), _dtype_code(feats), algo, _stream()))
-        ctx.save_for_backward(feats, wk)
-        ctx.km, ctx.algo, ctx.w_shape, ctx.w_dtype, ctx.has_bias = km, algo, weight.shape, weight.dtype, bias is not None
+                                        _lib.ptr(out), dt, a, _stream()))
+        if need_dgrad and not bwd_tc:
+            w_bwd = w32.to(feats.dtype)                           # [K, c_in, c_out] read as LGS_W_KNC by the SIMT dgrad
+        ctx.save_for_backward(feats, w_bwd)
+        ctx.km, ctx.algo, ctx.bwd_tc, ctx.tc_layout = km, algo, bwd_tc, tc_layout
+        ctx.dims, ctx.w_shape, ctx.w_dtype, ctx.has_bias = (K, c_in, c_out), weight.shape, weight.dtype, bias is not None
         return out
 
     @staticmethod
     def backward(ctx, gout):
         lib = _lib.load()
-        feats, wk = ctx.saved_tensors
+        feats, w_bwd = ctx.saved_tensors
         km, algo = ctx.km, ctx.algo
         gout = gout.contiguous()
-        K, c_in, c_out = wk.shape
+        K, c_in, c_out = ctx.dims
         n_in, n_out = feats.shape[0], gout.shape[0]
         dt = _dtype_code(feats)
         gin = gw = gb = None
         if ctx.needs_input_grad[0]:
-            # dgrad = the same kernel on the transposed problem; W[k] ([c_in,c_out]) read as LGS_W_KNC needs no copy
+            # dgrad = the same kernel on the transposed problem; W[k] ([c_in,c_out]) is its K-major B operand as is
             gin = torch.empty((n_in, c_in), dtype=feats.dtype, device=feats.device)
+            layout, a = (ctx.tc_layout, algo) if ctx.bwd_tc else (_lib.W_KNC, _lib.ALGO_SIMT)
             with _Timed("dgrad", K, c_out, c_in, n_out, n_in, km, feats.dtype):
-                _lib.check(lib.lgs_conv_fwd(_lib.ptr(gout), n_out, c_out, _lib.ptr(wk), _lib.W_KNC, K, c_in,
+                _lib.check(lib.lgs_conv_fwd(_lib.ptr(gout), n_out, c_out, _lib.ptr(w_bwd), layout, K, c_in,
                                             _lib.ptr(km.bwd_table) if km is not None else None, n_in,
                                             1 if (km is not None and km.bwd_reverse) else 0, None, _lib.ptr(gin), dt,
-                                            algo, _stream()))
+                                            a, _stream()))
         if ctx.needs_input_grad[1]:
             gw = torch.empty((K, c_in, c_out), dtype=torch.float32, device=feats.device)
             with _Timed("wgrad", K, c_in, c_out, n_in, n_out, km, feats.dtype):

@@ -9,7 +9,7 @@ torch.manual_seed(0)
 lib = _lib.load()
 
 def run(algo, feats, w, km, bias=None):
-    return E._SparseConvFn.apply(feats, w, bias, km, _lib.ALGO_TC if algo == "tc" else _lib.ALGO_SIMT)
+    return E._SparseConvFn.apply(feats, w, bias, km, E._ALGO[algo])
 
 def check(name, c, cin, cout, ks=3, dtype=torch.float32, nscale=1.0):
     cc = torch.from_numpy(c).cuda()
@@ -23,17 +23,20 @@ def check(name, c, cin, cout, ks=3, dtype=torch.float32, nscale=1.0):
         w = w.detach().view(cin, cout).requires_grad_(True)
     gy = torch.randn(c.shape[0], cout, device="cuda").to(dtype)
     res = {}
-    for algo in ("simt", "tc"):
+    for algo in ("simt", "tc", "tf32"):
         f.grad = None
         y = run(algo, f, w, km)
         y.backward(gy)
         torch.cuda.synchronize()
         res[algo] = (y.detach().float(), f.grad.detach().float(), w.grad.detach().float().clone())
         w.grad = None
-    e_out = ((res["tc"][0] - res["simt"][0]).abs().max() / res["simt"][0].abs().max()).item()
-    e_gin = ((res["tc"][1] - res["simt"][1]).abs().max() / res["simt"][1].abs().max()).item()
-    e_gw = ((res["tc"][2] - res["simt"][2]).abs().max() / res["simt"][2].abs().max()).item()
-    print(f"{name:28s} n={c.shape[0]:7d} {cin:4d}->{cout:4d} ks={ks} {str(dtype)[6:]:9s} rel err out={e_out:.2e} dgrad={e_gin:.2e} wgrad={e_gw:.2e}", flush=True)
+    msg = ""
+    for a in ("tc", "tf32"):
+        e_out = ((res[a][0] - res["simt"][0]).abs().max() / res["simt"][0].abs().max()).item()
+        e_gin = ((res[a][1] - res["simt"][1]).abs().max() / res["simt"][1].abs().max()).item()
+        e_gw = ((res[a][2] - res["simt"][2]).abs().max() / res["simt"][2].abs().max()).item()
+        msg += f" | {a}: out={e_out:.1e} dgrad={e_gin:.1e} wgrad={e_gw:.1e}"
+    print(f"{name:14s} n={c.shape[0]:7d} {cin:4d}->{cout:4d} ks={ks} {str(dtype)[6:]:8s}{msg}", flush=True)
     return km, f, w
 
 rng = np.random.default_rng(0)
@@ -51,7 +54,7 @@ c, _, _ = scenes.synthetic_voxel_scene(0, 150000)
 for cin, cout, dtype in [(96, 96, torch.float32), (128, 96, torch.float32), (32, 32, torch.float32), (96, 96, torch.bfloat16)]:
     km, f, w = check("scene150k", c, cin, cout, dtype=dtype)
     P = int(km.counts.sum().item())
-    for algo in ("simt", "tc"):
+    for algo in ("simt", "tc", "tf32"):
         with torch.no_grad():
             for _ in range(3):
                 run(algo, f, w, km)
@@ -67,7 +70,7 @@ for cin, cout, dtype in [(96, 96, torch.float32), (128, 96, torch.float32), (32,
         byts = P * (cin + cout) * s + 8 * P + 27 * cin * cout * s
         print(f"   {algo:5s} fwd {ms:8.3f} ms  {2*P*cin*cout/ms/1e9:8.2f} TFLOP/s  gather-model {byts/ms/1e6:8.1f} GB/s  (P={P})", flush=True)
         gw = torch.empty(27, cin, cout, device="cuda")
-        a = _lib.ALGO_TC if algo == "tc" else _lib.ALGO_SIMT
+        a = E._ALGO[algo]
         fd, gyd = f.detach().contiguous(), torch.randn(c.shape[0], cout, device="cuda").to(dtype)
         st = E._stream()
         def wg():

@@ -1,7 +1,9 @@
 """-m gpu: sparse convolution forward / dgrad / wgrad of the CUDA engine vs the oracle (same seeded inputs).
-Tolerances: LGS_ALGO_SIMT is fp32 FMA -> 2e-5 relative (summation order only);
-            LGS_ALGO_TC uses TF32 tensor cores -> 2e-3 relative per layer (north_star's 1e-3 is on whole-net logits,
-            checked in test_gpu_nets.py)."""
+Tolerances (max-norm relative error per layer):
+  'simt'  fp32 FMA                               2e-5  (summation order only)
+  'tc'    tcgen05 3xTF32 (default)               2e-4  fwd/dgrad (measured ~1e-5); wgrad is single-pass TF32 -> 2e-3
+  'tf32'  tcgen05 single-pass TF32 (fast mode)   2e-3
+north_star's 1e-3 bound is on whole-network logits and is checked in test_gpu_nets.py."""
 import numpy as np
 import pytest
 import torch
@@ -10,7 +12,9 @@ from tests.helpers import random_sparse_coords, rel_err
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"simt": 2e-5, "tc": 2e-3}
+TOL = {"simt": 2e-5, "tc": 2e-4, "tf32": 2e-3}
+TOL_GW = {"simt": 2e-5, "tc": 2e-3, "tf32": 2e-3}
+ALGOS = ["simt", "tc", "tf32"]
 
 
 @pytest.fixture(scope="module")
@@ -63,7 +67,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("algo", ["simt", "tc"])
+@pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("cin,cout,ks,stride,transpose,bias", CASES)
 def test_conv_layer_parity(E, algo, cin, cout, ks, stride, transpose, bias):
     rng = np.random.default_rng(cin * 1000 + cout)
@@ -74,12 +78,12 @@ def test_conv_layer_parity(E, algo, cin, cout, ks, stride, transpose, bias):
     tol = TOL[algo]
     assert rel_err(g["out"], o["out"]) < tol
     assert rel_err(g["gin"], o["gin"]) < tol
-    assert rel_err(g["gw"], o["gw"]) < tol
+    assert rel_err(g["gw"], o["gw"]) < TOL_GW[algo]
     if bias:
-        assert rel_err(g["gb"], o["gb"]) < tol
+        assert rel_err(g["gb"], o["gb"]) < 2e-5
 
 
-@pytest.mark.parametrize("algo", ["simt", "tc"])
+@pytest.mark.parametrize("algo", ALGOS)
 def test_conv_kats(E, algo):
     """closed-form answers through the CUDA path"""
     from tests.helpers import dense_cube
@@ -116,7 +120,7 @@ def test_conv_kats(E, algo):
         assert torch.equal(out, exp), k
 
 
-@pytest.mark.parametrize("algo", ["simt", "tc"])
+@pytest.mark.parametrize("algo", ALGOS)
 def test_linearity_full_size(E, algo):
     """size-independent property at BASELINE config-2 size: conv(a*x + y) == a*conv(x) + conv(y)"""
     from languagegroundedsemseg_b200 import scenes
@@ -131,7 +135,7 @@ def test_linearity_full_size(E, algo):
         mgr = xa.coordinate_manager
         mk = lambda f: E.SparseTensor(f, coordinate_map_key=xa.coordinate_map_key, coordinate_manager=mgr)
         ya, yb, yab = conv(xa).F, conv(mk(b)).F, conv(mk(2 * a + b)).F
-    assert rel_err(yab, 2 * ya + yb) < (1e-5 if algo == "simt" else 3e-3)
+    assert rel_err(yab, 2 * ya + yb) < {"simt": 1e-5, "tc": 2e-4, "tf32": 3e-3}[algo]
     # isolated-voxel property: rows with no neighbours other than themselves equal F @ W[13]
     t = mgr.kernel_map(xa.coordinate_map_key, xa.coordinate_map_key, [3, 3, 3], [1, 1, 1]).fwd_table
     iso = torch.nonzero((t >= 0).sum(0) == 1).squeeze(1)
@@ -150,7 +154,7 @@ def test_bf16_features(E):
     km = x.coordinate_manager.kernel_map(x.coordinate_map_key, x.coordinate_map_key, [3, 3, 3], [1, 1, 1])
     ref = me_cpu.sparse_conv(x.F, w.bfloat16().float(), km, c.shape[0])
     for algo in ("simt", "tc"):
-        E.set_conv_algo(algo)
+        E.set_conv_algo(algo)   # bf16 features: 'tc' = bf16 tensor-core products, fp32 accumulate
         g = E.SparseTensor(f.cuda().bfloat16(), torch.from_numpy(c).cuda())
         gk = g.coordinate_manager.kernel_map(g.coordinate_map_key, g.coordinate_map_key, [3, 3, 3], [1, 1, 1])
         out = E.sparse_conv(g.F, w.cuda(), None, gk)
