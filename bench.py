@@ -145,7 +145,8 @@ def run_engine(args, rank, world, local_rank):
     E.set_conv_algo(args.algo)
     fdtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
 
-    coords_np, feats_np, labels_np = make_scene(seed=rank)
+    from languagegroundedsemseg_b200.ddp import shard_scenes
+    coords_np, feats_np, labels_np = make_scene(seed=shard_scenes(world, world, rank)[0])   # one scene per rank
     n_vox = coords_np.shape[0]
     # host (pinned) copies for the e2e leg; device-resident copies for `value`
     h_coords = torch.from_numpy(coords_np).pin_memory()
@@ -157,10 +158,8 @@ def run_engine(args, rank, world, local_rank):
     if args.dtype == "bf16":
         # bf16 features; parameters stay fp32 (master weights), BN in fp32 statistics via autocast-free mixed dtype
         pass
-    model = net
-    if world > 1:
-        from torch.nn.parallel import DistributedDataParallel as DDP
-        model = DDP(net, device_ids=[local_rank], find_unused_parameters=False, gradient_as_bucket_view=True)
+    from languagegroundedsemseg_b200 import ddp
+    model = ddp.wrap_ddp(net, local_rank)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -375,10 +374,8 @@ def main():
         return 0
 
     if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from languagegroundedsemseg_b200 import ddp
+        ddp.init_process_group("nccl")
     res = run_engine(args, rank, world, local_rank)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
