@@ -264,6 +264,16 @@ def run_engine(args, rank, world, local_rank):
         d[1] += by
         d[2] += fl
         d[3] += 1
+    if os.environ.get("LGS_BENCH_LAYERS"):
+        per = {}
+        for meta, (a, b) in prof:
+            kind, K, ci, co, n_in, n_out = meta[:6]
+            d = per.setdefault((kind, K, ci, co, n_out), [0.0, 0])
+            d[0] += a.elapsed_time(b) / PROF_STEPS
+            d[1] += 1
+        for key, (t, c) in sorted(per.items(), key=lambda kv: -kv[1][0])[:40]:
+            print(f"LAYER {key[0]:6s} K={key[1]:2d} {key[2]:4d}->{key[3]:4d} n_out={key[4]:7d} launches/step={c // PROF_STEPS:3d} "
+                  f"ms/step={t:7.3f}", file=sys.stderr)
     step_flops = sum(v[2] for v in agg.values()) / PROF_STEPS
     step_bytes = sum(v[1] for v in agg.values()) / PROF_STEPS
     conv_ms, conv_bytes, conv_flops, conv_n = agg.get("conv", [1e-9, 0, 0, 1])

@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -135,23 +136,43 @@ struct Params {
   int32_t stages;
   int32_t tmem_cols;
   int32_t b_stage_bytes;    // n_tile * 128
+  int32_t k_per_split;      // offsets handled by one CTA (blockIdx.z selects the range); < K => partial sums, red.add
+  int32_t k_splits;
 };
 
 // PRECISE (fp32 features only): 3xTF32 error-compensated product.  Four extra warps split every landed A tile into
 // hi = tf32-truncated value (rewritten in place) and lo = a - hi (second tile); the weights arrive pre-split (hi, lo
 // stacked, see lgs_weight_prep); three MMAs per K step accumulate hi*hi + lo*hi + hi*lo, i.e. fp32-grade products
 // (relative error ~2^-21) with fp32 accumulation in TMEM.
+//
+// The hot loops are written for ONE warp per SM sub-partition (no latency hiding by other warps): everything that does
+// not change per stage is hoisted — row pointers once per offset, destination offsets once per thread, descriptor
+// high words once per kernel, stage index / phase carried incrementally (no division).
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <bool BF16, bool PRECISE>
 __global__ void __launch_bounds__(PRECISE ? THREADS + 128 : THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x (A 16 KB | B n_tile*128)] [idx K*128 int32] [klist 32] [barriers] [tmem ptr]
+  // carve: [stages x ([A hi | A lo] [B hi | B lo])] [idx K*128 int32] [klist 32] [kflag 32] [barriers] [tmem ptr]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int NSPLIT = PRECISE ? 2 : 1;
   constexpr int NTHREADS = PRECISE ? THREADS + 128 : THREADS;
-  const int stage_bytes = NSPLIT * (A_STAGE_BYTES + p.b_stage_bytes);   // [A hi | A lo] [B hi | B lo]
-  int32_t* sidx = reinterpret_cast<int32_t*>(smem + size_t(p.stages) * stage_bytes);
-  int32_t* klist = sidx + p.K * BM;
+  const int stages = p.stages;
+  const uint32_t stage_bytes = NSPLIT * (A_STAGE_BYTES + p.b_stage_bytes);
+  int32_t* sidx = reinterpret_cast<int32_t*>(smem + size_t(stages) * stage_bytes);
+  int32_t* klist = sidx + p.k_per_split * BM;
   int32_t* kflag = klist + 32;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(kflag + 32);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
@@ -162,18 +183,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t m0 = int64_t(blockIdx.x) * BM;
-  const int n0 = blockIdx.y * 256;
+  const int n0 = blockIdx.y * p.n_tile;
+  // split-K over kernel offsets for small coordinate maps: this CTA owns offsets [kbeg, kbeg + kcnt)
+  const int kbeg = blockIdx.z * p.k_per_split;
+  const int kcnt = min(p.k_per_split, p.K - kbeg);
+  const bool partial = p.k_splits > 1;
+  const uint32_t smem_base = smem_u32(smem);
 
-  // ---- prologue -----------------------------------------------------------------------------------------
-  for (int e = tid; e < p.K * BM; e += NTHREADS) {
-    const int k = e / BM, r = e - k * BM;
-    const int64_t o = m0 + r;
-    int32_t v = -1;
-    if (o < p.n_out) v = p.table ? __ldg(p.table + int64_t(p.reverse_k ? p.K - 1 - k : k) * p.n_out + o) : int32_t(o);
-    sidx[e] = v;
+  // ---- prologue: neighbour table of this tile -> shared memory (async, all offsets in flight at once) ----
+  {
+    const int64_t rows_valid = (p.n_out - m0) < int64_t(BM) ? (p.n_out - m0) : int64_t(BM);
+    for (int e = tid; e < kcnt * BM; e += NTHREADS) {
+      const int k = kbeg + (e >> 7), r = e & (BM - 1);
+      if (r < rows_valid && p.table) {
+        cp_async4(smem_u32(sidx + e), p.table + int64_t(p.reverse_k ? p.K - 1 - k : k) * p.n_out + m0 + r);
+      } else {
+        sidx[e] = r < rows_valid ? int32_t(m0 + r) : -1;
+      }
+    }
   }
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) {
+    for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar + s, 128 + 1);
       mbar_init(empty_bar + s, 1);
       mbar_init(split_bar + s, 128);
@@ -187,12 +217,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp == 5 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
-  }
+  if (warp == 5 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+  cp_async_wait_all();
   __syncthreads();
   // which offsets have any neighbour in this tile
-  for (int k = warp; k < p.K; k += NTHREADS / 32) {
+  for (int k = warp; k < kcnt; k += NTHREADS / 32) {
     bool any = false;
 #pragma unroll
     for (int j = 0; j < BM / 32; ++j) any |= sidx[k * BM + lane + 32 * j] >= 0;
@@ -204,40 +233,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
   tc_fence_after();
   if (tid == 0) {
     int nk = 0;
-    for (int k = 0; k < p.K; ++k)
-      if (kflag[k]) klist[nk++] = k;
+    for (int k = 0; k < kcnt; ++k)
+      if (kflag[k]) klist[nk++] = k;   // local offset index; the weight block is kbeg + k
     *nk_smem = nk;
   }
   __syncthreads();
   const int nk = *nk_smem;
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const int total = nk * p.num_kb;
+  const int num_kb = p.num_kb;
+  const int total = nk * num_kb;
 
   if (warp < 4) {
     // =================================== gather producers ===================================
     const int chunk = tid & 7, rbase = tid >> 3;  // 8 lanes cover one 128-byte row segment; 16 rows per pass
-    int it = 0;
-    for (int a = 0; a < nk; ++a) {
-      const int k = klist[a];
-      const int32_t* idx = sidx + k * BM;
-      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(empty_bar + s, ph ^ 1);
-        const uint32_t a_base = smem_u32(smem + size_t(s) * stage_bytes);
-        const int col = kb * KBLOCK_BYTES + chunk * 16;
-        const bool col_ok = col < p.row_bytes;
+    uint32_t dst_off[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = rbase + 16 * i;
-          const int32_t src_row = idx[r];
-          const bool ok = col_ok && src_row >= 0;
-          const uint8_t* src = ok ? p.in + size_t(src_row) * p.row_bytes + col : p.in;
-          cp_async16(a_base + r * KBLOCK_BYTES + ((chunk ^ (r & 7)) << 4), src, ok ? 16u : 0u);
-        }
+    for (int i = 0; i < 8; ++i) {
+      const int r = rbase + 16 * i;
+      dst_off[i] = uint32_t(r * KBLOCK_BYTES + ((chunk ^ (r & 7)) << 4));
+    }
+    const int row_bytes = p.row_bytes;
+    const uint8_t* in_chunk = p.in + chunk * 16;
+    int s = 0;
+    uint32_t ph = 0;
+    uint32_t a_base = smem_base;
+    for (int a = 0; a < nk; ++a) {
+      const int32_t* idx = sidx + klist[a] * BM + rbase;
+      const uint8_t* src[8];
+      uint32_t okmask = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int32_t row = idx[16 * i];
+        okmask |= (row >= 0 ? 1u : 0u) << i;
+        src[i] = in_chunk + size_t(row >= 0 ? row : 0) * row_bytes;
+      }
+      int col = chunk * 16;
+      for (int kb = 0; kb < num_kb; ++kb, col += KBLOCK_BYTES) {
+        mbar_wait(empty_bar + s, ph ^ 1);
+        const uint32_t m = col < row_bytes ? okmask : 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cp_async16(a_base + dst_off[i], src[i] + kb * KBLOCK_BYTES, ((m >> i) & 1u) ? 16u : 0u);
         // hardware arrives on full[s] when this thread's copies have landed: nothing blocks, every free stage of the
         // ring is in flight.  The generic->async proxy fence is issued by the consumer after it observes the barrier.
         cp_async_mbar_arrive_noinc(full_bar + s);
+        a_base += stage_bytes;
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+          a_base = smem_base;
+        }
       }
     }
 
@@ -248,7 +292,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
     }
     const int64_t o = m0 + warp * 32 + lane;
     const int ncols = min(p.n_tile, p.c_out - n0);
-    for (int c0 = 0; c0 < ncols; c0 += 32) {
+    const float* bias = (partial && blockIdx.z != 0) ? nullptr : p.bias;
+    for (int c0 = 0; c0 < ((partial && total == 0) ? 0 : ncols); c0 += 32) {
       uint32_t v[32];
       if (total > 0) {
         tmem_ld32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(c0), v);
@@ -262,11 +307,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             if (c0 + j + 1 < ncols) {
-              const float x0 = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
-              const float x1 = __uint_as_float(v[j + 1]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 1) : 0.f);
+              const float x0 = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + c0 + j) : 0.f);
+              const float x1 = __uint_as_float(v[j + 1]) + (bias ? __ldg(bias + n0 + c0 + j + 1) : 0.f);
               *reinterpret_cast<__nv_bfloat162*>(orow + j) = __floats2bfloat162_rn(x0, x1);
             } else if (c0 + j < ncols) {
-              orow[j] = __float2bfloat16(__uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f));
+              orow[j] = __float2bfloat16(__uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + c0 + j) : 0.f));
             }
           }
         } else {
@@ -275,14 +320,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
           for (int j = 0; j < 32; j += 4) {
             if (c0 + j + 3 < ncols) {
               float4 x;
-              x.x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
-              x.y = __uint_as_float(v[j + 1]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 1) : 0.f);
-              x.z = __uint_as_float(v[j + 2]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 2) : 0.f);
-              x.w = __uint_as_float(v[j + 3]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 3) : 0.f);
-              *reinterpret_cast<float4*>(orow + j) = x;
+              x.x = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + c0 + j) : 0.f);
+              x.y = __uint_as_float(v[j + 1]) + (bias ? __ldg(bias + n0 + c0 + j + 1) : 0.f);
+              x.z = __uint_as_float(v[j + 2]) + (bias ? __ldg(bias + n0 + c0 + j + 2) : 0.f);
+              x.w = __uint_as_float(v[j + 3]) + (bias ? __ldg(bias + n0 + c0 + j + 3) : 0.f);
+              if (partial) red_add_v4(orow + j, x.x, x.y, x.z, x.w);
+              else *reinterpret_cast<float4*>(orow + j) = x;
             } else {
               for (int jj = j; jj < j + 4; ++jj)
-                if (c0 + jj < ncols) orow[jj] = __uint_as_float(v[jj]) + (p.bias ? __ldg(p.bias + n0 + c0 + jj) : 0.f);
+                if (c0 + jj < ncols) {
+                  const float x1 = __uint_as_float(v[jj]) + (bias ? __ldg(bias + n0 + c0 + jj) : 0.f);
+                  if (partial) atomicAdd(orow + jj, x1);
+                  else orow[jj] = x1;
+                }
             }
           }
         }
@@ -295,28 +345,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
       // instruction descriptor: D fp32, A/B tf32 (or bf16), both K-major, N = n_tile, M = 128
       const uint32_t fmt = BF16 ? 1u : 2u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(p.n_tile >> 3) << 17) | (uint32_t(BM >> 4) << 24);
-      int it = 0;
+      // shared-memory descriptor: hi word constant (SBO 1024 B, version 1, SWIZZLE_128B); lo word = addr>>4 | LBO(1)<<16
+      const uint32_t desc_hi = uint32_t(1024 >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t b_off = NSPLIT * A_STAGE_BYTES;
+      const int row_bytes = p.row_bytes;
+      int s = 0;
+      uint32_t ph = 0, first = 0;
+      uint32_t a_base = smem_base;
       for (int a = 0; a < nk; ++a) {
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + s, ph);          // gathered rows (cp.async) and weights (TMA) have landed
           if constexpr (PRECISE) mbar_wait(split_bar + s, ph);   // ... and the hi/lo split of A is done
           fence_proxy_async();  // generic-proxy writes (cp.async / splitters) -> visible to the tensor core's reads
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + size_t(s) * stage_bytes);
-          const uint32_t b_base = a_base + NSPLIT * A_STAGE_BYTES;
-          const int valid = min(KBLOCK_BYTES, p.row_bytes - kb * KBLOCK_BYTES);
-          const int ksteps = (valid + 31) / 32;  // 32 bytes of K per instruction (8 tf32 / 16 bf16)
+          const int valid = min(KBLOCK_BYTES, row_bytes - kb * KBLOCK_BYTES);
+          const int ksteps = (valid + 31) >> 5;  // 32 bytes of K per instruction (8 tf32 / 16 bf16)
+          const uint32_t a_lo32 = ((a_base >> 4) & 0x3FFF) | (1u << 16);
+          const uint32_t b_lo32 = (((a_base + b_off) >> 4) & 0x3FFF) | (1u << 16);
+#pragma unroll 4
           for (int j = 0; j < ksteps; ++j) {
-            const uint64_t a_hi = make_kmajor_sw128_desc(a_base + j * 32), b_hi = make_kmajor_sw128_desc(b_base + j * 32);
-            umma<BF16>(tmem_base, a_hi, b_hi, idesc, (it > 0 || j > 0) ? 1u : 0u);
+            const uint64_t a_hi = desc_from(a_lo32 + 2 * j, desc_hi), b_hi = desc_from(b_lo32 + 2 * j, desc_hi);
+            umma<BF16>(tmem_base, a_hi, b_hi, idesc, first | uint32_t(j));
             if constexpr (PRECISE) {
-              umma<BF16>(tmem_base, make_kmajor_sw128_desc(a_base + A_STAGE_BYTES + j * 32), b_hi, idesc, 1u);
-              umma<BF16>(tmem_base, a_hi, make_kmajor_sw128_desc(b_base + p.b_stage_bytes + j * 32), idesc, 1u);
+              umma<BF16>(tmem_base, desc_from(a_lo32 + (A_STAGE_BYTES >> 4) + 2 * j, desc_hi), b_hi, idesc, 1u);
+              umma<BF16>(tmem_base, a_hi, desc_from(b_lo32 + (p.b_stage_bytes >> 4) + 2 * j, desc_hi), idesc, 1u);
             }
           }
+          first = 1;
           umma_commit(empty_bar + s);  // frees the stage once these MMAs have read it
+          a_base += stage_bytes;
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+            a_base = smem_base;
+          }
         }
       }
       if (total > 0) umma_commit(acc_bar);
@@ -326,18 +388,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
     // =================================== weight TMA producer (one thread) ===================================
     if (lane == 0) {
       const int kelems = KBLOCK_BYTES / (BF16 ? 2 : 4);
-      int it = 0;
+      const uint32_t b_off = NSPLIT * A_STAGE_BYTES;
+      const uint32_t tx = NSPLIT * p.b_stage_bytes;
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t b_dst = smem_base + b_off;
       for (int a = 0; a < nk; ++a) {
-        const int k = klist[a];
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        const int row = (kbeg + klist[a]) * p.c_out + n0;
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + s, ph ^ 1);
-          mbar_expect_tx(full_bar + s, uint32_t(NSPLIT * p.b_stage_bytes));
-          const uint32_t b_dst = smem_u32(smem + size_t(s) * stage_bytes + NSPLIT * A_STAGE_BYTES);
-          tma_load_2d(b_dst, &tmap_w, full_bar + s, kb * kelems, k * p.c_out + n0);
+          mbar_expect_tx(full_bar + s, tx);
+          tma_load_2d(b_dst, &tmap_w, full_bar + s, kb * kelems, row);
           if constexpr (PRECISE)   // lo halves are stacked after the K*c_out hi rows
-            tma_load_2d(b_dst + p.b_stage_bytes, &tmap_w, full_bar + s, kb * kelems, (p.K + k) * p.c_out + n0);
+            tma_load_2d(b_dst + p.b_stage_bytes, &tmap_w, full_bar + s, kb * kelems, p.K * p.c_out + row);
+          b_dst += stage_bytes;
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+            b_dst = smem_base + b_off;
+          }
         }
       }
     }
@@ -347,30 +416,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
     if (warp >= 6) {
       // =================================== hi/lo splitters (128 threads) ===================================
       const int st = tid - THREADS;
+      int s = 0;
+      uint32_t ph = 0;
+      uint8_t* a_ptr = smem;
       for (int it = 0; it < total; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
         mbar_wait(full_bar + s, ph);
-        float4* a_hi = reinterpret_cast<float4*>(smem + size_t(s) * stage_bytes);
-        float4* a_lo = reinterpret_cast<float4*>(smem + size_t(s) * stage_bytes + A_STAGE_BYTES);
+        float4* a_hi = reinterpret_cast<float4*>(a_ptr) + st;
+        float4* a_lo = reinterpret_cast<float4*>(a_ptr + A_STAGE_BYTES) + st;
+        float4 v[8];
 #pragma unroll
-        for (int i = 0; i < A_STAGE_BYTES / 16 / 128; ++i) {
-          const int e = st + 128 * i;
-          const float4 v = a_hi[e];
+        for (int i = 0; i < 8; ++i) v[i] = a_hi[128 * i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
           float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-          l.x = v.x - h.x;
-          l.y = v.y - h.y;
-          l.z = v.z - h.z;
-          l.w = v.w - h.w;
-          a_hi[e] = h;
-          a_lo[e] = l;
+          h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
+          l.x = v[i].x - h.x;
+          l.y = v[i].y - h.y;
+          l.z = v[i].z - h.z;
+          l.w = v[i].w - h.w;
+          a_hi[128 * i] = h;
+          a_lo[128 * i] = l;
         }
         fence_proxy_async();
         mbar_arrive(split_bar + s);
+        a_ptr += stage_bytes;
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+          a_ptr = smem;
+        }
       }
     }
   }
@@ -496,25 +573,52 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
   p.bias = bias;
   p.out = out;
   p.num_kb = (row_bytes + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
-  const int n_tiles = (c_out + 255) / 256;
   const int c_pad = ((c_out + 15) / 16) * 16;
+  const int64_t m_tiles = cdiv(n_out, BM);
+  // Work decomposition.  Large maps: one CTA per 128-row tile (all offsets, all channels <= 256) — deterministic,
+  // no atomics.  Small maps (fewer tiles than SMs; the coarse U-Net levels, where the WEIGHTS are the traffic):
+  // split the kernel offsets (and, if still short, the output channels) over CTAs; partial sums meet in global memory
+  // through red.add on a zeroed output.
+  int n_tiles = (c_out + 255) / 256;
   p.n_tile = n_tiles == 1 ? c_pad : 256;
-  if (n_tiles > 1 && c_out % 256 != 0) {
+  int k_splits = 1;
+  if (m_tiles * n_tiles <= 74) {
+    int want = int(cdiv(148, m_tiles * n_tiles));
+    if (dtype == LGS_F32 && K > 1) {
+      k_splits = want < K ? want : K;
+      want = int(cdiv(want, k_splits));
+    }
+    if (want > 1 && n_tiles == 1 && c_pad >= 128) {   // split channels too (N >= 64 per CTA)
+      int ns = c_pad / 64;
+      if (ns > want) ns = want;
+      while (ns > 1 && (c_pad % (ns * 16)) != 0) --ns;
+      if (ns > 1) {
+        p.n_tile = c_pad / ns;
+        n_tiles = ns;
+      }
+    }
+  }
+  if (n_tiles > 1 && c_out % p.n_tile != 0 && p.n_tile == 256) {
     // keep every N tile the same width: only multiples of 256 beyond 256 channels
     return LGS_E_UNSUPPORTED;
   }
+  p.k_per_split = (K + k_splits - 1) / k_splits;
+  k_splits = (K + p.k_per_split - 1) / p.k_per_split;
+  p.k_splits = k_splits;
   p.b_stage_bytes = p.n_tile * KBLOCK_BYTES;
   int cols = 32;
   while (cols < p.n_tile) cols <<= 1;
   p.tmem_cols = cols;
   const int stage_bytes = nsplit * (A_STAGE_BYTES + p.b_stage_bytes);
-  const int fixed = K * BM * 4 + 64 * 4 + (3 * MAX_STAGES + 1) * 8 + 16 + 1024;  // idx + klist/kflag + barriers + align
+  const int fixed = p.k_per_split * BM * 4 + 64 * 4 + (3 * MAX_STAGES + 1) * 8 + 16 + 1024;  // idx, lists, barriers, align
   int stages = (100 * 1024 - fixed) / stage_bytes;            // try to leave room for two CTAs per SM
   if (stages < MIN_STAGES + 1) stages = (227 * 1024 - fixed) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (const char* e = getenv("LGS_TC_STAGES")) { const int v = atoi(e); if (v >= 2 && v < stages) stages = v; }  // tuning knob
   if (stages < (precise ? 2 : MIN_STAGES)) return LGS_E_UNSUPPORTED;
   p.stages = stages;
   const size_t smem_bytes = size_t(stages) * stage_bytes + fixed;
+  if (k_splits > 1) LGS_CUDA(cudaMemsetAsync(out, 0, size_t(n_out) * c_out * sizeof(float), stream));
 
   // tensor map over W^T viewed as [K * c_out rows, c_in] with box {128 B of channels, n_tile rows}, 128B swizzle
   CUtensorMap tmap;
@@ -539,7 +643,7 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
   });
   if (attr_err != cudaSuccess) return fail(LGS_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
 
-  dim3 grid(unsigned(cdiv(n_out, BM)), unsigned(n_tiles));
+  const dim3 grid{unsigned(m_tiles), unsigned(n_tiles), unsigned(k_splits)};
   if (dtype == LGS_BF16) {
     LGS_LAUNCH((conv_tc_kernel<true, false>), grid, THREADS, smem_bytes, stream, tmap, p);
   } else if (precise) {
@@ -604,10 +708,6 @@ __device__ __forceinline__ uint32_t mn_chunk_pos(uint32_t c, uint32_t r) {
   return ((((c >> 1) ^ (r & 3)) << 1) | (c & 1));
 }
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 template <bool BF16>
 __global__ void __launch_bounds__(THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
@@ -661,35 +761,44 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
     // =================================== gather producers ===================================
     const int chunk = tid & 7, rbase = tid >> 3;
     const int passes = p.R / 16;
-    int it = 0;
+    uint32_t dst_off[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = rbase + 16 * i;
+      dst_off[i] = uint32_t(r * KBLOCK_BYTES) + (mn_chunk_pos<BF16>(chunk, r) << 4);
+    }
+    const int row_bytes = p.in_row_bytes;
+    const uint8_t* in_chunk = p.in + chunk * 16;
+    const uint32_t a_smem_base = smem_u32(a_smem);
+    int s = 0;
+    uint32_t ph = 0;
     for (int t = 0; t < n_tiles; ++t) {
-      const int64_t row0 = r_begin + int64_t(t) * p.R;
-      for (int g = 0; g < g_count; ++g, ++it) {
-        const int s = it & (A_STAGES - 1);
-        const uint32_t ph = (it / A_STAGES) & 1;
+      const int64_t row0 = r_begin + int64_t(t) * p.R + rbase;
+      for (int g = 0; g < g_count; ++g) {
         const int32_t* trow = p.table ? p.table + int64_t(k0 + g) * p.n_out : nullptr;
-        int32_t src_rows[8];
+        const uint8_t* src[8];
+        uint32_t okmask = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int64_t o = row0 + rbase + 16 * i;
-          src_rows[i] = (i < passes && o < r_end) ? (trow ? __ldg(trow + o) : int32_t(o)) : -1;
+          const int64_t o = row0 + 16 * i;
+          const int32_t row = (i < passes && o < r_end) ? (trow ? __ldg(trow + o) : int32_t(o)) : -1;
+          okmask |= (row >= 0 ? 1u : 0u) << i;
+          src[i] = in_chunk + size_t(row >= 0 ? row : 0) * row_bytes;
         }
         mbar_wait(aempty + s, ph ^ 1);
-        const uint32_t a_base = smem_u32(a_smem + size_t(s) * a_stage_bytes);
-        for (int kb = 0; kb < p.nb_in; ++kb) {
-          const int col = kb * KBLOCK_BYTES + chunk * 16;
-          const bool col_ok = col < p.in_row_bytes;
+        uint32_t a_base = a_smem_base + uint32_t(s) * uint32_t(a_stage_bytes);
+        int col = chunk * 16;
+        for (int kb = 0; kb < p.nb_in; ++kb, col += KBLOCK_BYTES, a_base += blk_bytes) {
+          const uint32_t m = col < row_bytes ? okmask : 0u;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (i < passes) {
-              const int r = rbase + 16 * i;
-              const bool ok = col_ok && src_rows[i] >= 0;
-              const uint8_t* src = ok ? p.in + size_t(src_rows[i]) * p.in_row_bytes + col : p.in;
-              cp_async16(a_base + kb * blk_bytes + r * KBLOCK_BYTES + (mn_chunk_pos<BF16>(chunk, r) << 4), src, ok ? 16u : 0u);
-            }
-          }
+          for (int i = 0; i < 8; ++i)
+            if (i < passes) cp_async16(a_base + dst_off[i], src[i] + kb * KBLOCK_BYTES, ((m >> i) & 1u) ? 16u : 0u);
         }
         cp_async_mbar_arrive_noinc(afull + s);
+        if (++s == A_STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
       }
     }
     // =================================== epilogue: TMEM -> red.add into dW ===================================
@@ -729,28 +838,36 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
                              (uint32_t(p.n_cols >> 3) << 17) | (uint32_t(m_dim >> 4) << 24);
       const int rows_per_mma = BF16 ? 16 : 8;
       const int mmas = p.R / rows_per_mma;
-      const int mma_stride = rows_per_mma * KBLOCK_BYTES;           // bytes of one K step (8 or 16 rows)
+      const uint32_t mma_step16 = uint32_t(rows_per_mma * KBLOCK_BYTES) >> 4;   // K step (8 or 16 rows) in 16-byte units
       const int mc_blocks = 128 * (BF16 ? 2 : 4) / KBLOCK_BYTES;     // channel blocks per 128-lane chunk (4 fp32 / 2 bf16)
-      int it = 0;
+      // MN-major descriptor: hi word constant (SBO, version, layout); lo word = addr>>4 | (LBO>>4)<<16
+      const uint32_t desc_hi = uint32_t((BF16 ? 1024 : 512) >> 4) | (1u << 14) | (uint32_t(BF16 ? 2 : 1) << 29);
+      const uint32_t lbo16 = (uint32_t(blk_bytes) >> 4) << 16;
+      const uint32_t a_smem_base = smem_u32(a_smem), b_smem_base = smem_u32(b_smem);
+      int s = 0;
+      uint32_t ph = 0;
       for (int t = 0; t < n_tiles; ++t) {
         const int bs = t & 1;
         mbar_wait(bfull + bs, (t >> 1) & 1);
-        const uint32_t b_base = smem_u32(b_smem + size_t(bs) * b_buf_bytes);
-        for (int g = 0; g < g_count; ++g, ++it) {
-          const int s = it & (A_STAGES - 1);
-          mbar_wait(afull + s, (it / A_STAGES) & 1);
+        const uint32_t b_lo32 = (((b_smem_base + uint32_t(bs) * uint32_t(b_buf_bytes)) >> 4) & 0x3FFF) | lbo16;
+        for (int g = 0; g < g_count; ++g) {
+          mbar_wait(afull + s, ph);
           fence_proxy_async();
           tc_fence_after();
-          const uint32_t a_base = smem_u32(a_smem + size_t(s) * a_stage_bytes);
+          const uint32_t a_base = a_smem_base + uint32_t(s) * uint32_t(a_stage_bytes);
           for (int mc = 0; mc < p.MC; ++mc) {
             const uint32_t d_addr = tmem_base + uint32_t((g * p.MC + mc) * p.n_cols);
-            const uint32_t a_mc = a_base + mc * mc_blocks * blk_bytes;
-            for (int j = 0; j < mmas; ++j) {
-              umma<BF16>(d_addr, make_mnmajor_desc<BF16>(a_mc + j * mma_stride, blk_bytes),
-                         make_mnmajor_desc<BF16>(b_base + j * mma_stride, blk_bytes), idesc, (t > 0 || j > 0) ? 1u : 0u);
-            }
+            const uint32_t a_lo32 = (((a_base + uint32_t(mc * mc_blocks) * uint32_t(blk_bytes)) >> 4) & 0x3FFF) | lbo16;
+#pragma unroll 4
+            for (int j = 0; j < mmas; ++j)
+              umma<BF16>(d_addr, desc_from(a_lo32 + j * mma_step16, desc_hi), desc_from(b_lo32 + j * mma_step16, desc_hi),
+                         idesc, (t > 0 || j > 0) ? 1u : 0u);
           }
           umma_commit(aempty + s);
+          if (++s == A_STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
         }
         umma_commit(bempty + bs);
       }

@@ -391,12 +391,20 @@ class _SparseConvFn(torch.autograd.Function):
         out = torch.empty((n_out, c_out), dtype=feats.dtype, device=feats.device)
         b32 = bias.detach().float().contiguous().view(-1) if bias is not None else None
         need_dgrad = ctx.needs_input_grad[0]
+        w32 = w3.detach().float().contiguous()
+        # A tiny channel count (the 3 colour channels of conv0p1s1) is zero-padded to a 16-byte row so that the layer
+        # takes the tensor-core kernels; the padded weight rows are zero and the padded gradients are dropped.
+        c_in_true = c_in
+        row_bytes = c_in * feats.element_size()
+        if algo != _lib.ALGO_SIMT and c_in < 16 and row_bytes % 16 != 0:
+            c_in = -(-row_bytes // 16) * 16 // feats.element_size()
+            feats = torch.nn.functional.pad(feats, (0, c_in - c_in_true))
+            w32 = torch.nn.functional.pad(w32, (0, 0, 0, c_in - c_in_true))
         # tensor-core operand forms of the weights (one launch); a direction the TC kernels do not take (e.g. c_in = 3)
         # runs on the exact SIMT kernel with the parameter itself
         fwd_tc = algo != _lib.ALGO_SIMT and bool(lib.lgs_conv_tc_supported(c_in, c_out, dt))
         bwd_tc = algo != _lib.ALGO_SIMT and need_dgrad and bool(lib.lgs_conv_tc_supported(c_out, c_in, dt))
         nsplit = 2 if algo == _lib.ALGO_TC3 else 1
-        w32 = w3.detach().float().contiguous()
         w_fwd = w_bwd = None
         if fwd_tc or bwd_tc:
             if fwd_tc:
@@ -419,6 +427,7 @@ class _SparseConvFn(torch.autograd.Function):
         ctx.save_for_backward(feats, w_bwd)
         ctx.km, ctx.algo, ctx.bwd_tc, ctx.tc_layout = km, algo, bwd_tc, tc_layout
         ctx.dims, ctx.w_shape, ctx.w_dtype, ctx.has_bias = (K, c_in, c_out), weight.shape, weight.dtype, bias is not None
+        ctx.c_in_true = c_in_true
         return out
 
     @staticmethod
@@ -446,9 +455,13 @@ class _SparseConvFn(torch.autograd.Function):
                 _lib.check(lib.lgs_conv_wgrad(_lib.ptr(feats), n_in, c_in, _lib.ptr(gout), n_out, c_out,
                                               _lib.ptr(km.fwd_table) if km is not None else None, K, _lib.ptr(gw), dt,
                                               algo, _stream()))
+            if ctx.c_in_true != c_in:
+                gw = gw[:, :ctx.c_in_true, :].contiguous()
             gw = gw.view(ctx.w_shape).to(ctx.w_dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gout.float().sum(0, keepdim=True)
+        if gin is not None and ctx.c_in_true != c_in:
+            gin = gin[:, :ctx.c_in_true].contiguous()
         return gin, gw, gb, None, None
 
 
