@@ -76,6 +76,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tma
       : "memory");
 }
 
+// TMA row gather: 4 rows {r0..r3} x one 128-byte column block -> 4 consecutive 128-byte shared-memory rows (512 B),
+// swizzled by the absolute shared-memory row; negative / out-of-range rows are ZERO-FILLED by the hardware, which is
+// exactly the "missing neighbour" semantics of the kernel-map table (probed in scripts/micro/gather4_probe.cu).
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tmap, uint64_t* bar, int32_t col, int32_t r0,
+                                            int32_t r1, int32_t r2, int32_t r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100): rows of 128 B, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -138,6 +149,7 @@ struct Params {
   int32_t b_stage_bytes;    // n_tile * 128
   int32_t k_per_split;      // offsets handled by one CTA (blockIdx.z selects the range); < K => partial sums, red.add
   int32_t k_splits;
+  int32_t dbg;              // development knobs (LGS_TC_DBG): bit0 no cp.async at all, bit1 only 2 of 8 cp.async, bit2 no MMA
 };
 
 // PRECISE (fp32 features only): 3xTF32 error-compensated product.  Four extra warps split every landed A tile into
@@ -271,8 +283,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
       for (int kb = 0; kb < num_kb; ++kb, col += KBLOCK_BYTES) {
         mbar_wait(empty_bar + s, ph ^ 1);
         const uint32_t m = col < row_bytes ? okmask : 0u;
+        if (!(p.dbg & 1)) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) cp_async16(a_base + dst_off[i], src[i] + kb * KBLOCK_BYTES, ((m >> i) & 1u) ? 16u : 0u);
+          for (int i = 0; i < 8; ++i)
+            if (!(p.dbg & 2) || i < 2) cp_async16(a_base + dst_off[i], src[i] + kb * KBLOCK_BYTES, ((m >> i) & 1u) ? 16u : 0u);
+        }
         // hardware arrives on full[s] when this thread's copies have landed: nothing blocks, every free stage of the
         // ring is in flight.  The generic->async proxy fence is issued by the consumer after it observes the barrier.
         cp_async_mbar_arrive_noinc(full_bar + s);
@@ -363,7 +378,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
           const uint32_t a_lo32 = ((a_base >> 4) & 0x3FFF) | (1u << 16);
           const uint32_t b_lo32 = (((a_base + b_off) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll 4
-          for (int j = 0; j < ksteps; ++j) {
+          for (int j = 0; j < ((p.dbg & 4) ? 0 : ksteps); ++j) {
             const uint64_t a_hi = desc_from(a_lo32 + 2 * j, desc_hi), b_hi = desc_from(b_lo32 + 2 * j, desc_hi);
             umma<BF16>(tmem_base, a_hi, b_hi, idesc, first | uint32_t(j));
             if constexpr (PRECISE) {
@@ -454,6 +469,314 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
 
   __syncthreads();
   if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(p.tmem_cols))
+                 : "memory");
+  }
+}
+
+// =============================================================================================================
+// Multi-tile variant for large coordinate maps: one CTA owns TM (<= 4) consecutive 128-row tiles and keeps TM
+// accumulators in TMEM (TM * n_tile <= 512 columns).  Loop order  offset k -> channel block kb -> tile t :
+// every weight block W[k][kb] is TMA-loaded ONCE per CTA and feeds TM MMAs groups, cutting the L2->SM weight traffic
+// (the dominant stream of the single-tile kernel: 27 * Cin * Cout * 4 B per 128 rows) by TM.  A and B live in separate
+// mbarrier rings.  The neighbour table is staged per offset (double buffered, 2 * TM * 128 indices), prefetched one
+// offset ahead by the producers themselves.
+// =============================================================================================================
+struct Params2 {
+  const uint8_t* in;
+  int32_t row_bytes;
+  int32_t K;
+  int32_t c_out;
+  const int32_t* table;
+  int64_t n_out;
+  int32_t reverse_k;
+  const float* bias;
+  void* out;
+  int32_t num_kb;
+  int32_t n_tile;        // == padded c_out (this kernel does not split channels)
+  int32_t TM;            // tiles per CTA
+  int32_t a_stages, b_stages;
+  int32_t tmem_cols;
+  int32_t b_stage_bytes;
+  int32_t dbg;           // development knobs (LGS_TC_DBG): bit1 skip MMAs, bit3 plain arrives instead of tcgen05.commit
+};
+
+constexpr int MAX_A_STAGES = 12, MAX_B_STAGES = 4;
+constexpr int T2_PROD_WARPS = 8;                       // gather producers (and epilogue)
+constexpr int T2_THREADS = (T2_PROD_WARPS + 2) * 32;    // + MMA issuer warp + weight TMA warp
+
+template <bool BF16, bool PRECISE>
+__global__ void __launch_bounds__(PRECISE ? T2_THREADS + 128 : T2_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NSPLIT = PRECISE ? 2 : 1;
+  constexpr uint32_t A_BYTES = NSPLIT * A_STAGE_BYTES;          // [A hi | A lo]
+  const uint32_t b_bytes = NSPLIT * p.b_stage_bytes;             // [B hi | B lo]
+  const int SA = p.a_stages, SB = p.b_stages, TM = p.TM;
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + size_t(SA) * A_BYTES;
+  int32_t* sidx = reinterpret_cast<int32_t*>(b_ring + size_t(SB) * b_bytes);   // [2][TM*128]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sidx + 2 * 4 * BM);
+  uint64_t* a_empty = a_full + MAX_A_STAGES;
+  uint64_t* a_split = a_empty + MAX_A_STAGES;
+  uint64_t* b_full = a_split + MAX_A_STAGES;
+  uint64_t* b_empty = b_full + MAX_B_STAGES;
+  uint64_t* acc_bar = b_empty + MAX_B_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = int64_t(blockIdx.x) * (int64_t(TM) * BM);
+  const int K = p.K, num_kb = p.num_kb;
+
+  if (tid == 0) {
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(a_full + s, T2_PROD_WARPS * 32);   // cp.async-completion arrivals of the producer threads
+      mbar_init(a_empty + s, 1);
+      mbar_init(a_split + s, 128);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(b_full + s, 1);
+      mbar_init(b_empty + s, 1);
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == T2_PROD_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(uint32_t(p.tmem_cols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == T2_PROD_WARPS + 1 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < T2_PROD_WARPS) {
+    {
+      // =================================== gather producers: 8 warps, cp.async ===================================
+      // Two producer warps per SM sub-partition hide each other's issue latency; 8 lanes cover one 128-byte row
+      // segment, 32 rows per pass, 4 passes per 128-row tile.  Table entries are read straight from global memory one
+      // offset ahead (8 lanes share an address -> one sector, broadcast).
+      const int chunk = tid & 7, rbase = tid >> 3;          // rbase 0..31
+      uint32_t dst_off[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = rbase + 32 * i;
+        dst_off[i] = uint32_t(r * KBLOCK_BYTES + ((chunk ^ (r & 7)) << 4));
+      }
+      const int row_bytes = p.row_bytes;
+      const uint8_t* in_chunk = p.in + chunk * 16;
+      const uint32_t a_ring_base = smem_u32(a_ring);
+      auto load_idx = [&](int k, int32_t (&v)[4][4]) {
+        const int32_t* trow = p.table ? p.table + int64_t(p.reverse_k ? K - 1 - k : k) * p.n_out : nullptr;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int64_t o = m0 + int64_t(t) * BM + rbase + 32 * i;
+            v[t][i] = (t < TM && o < p.n_out) ? (trow ? __ldg(trow + o) : int32_t(o)) : -1;
+          }
+        }
+      };
+      int32_t cur[4][4], nxt[4][4];
+      load_idx(0, cur);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int k = 0; k < K; ++k) {
+        if (k + 1 < K) load_idx(k + 1, nxt);        // in flight while this offset is gathered
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int col = kb * KBLOCK_BYTES + chunk * 16;
+          const bool col_ok = col < row_bytes;
+          const uint8_t* in_kb = in_chunk + kb * KBLOCK_BYTES;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (t < TM) {
+              mbar_wait(a_empty + s, ph ^ 1);
+              const uint32_t a_base = a_ring_base + uint32_t(s) * A_BYTES;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int32_t row = cur[t][i];
+                const bool ok = col_ok && row >= 0;
+                cp_async16(a_base + dst_off[i], in_kb + size_t(ok ? row : 0) * row_bytes, ok ? 16u : 0u);
+              }
+              cp_async_mbar_arrive_noinc(a_full + s);
+              if (++s == SA) {
+                s = 0;
+                ph ^= 1;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cur[t][i] = nxt[t][i];
+      }
+    }
+
+    // =================================== epilogue ===================================
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int ncols = p.c_out;
+    const int lq = warp & 3;                       // TMEM lane quadrant this warp may read
+    for (int t = warp >> 2; t < TM; t += T2_PROD_WARPS / 4) {
+      const int64_t o = m0 + int64_t(t) * BM + lq * 32 + lane;
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (uint32_t(lq * 32) << 16) + uint32_t(t * p.n_tile + c0), v);
+        if (o < p.n_out) {
+          if constexpr (BF16) {
+            __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out) + size_t(o) * p.c_out + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              if (c0 + j + 1 < ncols) {
+                const float x0 = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+                const float x1 = __uint_as_float(v[j + 1]) + (p.bias ? __ldg(p.bias + c0 + j + 1) : 0.f);
+                *reinterpret_cast<__nv_bfloat162*>(orow + j) = __floats2bfloat162_rn(x0, x1);
+              } else if (c0 + j < ncols) {
+                orow[j] = __float2bfloat16(__uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f));
+              }
+            }
+          } else {
+            float* orow = static_cast<float*>(p.out) + size_t(o) * p.c_out + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (c0 + j + 3 < ncols) {
+                float4 x;
+                x.x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+                x.y = __uint_as_float(v[j + 1]) + (p.bias ? __ldg(p.bias + c0 + j + 1) : 0.f);
+                x.z = __uint_as_float(v[j + 2]) + (p.bias ? __ldg(p.bias + c0 + j + 2) : 0.f);
+                x.w = __uint_as_float(v[j + 3]) + (p.bias ? __ldg(p.bias + c0 + j + 3) : 0.f);
+                *reinterpret_cast<float4*>(orow + j) = x;
+              } else {
+                for (int jj = j; jj < j + 4; ++jj)
+                  if (c0 + jj < ncols) orow[jj] = __uint_as_float(v[jj]) + (p.bias ? __ldg(p.bias + c0 + jj) : 0.f);
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == T2_PROD_WARPS) {
+    // =================================== MMA issuer (one thread) ===================================
+    if (lane == 0) {
+      const uint32_t fmt = BF16 ? 1u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(p.n_tile >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+      const uint32_t desc_hi = uint32_t(1024 >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_ring_base = smem_u32(a_ring), b_ring_base = smem_u32(b_ring);
+      const int row_bytes = p.row_bytes;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      for (int k = 0; k < K; ++k) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(b_full + sb, phb);
+          const uint32_t b_base = b_ring_base + uint32_t(sb) * b_bytes;
+          const uint32_t b_lo32 = ((b_base >> 4) & 0x3FFF) | (1u << 16);
+          const int valid = min(KBLOCK_BYTES, row_bytes - kb * KBLOCK_BYTES);
+          const int ksteps = (valid + 31) >> 5;
+          const uint32_t acc_flag = (k | kb) ? 1u : 0u;
+          for (int t = 0; t < TM; ++t) {
+            mbar_wait(a_full + sa, pha);
+            if constexpr (PRECISE) mbar_wait(a_split + sa, pha);
+            fence_proxy_async();   // generic-proxy writes (cp.async / splitters) -> visible to the tensor core's reads
+            tc_fence_after();
+            const uint32_t a_base = a_ring_base + uint32_t(sa) * A_BYTES;
+            const uint32_t a_lo32 = ((a_base >> 4) & 0x3FFF) | (1u << 16);
+            const uint32_t d_addr = tmem_base + uint32_t(t * p.n_tile);
+#pragma unroll 4
+            for (int j = 0; j < ((p.dbg & 2) ? 0 : ksteps); ++j) {
+              const uint64_t a_hi = desc_from(a_lo32 + 2 * j, desc_hi), b_hi = desc_from(b_lo32 + 2 * j, desc_hi);
+              umma<BF16>(d_addr, a_hi, b_hi, idesc, acc_flag | uint32_t(j));
+              if constexpr (PRECISE) {
+                umma<BF16>(d_addr, desc_from(a_lo32 + (A_STAGE_BYTES >> 4) + 2 * j, desc_hi), b_hi, idesc, 1u);
+                umma<BF16>(d_addr, a_hi, desc_from(b_lo32 + (p.b_stage_bytes >> 4) + 2 * j, desc_hi), idesc, 1u);
+              }
+            }
+            if (p.dbg & 8) mbar_arrive(a_empty + sa); else umma_commit(a_empty + sa);
+            if (++sa == SA) {
+              sa = 0;
+              pha ^= 1;
+            }
+          }
+          if (p.dbg & 8) mbar_arrive(b_empty + sb); else umma_commit(b_empty + sb);
+          if (++sb == SB) {
+            sb = 0;
+            phb ^= 1;
+          }
+        }
+      }
+      umma_commit(acc_bar);
+    }
+    __syncwarp();
+  } else if (warp == T2_PROD_WARPS + 1) {
+    // =================================== weight TMA producer (one thread) ===================================
+    if (lane == 0) {
+      const int kelems = KBLOCK_BYTES / (BF16 ? 2 : 4);
+      const uint32_t b_ring_base = smem_u32(b_ring);
+      int sb = 0;
+      uint32_t phb = 0;
+      for (int k = 0; k < K; ++k) {
+        const int row = k * p.c_out;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(b_empty + sb, phb ^ 1);
+          mbar_expect_tx(b_full + sb, b_bytes);
+          const uint32_t b_dst = b_ring_base + uint32_t(sb) * b_bytes;
+          tma_load_2d(b_dst, &tmap_w, b_full + sb, kb * kelems, row);
+          if constexpr (PRECISE) tma_load_2d(b_dst + p.b_stage_bytes, &tmap_w, b_full + sb, kb * kelems, K * p.c_out + row);
+          if (++sb == SB) {
+            sb = 0;
+            phb ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if constexpr (PRECISE) {
+    if (warp >= T2_PROD_WARPS + 2) {
+      // =================================== hi/lo splitters (128 threads) ===================================
+      const int st = tid - T2_THREADS;
+      const int total = K * num_kb * TM;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < total; ++it) {
+        mbar_wait(a_full + s, ph);
+        float4* a_hi = reinterpret_cast<float4*>(a_ring + size_t(s) * A_BYTES) + st;
+        float4* a_lo = reinterpret_cast<float4*>(a_ring + size_t(s) * A_BYTES + A_STAGE_BYTES) + st;
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = a_hi[128 * i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
+          l.x = v[i].x - h.x;
+          l.y = v[i].y - h.y;
+          l.z = v[i].z - h.z;
+          l.w = v[i].w - h.w;
+          a_hi[128 * i] = h;
+          a_lo[128 * i] = l;
+        }
+        fence_proxy_async();
+        mbar_arrive(a_split + s);
+        if (++s == SA) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == T2_PROD_WARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(p.tmem_cols))
                  : "memory");
@@ -561,6 +884,92 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
   EncodeTiledFn encode = get_encode();
   if (!encode) return fail(LGS_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
 
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    const void* fns[] = {(const void*)conv_tc_kernel<false, false>, (const void*)conv_tc_kernel<true, false>,
+                         (const void*)conv_tc_kernel<false, true>,  (const void*)conv_tc2_kernel<false, false>,
+                         (const void*)conv_tc2_kernel<true, false>, (const void*)conv_tc2_kernel<false, true>};
+    for (const void* f : fns)
+      if (attr_err == cudaSuccess)
+        attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) return fail(LGS_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+
+  // ---- large maps: multi-tile CTAs sharing each weight block across TM row tiles --------------------------------
+  {
+    const int c_pad2 = ((c_out + 15) / 16) * 16;
+    const int64_t tiles = cdiv(n_out, BM);
+    int TM = 0;
+    if (c_pad2 <= 256 && tiles >= 148 && n_in > 0 && !getenv("LGS_TC_NO_MULTI")) {
+      // pick TM in {4,2,1} minimising waves*TM (ties -> larger TM: less weight traffic)
+      int64_t best = -1;
+      for (int tm = 1; tm <= 4; tm *= 2) {
+        if (tm * c_pad2 > 512) break;
+        const int64_t cost = cdiv(cdiv(tiles, tm), 148) * tm;
+        if (best < 0 || cost <= best) {
+          best = cost;
+          TM = tm;
+        }
+      }
+      if (const char* e = getenv("LGS_TC_TM")) TM = atoi(e);
+    }
+    if (TM >= 2) {
+      Params2 q;
+      q.in = static_cast<const uint8_t*>(in);
+      q.row_bytes = row_bytes;
+      q.K = K;
+      q.c_out = c_out;
+      q.table = table;
+      q.n_out = n_out;
+      q.reverse_k = reverse_k;
+      q.bias = bias;
+      q.out = out;
+      q.num_kb = (row_bytes + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
+      q.n_tile = c_pad2;
+      q.TM = TM;
+      q.dbg = getenv("LGS_TC_DBG") ? atoi(getenv("LGS_TC_DBG")) : 0;
+      q.b_stage_bytes = c_pad2 * KBLOCK_BYTES;
+      int cols = 32;
+      while (cols < TM * c_pad2) cols <<= 1;
+      q.tmem_cols = cols;
+      const int a_bytes = nsplit * A_STAGE_BYTES, b_bytes = nsplit * q.b_stage_bytes;
+      const int fixed2 = 2 * 4 * BM * 4 + (3 * MAX_A_STAGES + 2 * MAX_B_STAGES + 1) * 8 + 16 + 1024;
+      int sb = 2;
+      int sa = (227 * 1024 - fixed2 - sb * b_bytes) / a_bytes;
+      if (sa > MAX_A_STAGES) sa = MAX_A_STAGES;
+      if (sa >= 6 && (227 * 1024 - fixed2 - 3 * b_bytes) / a_bytes >= 5) {   // room for a third weight stage
+        sb = 3;
+        sa = (227 * 1024 - fixed2 - sb * b_bytes) / a_bytes;
+        if (sa > MAX_A_STAGES) sa = MAX_A_STAGES;
+      }
+      if (sa >= 2) {
+        q.a_stages = sa;
+        q.b_stages = sb;
+        const size_t smem2 = size_t(sa) * a_bytes + size_t(sb) * b_bytes + fixed2;
+        CUtensorMap tmap2;
+        const cuuint64_t gdim2[2] = {cuuint64_t(c_in), cuuint64_t(nsplit) * cuuint64_t(K) * cuuint64_t(c_out)};
+        const cuuint64_t gstride2[1] = {cuuint64_t(row_bytes)};
+        const cuuint32_t box2[2] = {cuuint32_t(KBLOCK_BYTES / es), cuuint32_t(c_pad2)};
+        const cuuint32_t estr2[2] = {1, 1};
+        const CUresult cr2 = encode(&tmap2, dtype == LGS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                    2, const_cast<void*>(w_nk), gdim2, gstride2, box2, estr2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr2 != CUDA_SUCCESS) return fail(LGS_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(cr2));
+        const dim3 grid2{unsigned(cdiv(tiles, TM)), 1u, 1u};
+        if (dtype == LGS_BF16) {
+          LGS_LAUNCH((conv_tc2_kernel<true, false>), grid2, T2_THREADS, smem2, stream, tmap2, q);
+        } else if (precise) {
+          LGS_LAUNCH((conv_tc2_kernel<false, true>), grid2, T2_THREADS + 128, smem2, stream, tmap2, q);
+        } else {
+          LGS_LAUNCH((conv_tc2_kernel<false, false>), grid2, T2_THREADS, smem2, stream, tmap2, q);
+        }
+        return LGS_OK;
+      }
+    }
+  }
+
   Params p;
   p.in = static_cast<const uint8_t*>(in);
   p.n_in = n_in;
@@ -606,6 +1015,7 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
   k_splits = (K + p.k_per_split - 1) / p.k_per_split;
   p.k_splits = k_splits;
   p.b_stage_bytes = p.n_tile * KBLOCK_BYTES;
+  p.dbg = getenv("LGS_TC_DBG") ? atoi(getenv("LGS_TC_DBG")) : 0;
   int cols = 32;
   while (cols < p.n_tile) cols <<= 1;
   p.tmem_cols = cols;
@@ -631,17 +1041,6 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(LGS_E_CUDA, "cuTensorMapEncodeTiled failed (%d) c_in=%d c_out=%d K=%d", int(cr), c_in, c_out, K);
-
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  if (attr_err != cudaSuccess) return fail(LGS_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
 
   const dim3 grid{unsigned(m_tiles), unsigned(n_tiles), unsigned(k_splits)};
   if (dtype == LGS_BF16) {
