@@ -196,6 +196,10 @@ def run_engine(args, rank, world, local_rank):
     ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - l0
     loss_val = float(loss.item())
+    if args.profile_run:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches)}))
+        return None
 
     # ---- per-launch CUDA-event timing of the engine's conv kernels (same process, same data, right after the timed
     # region; kept out of it because ~380 event records per step starve the launch queue and double the step time)
@@ -359,8 +363,10 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--cpu-sample-voxels", type=int, default=60_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-run", action="store_true",
+                    help="for ncu launch lists: allow fewer warm-up steps and skip the e2e / map-build / roofline legs")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+    args.warmup = max(args.warmup, 3) if (args.impl == "engine" and not args.profile_run) else args.warmup
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -387,7 +393,7 @@ def main():
         from languagegroundedsemseg_b200 import ddp
         ddp.init_process_group("nccl")
     res = run_engine(args, rank, world, local_rank)
-    if rank == 0:
+    if rank == 0 and res is not None:
         if world == 1 and not args.no_cpu_baseline:
             cb, _, _ = cpu_arm(1, 0, args.cpu_sample_voxels)
             cb["cpu"] = cpu_model_name()

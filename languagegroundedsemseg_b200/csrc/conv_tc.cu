@@ -57,6 +57,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// One lane of a fully converged warp (the CUTLASS elect_one_sync idiom).  The issuing warps run their loops
+// warp-uniformly and guard only the tcgen05 / TMA instruction with this predicate: under a divergent `lane == 0` branch
+// ptxas serialises every such instruction in an ELECT ... BRA.U.ANY loop (seen in SASS), which made the issuing thread
+// the bottleneck of the whole pipeline.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -149,11 +162,11 @@ struct Params {
   int32_t b_stage_bytes;    // n_tile * 128
   int32_t k_per_split;      // offsets handled by one CTA (blockIdx.z selects the range); < K => partial sums, red.add
   int32_t k_splits;
-  int32_t dbg;              // development knobs (LGS_TC_DBG): bit0 no cp.async at all, bit1 only 2 of 8 cp.async, bit2 no MMA
 };
 
-// PRECISE (fp32 features only): 3xTF32 error-compensated product.  Four extra warps split every landed A tile into
-// hi = tf32-truncated value (rewritten in place) and lo = a - hi (second tile); the weights arrive pre-split (hi, lo
+// PRECISE (fp32 features only): 3xTF32 error-compensated product.  Four extra warps derive from every landed A tile the
+// residual lo = a - trunc_tf32(a) (second tile); the tensor core itself truncates the raw tile to hi (kind::tf32 ignores the
+// low 13 mantissa bits of both operands — verified bit-exactly by scripts/dev_trunc.py); the weights arrive pre-split (hi, lo
 // stacked, see lgs_weight_prep); three MMAs per K step accumulate hi*hi + lo*hi + hi*lo, i.e. fp32-grade products
 // (relative error ~2^-21) with fp32 accumulation in TMEM.
 //
@@ -283,11 +296,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
       for (int kb = 0; kb < num_kb; ++kb, col += KBLOCK_BYTES) {
         mbar_wait(empty_bar + s, ph ^ 1);
         const uint32_t m = col < row_bytes ? okmask : 0u;
-        if (!(p.dbg & 1)) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (!(p.dbg & 2) || i < 2) cp_async16(a_base + dst_off[i], src[i] + kb * KBLOCK_BYTES, ((m >> i) & 1u) ? 16u : 0u);
-        }
+        for (int i = 0; i < 8; ++i) cp_async16(a_base + dst_off[i], src[i] + kb * KBLOCK_BYTES, ((m >> i) & 1u) ? 16u : 0u);
         // hardware arrives on full[s] when this thread's copies have landed: nothing blocks, every free stage of the
         // ring is in flight.  The generic->async proxy fence is issued by the consumer after it observes the barrier.
         cp_async_mbar_arrive_noinc(full_bar + s);
@@ -355,8 +365,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
     }
     tc_fence_before();
   } else if (warp == 4) {
-    // =================================== MMA issuer (one thread) ===================================
-    if (lane == 0) {
+    // =================================== MMA issuer (warp-uniform loop, one elected lane issues) ================
+    {
       // instruction descriptor: D fp32, A/B tf32 (or bf16), both K-major, N = n_tile, M = 128
       const uint32_t fmt = BF16 ? 1u : 2u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(p.n_tile >> 3) << 17) | (uint32_t(BM >> 4) << 24);
@@ -377,17 +387,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
           const int ksteps = (valid + 31) >> 5;  // 32 bytes of K per instruction (8 tf32 / 16 bf16)
           const uint32_t a_lo32 = ((a_base >> 4) & 0x3FFF) | (1u << 16);
           const uint32_t b_lo32 = (((a_base + b_off) >> 4) & 0x3FFF) | (1u << 16);
+          if (elect_one()) {
 #pragma unroll 4
-          for (int j = 0; j < ((p.dbg & 4) ? 0 : ksteps); ++j) {
-            const uint64_t a_hi = desc_from(a_lo32 + 2 * j, desc_hi), b_hi = desc_from(b_lo32 + 2 * j, desc_hi);
-            umma<BF16>(tmem_base, a_hi, b_hi, idesc, first | uint32_t(j));
-            if constexpr (PRECISE) {
-              umma<BF16>(tmem_base, desc_from(a_lo32 + (A_STAGE_BYTES >> 4) + 2 * j, desc_hi), b_hi, idesc, 1u);
-              umma<BF16>(tmem_base, a_hi, desc_from(b_lo32 + (p.b_stage_bytes >> 4) + 2 * j, desc_hi), idesc, 1u);
+            for (int j = 0; j < ksteps; ++j) {
+              const uint64_t a_hi = desc_from(a_lo32 + 2 * j, desc_hi), b_hi = desc_from(b_lo32 + 2 * j, desc_hi);
+              umma<BF16>(tmem_base, a_hi, b_hi, idesc, first | uint32_t(j));
+              if constexpr (PRECISE) {
+                umma<BF16>(tmem_base, desc_from(a_lo32 + (A_STAGE_BYTES >> 4) + 2 * j, desc_hi), b_hi, idesc, 1u);
+                umma<BF16>(tmem_base, a_hi, desc_from(b_lo32 + (p.b_stage_bytes >> 4) + 2 * j, desc_hi), idesc, 1u);
+              }
             }
+            umma_commit(empty_bar + s);  // frees the stage once these MMAs have read it
           }
+          __syncwarp();
           first = 1;
-          umma_commit(empty_bar + s);  // frees the stage once these MMAs have read it
           a_base += stage_bytes;
           if (++s == stages) {
             s = 0;
@@ -396,12 +409,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
           }
         }
       }
-      if (total > 0) umma_commit(acc_bar);
+      if (total > 0 && elect_one()) umma_commit(acc_bar);
     }
     __syncwarp();
   } else if (warp == 5) {
-    // =================================== weight TMA producer (one thread) ===================================
-    if (lane == 0) {
+    // =================================== weight TMA producer (warp-uniform loop, one elected lane issues) ======
+    {
       const int kelems = KBLOCK_BYTES / (BF16 ? 2 : 4);
       const uint32_t b_off = NSPLIT * A_STAGE_BYTES;
       const uint32_t tx = NSPLIT * p.b_stage_bytes;
@@ -412,10 +425,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
         const int row = (kbeg + klist[a]) * p.c_out + n0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + s, ph ^ 1);
-          mbar_expect_tx(full_bar + s, tx);
-          tma_load_2d(b_dst, &tmap_w, full_bar + s, kb * kelems, row);
-          if constexpr (PRECISE)   // lo halves are stacked after the K*c_out hi rows
-            tma_load_2d(b_dst + p.b_stage_bytes, &tmap_w, full_bar + s, kb * kelems, p.K * p.c_out + row);
+          if (elect_one()) {
+            mbar_expect_tx(full_bar + s, tx);
+            tma_load_2d(b_dst, &tmap_w, full_bar + s, kb * kelems, row);
+            if constexpr (PRECISE)   // lo halves are stacked after the K*c_out hi rows
+              tma_load_2d(b_dst + p.b_stage_bytes, &tmap_w, full_bar + s, kb * kelems, p.K * p.c_out + row);
+          }
+          __syncwarp();
           b_dst += stage_bytes;
           if (++s == stages) {
             s = 0;
@@ -452,7 +468,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
           l.y = v[i].y - h.y;
           l.z = v[i].z - h.z;
           l.w = v[i].w - h.w;
-          a_hi[128 * i] = h;
           a_lo[128 * i] = l;
         }
         fence_proxy_async();
@@ -499,7 +514,6 @@ struct Params2 {
   int32_t a_stages, b_stages;
   int32_t tmem_cols;
   int32_t b_stage_bytes;
-  int32_t dbg;           // development knobs (LGS_TC_DBG): bit1 skip MMAs, bit3 plain arrives instead of tcgen05.commit
 };
 
 constexpr int MAX_A_STAGES = 12, MAX_B_STAGES = 4;
@@ -663,8 +677,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
     }
     tc_fence_before();
   } else if (warp == T2_PROD_WARPS) {
-    // =================================== MMA issuer (one thread) ===================================
-    if (lane == 0) {
+    // =================================== MMA issuer (warp-uniform loop, one elected lane issues) ================
+    {
       const uint32_t fmt = BF16 ? 1u : 2u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(p.n_tile >> 3) << 17) | (uint32_t(BM >> 4) << 24);
       const uint32_t desc_hi = uint32_t(1024 >> 4) | (1u << 14) | (2u << 29);
@@ -688,34 +702,38 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
             const uint32_t a_base = a_ring_base + uint32_t(sa) * A_BYTES;
             const uint32_t a_lo32 = ((a_base >> 4) & 0x3FFF) | (1u << 16);
             const uint32_t d_addr = tmem_base + uint32_t(t * p.n_tile);
+            if (elect_one()) {
 #pragma unroll 4
-            for (int j = 0; j < ((p.dbg & 2) ? 0 : ksteps); ++j) {
-              const uint64_t a_hi = desc_from(a_lo32 + 2 * j, desc_hi), b_hi = desc_from(b_lo32 + 2 * j, desc_hi);
-              umma<BF16>(d_addr, a_hi, b_hi, idesc, acc_flag | uint32_t(j));
-              if constexpr (PRECISE) {
-                umma<BF16>(d_addr, desc_from(a_lo32 + (A_STAGE_BYTES >> 4) + 2 * j, desc_hi), b_hi, idesc, 1u);
-                umma<BF16>(d_addr, a_hi, desc_from(b_lo32 + (p.b_stage_bytes >> 4) + 2 * j, desc_hi), idesc, 1u);
+              for (int j = 0; j < ksteps; ++j) {
+                const uint64_t a_hi = desc_from(a_lo32 + 2 * j, desc_hi), b_hi = desc_from(b_lo32 + 2 * j, desc_hi);
+                umma<BF16>(d_addr, a_hi, b_hi, idesc, acc_flag | uint32_t(j));
+                if constexpr (PRECISE) {
+                  umma<BF16>(d_addr, desc_from(a_lo32 + (A_STAGE_BYTES >> 4) + 2 * j, desc_hi), b_hi, idesc, 1u);
+                  umma<BF16>(d_addr, a_hi, desc_from(b_lo32 + (p.b_stage_bytes >> 4) + 2 * j, desc_hi), idesc, 1u);
+                }
               }
+              umma_commit(a_empty + sa);
             }
-            if (p.dbg & 8) mbar_arrive(a_empty + sa); else umma_commit(a_empty + sa);
+            __syncwarp();
             if (++sa == SA) {
               sa = 0;
               pha ^= 1;
             }
           }
-          if (p.dbg & 8) mbar_arrive(b_empty + sb); else umma_commit(b_empty + sb);
+          if (elect_one()) umma_commit(b_empty + sb);
+          __syncwarp();
           if (++sb == SB) {
             sb = 0;
             phb ^= 1;
           }
         }
       }
-      umma_commit(acc_bar);
+      if (elect_one()) umma_commit(acc_bar);
     }
     __syncwarp();
   } else if (warp == T2_PROD_WARPS + 1) {
-    // =================================== weight TMA producer (one thread) ===================================
-    if (lane == 0) {
+    // =================================== weight TMA producer (warp-uniform loop, one elected lane issues) ======
+    {
       const int kelems = KBLOCK_BYTES / (BF16 ? 2 : 4);
       const uint32_t b_ring_base = smem_u32(b_ring);
       int sb = 0;
@@ -724,10 +742,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
         const int row = k * p.c_out;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(b_empty + sb, phb ^ 1);
-          mbar_expect_tx(b_full + sb, b_bytes);
           const uint32_t b_dst = b_ring_base + uint32_t(sb) * b_bytes;
-          tma_load_2d(b_dst, &tmap_w, b_full + sb, kb * kelems, row);
-          if constexpr (PRECISE) tma_load_2d(b_dst + p.b_stage_bytes, &tmap_w, b_full + sb, kb * kelems, K * p.c_out + row);
+          if (elect_one()) {
+            mbar_expect_tx(b_full + sb, b_bytes);
+            tma_load_2d(b_dst, &tmap_w, b_full + sb, kb * kelems, row);
+            if constexpr (PRECISE) tma_load_2d(b_dst + p.b_stage_bytes, &tmap_w, b_full + sb, kb * kelems, K * p.c_out + row);
+          }
+          __syncwarp();
           if (++sb == SB) {
             sb = 0;
             phb ^= 1;
@@ -762,7 +783,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
           l.y = v[i].y - h.y;
           l.z = v[i].z - h.z;
           l.w = v[i].w - h.w;
-          a_hi[128 * i] = h;
           a_lo[128 * i] = l;
         }
         fence_proxy_async();
@@ -928,7 +948,6 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
       q.num_kb = (row_bytes + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
       q.n_tile = c_pad2;
       q.TM = TM;
-      q.dbg = getenv("LGS_TC_DBG") ? atoi(getenv("LGS_TC_DBG")) : 0;
       q.b_stage_bytes = c_pad2 * KBLOCK_BYTES;
       int cols = 32;
       while (cols < TM * c_pad2) cols <<= 1;
@@ -1015,7 +1034,6 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
   k_splits = (K + p.k_per_split - 1) / p.k_per_split;
   p.k_splits = k_splits;
   p.b_stage_bytes = p.n_tile * KBLOCK_BYTES;
-  p.dbg = getenv("LGS_TC_DBG") ? atoi(getenv("LGS_TC_DBG")) : 0;
   int cols = 32;
   while (cols < p.n_tile) cols <<= 1;
   p.tmem_cols = cols;
@@ -1068,7 +1086,7 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
 namespace tcw {
 using namespace tc;
 
-constexpr int A_STAGES = 2;
+constexpr int MAX_WA_STAGES = 8;
 
 struct WParams {
   const uint8_t* in;       // X [n_in, c_in]
@@ -1084,6 +1102,9 @@ struct WParams {
   int32_t n_cols;          // accumulator columns (c_out padded to 16)
   int32_t tmem_cols;
   int64_t rows_per_chunk;  // multiple of R
+  int32_t a_stages;        // gather ring depth
+  int32_t nb_in_real;      // channel blocks actually gathered per stage (the MMA may read up to MC*4 blocks: the tail
+                           // aliases the next stage / buffer = finite garbage in accumulator rows >= c_in, never stored)
 };
 
 // MN-major operand descriptor over a tile [rows][128 B of channels].
@@ -1113,17 +1134,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int blk_bytes = p.R * KBLOCK_BYTES;             // one channel block of one tile
-  const int a_stage_bytes = p.nb_in * blk_bytes;
+  const int a_stage_bytes = p.nb_in_real * blk_bytes;
+  const int A_STAGES = p.a_stages;
   const int b_buf_bytes = p.nb_out * blk_bytes;
-  uint8_t* a_smem = smem;
-  uint8_t* b_smem = smem + size_t(A_STAGES) * a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + 2 * size_t(b_buf_bytes));
-  uint64_t* afull = bars;               // [A_STAGES]
-  uint64_t* aempty = bars + 2;          // [A_STAGES]
-  uint64_t* bfull = bars + 4;           // [2]
-  uint64_t* bempty = bars + 6;          // [2]
-  uint64_t* acc_bar = bars + 8;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
+  // B (dY) buffers first, gather ring last: the MMA's over-read of a stage's missing tail blocks stays inside the ring
+  // or runs into the barrier words / padding that follow it (finite garbage, see WParams::nb_in_real)
+  uint8_t* b_smem = smem;
+  uint8_t* a_smem = smem + 2 * size_t(b_buf_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + size_t(A_STAGES) * a_stage_bytes + size_t(p.nb_in - p.nb_in_real) * blk_bytes);
+  uint64_t* afull = bars;                       // [MAX_WA_STAGES]
+  uint64_t* aempty = bars + MAX_WA_STAGES;      // [MAX_WA_STAGES]
+  uint64_t* bfull = bars + 2 * MAX_WA_STAGES;   // [2]
+  uint64_t* bempty = bfull + 2;                 // [2]
+  uint64_t* acc_bar = bempty + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t r_begin = int64_t(blockIdx.x) * p.rows_per_chunk;
@@ -1133,7 +1157,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
   const int n_tiles = int((r_end - r_begin + p.R - 1) / p.R);
 
   if (tid == 0) {
-    for (int s = 0; s < A_STAGES; ++s) {
+    for (int s = 0; s < p.a_stages; ++s) {
       mbar_init(afull + s, 128);
       mbar_init(aempty + s, 1);
     }
@@ -1171,33 +1195,42 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
     const uint32_t a_smem_base = smem_u32(a_smem);
     int s = 0;
     uint32_t ph = 0;
-    for (int t = 0; t < n_tiles; ++t) {
+    // table entries of step (t, g), read one step ahead so their latency hides behind the previous step's copies
+    auto load_rows = [&](int t, int g, int32_t (&v)[8]) {
+      const int32_t* trow = p.table ? p.table + int64_t(k0 + g) * p.n_out : nullptr;
       const int64_t row0 = r_begin + int64_t(t) * p.R + rbase;
-      for (int g = 0; g < g_count; ++g) {
-        const int32_t* trow = p.table ? p.table + int64_t(k0 + g) * p.n_out : nullptr;
-        const uint8_t* src[8];
-        uint32_t okmask = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t o = row0 + 16 * i;
-          const int32_t row = (i < passes && o < r_end) ? (trow ? __ldg(trow + o) : int32_t(o)) : -1;
-          okmask |= (row >= 0 ? 1u : 0u) << i;
-          src[i] = in_chunk + size_t(row >= 0 ? row : 0) * row_bytes;
-        }
+      for (int i = 0; i < 8; ++i) {
+        const int64_t o = row0 + 16 * i;
+        v[i] = (i < passes && o < r_end) ? (trow ? __ldg(trow + o) : int32_t(o)) : -1;
+      }
+    };
+    int32_t cur[8], nxt[8];
+    if (n_tiles > 0) load_rows(0, 0, cur);
+    for (int t = 0; t < n_tiles; ++t) {
+      for (int g = 0; g < g_count; ++g) {
+        const bool last = (g + 1 == g_count) && (t + 1 == n_tiles);
+        if (!last) load_rows(g + 1 == g_count ? t + 1 : t, g + 1 == g_count ? 0 : g + 1, nxt);
         mbar_wait(aempty + s, ph ^ 1);
         uint32_t a_base = a_smem_base + uint32_t(s) * uint32_t(a_stage_bytes);
         int col = chunk * 16;
-        for (int kb = 0; kb < p.nb_in; ++kb, col += KBLOCK_BYTES, a_base += blk_bytes) {
-          const uint32_t m = col < row_bytes ? okmask : 0u;
+        for (int kb = 0; kb < p.nb_in_real; ++kb, col += KBLOCK_BYTES, a_base += blk_bytes) {
+          const bool col_ok = col < row_bytes;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i < passes) cp_async16(a_base + dst_off[i], src[i] + kb * KBLOCK_BYTES, ((m >> i) & 1u) ? 16u : 0u);
+          for (int i = 0; i < 8; ++i) {
+            if (i < passes) {
+              const bool ok = col_ok && cur[i] >= 0;
+              cp_async16(a_base + dst_off[i], in_chunk + size_t(ok ? cur[i] : 0) * row_bytes + kb * KBLOCK_BYTES, ok ? 16u : 0u);
+            }
+          }
         }
         cp_async_mbar_arrive_noinc(afull + s);
         if (++s == A_STAGES) {
           s = 0;
           ph ^= 1;
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
       }
     }
     // =================================== epilogue: TMEM -> red.add into dW ===================================
@@ -1228,8 +1261,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
     }
     tc_fence_before();
   } else if (warp == 4) {
-    // =================================== MMA issuer ===================================
-    if (lane == 0) {
+    // =================================== MMA issuer (warp-uniform loop, one elected lane issues) ================
+    {
       const uint32_t fmt = BF16 ? 1u : 2u;
       const int m_dim = 128;  // always whole 128-lane chunks (channels beyond c_in are zero-filled by the gather)
       // D fp32, A/B tf32|bf16, BOTH MN-major (bits 15, 16), N = n_cols, M = m_dim
@@ -1254,37 +1287,44 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
           fence_proxy_async();
           tc_fence_after();
           const uint32_t a_base = a_smem_base + uint32_t(s) * uint32_t(a_stage_bytes);
-          for (int mc = 0; mc < p.MC; ++mc) {
-            const uint32_t d_addr = tmem_base + uint32_t((g * p.MC + mc) * p.n_cols);
-            const uint32_t a_lo32 = (((a_base + uint32_t(mc * mc_blocks) * uint32_t(blk_bytes)) >> 4) & 0x3FFF) | lbo16;
+          if (elect_one()) {
+            for (int mc = 0; mc < p.MC; ++mc) {
+              const uint32_t d_addr = tmem_base + uint32_t((g * p.MC + mc) * p.n_cols);
+              const uint32_t a_lo32 = (((a_base + uint32_t(mc * mc_blocks) * uint32_t(blk_bytes)) >> 4) & 0x3FFF) | lbo16;
 #pragma unroll 4
-            for (int j = 0; j < mmas; ++j)
-              umma<BF16>(d_addr, desc_from(a_lo32 + j * mma_step16, desc_hi), desc_from(b_lo32 + j * mma_step16, desc_hi),
-                         idesc, (t > 0 || j > 0) ? 1u : 0u);
+              for (int j = 0; j < mmas; ++j)
+                umma<BF16>(d_addr, desc_from(a_lo32 + j * mma_step16, desc_hi), desc_from(b_lo32 + j * mma_step16, desc_hi),
+                           idesc, (t > 0 || j > 0) ? 1u : 0u);
+            }
+            umma_commit(aempty + s);
           }
-          umma_commit(aempty + s);
+          __syncwarp();
           if (++s == A_STAGES) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(bempty + bs);
+        if (elect_one()) umma_commit(bempty + bs);
+        __syncwarp();
       }
-      umma_commit(acc_bar);
+      if (elect_one()) umma_commit(acc_bar);
     }
     __syncwarp();
   } else {
-    // =================================== dY tile TMA producer ===================================
-    if (lane == 0) {
+    // =================================== dY tile TMA producer (warp-uniform loop, one elected lane issues) ======
+    {
       const int kelems = KBLOCK_BYTES / (BF16 ? 2 : 4);
       for (int t = 0; t < n_tiles; ++t) {
         const int bs = t & 1;
         mbar_wait(bempty + bs, ((t >> 1) & 1) ^ 1);
-        mbar_expect_tx(bfull + bs, uint32_t(b_buf_bytes));
         const int64_t row0 = r_begin + int64_t(t) * p.R;
-        for (int kb = 0; kb < p.nb_out; ++kb)
-          tma_load_2d(smem_u32(b_smem + size_t(bs) * b_buf_bytes + kb * blk_bytes), &tmap_gy, bfull + bs, kb * kelems,
-                      int32_t(row0));
+        if (elect_one()) {
+          mbar_expect_tx(bfull + bs, uint32_t(b_buf_bytes));
+          for (int kb = 0; kb < p.nb_out; ++kb)
+            tma_load_2d(smem_u32(b_smem + size_t(bs) * b_buf_bytes + kb * blk_bytes), &tmap_gy, bfull + bs, kb * kelems,
+                        int32_t(row0));
+        }
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -1332,10 +1372,23 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
   const int blocks_per_mc = 128 * es / KBLOCK_BYTES;   // 4 (fp32) / 2 (bf16)
   const int nb_in_alloc = p.MC * blocks_per_mc;
   const int nb_out_alloc = (p.n_cols * es + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
-  int R = 128;
-  while (R >= 32 && size_t(A_STAGES * nb_in_alloc + 2 * nb_out_alloc) * R * KBLOCK_BYTES > 200 * 1024) R >>= 1;
-  if (R < 32) return LGS_E_UNSUPPORTED;
+  // tile height R and gather-ring depth: want >= 3 stages in flight; the ring's last stage is followed by the blocks the
+  // MMA may over-read (nb_in_alloc - nb_in), then the barriers
+  const int nb_in_real = p.nb_in;
+  int R = 128, a_stages = 0;
+  for (; R >= 32; R >>= 1) {
+    const size_t blk = size_t(R) * KBLOCK_BYTES;
+    const size_t avail = 216 * 1024 - 2 * nb_out_alloc * blk - size_t(nb_in_alloc - nb_in_real) * blk;
+    if (2 * nb_out_alloc * blk + size_t(nb_in_alloc - nb_in_real) * blk >= 216 * 1024) continue;
+    a_stages = int(avail / (nb_in_real * blk));
+    if (const char* e = getenv("LGS_WG_R")) { if (R != atoi(e)) continue; if (a_stages >= 2) break; continue; }
+    if (a_stages >= 3 || (R == 32 && a_stages >= 2)) break;
+  }
+  if (R < 32 || a_stages < 2) return LGS_E_UNSUPPORTED;
+  if (a_stages > MAX_WA_STAGES) a_stages = MAX_WA_STAGES;
   p.R = R;
+  p.a_stages = a_stages;
+  p.nb_in_real = nb_in_real;
   int G = 512 / (p.MC * p.n_cols);
   if (G < 1) return LGS_E_UNSUPPORTED;
   if (G > K) G = K;
@@ -1364,7 +1417,8 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
   // allocation counts and keep the number of gathered blocks implicit in in_row_bytes (col_ok masks the rest)
   q.nb_in = nb_in_alloc;
   q.nb_out = nb_out_alloc;
-  const size_t smem_bytes = size_t(A_STAGES * nb_in_alloc + 2 * nb_out_alloc) * blk_bytes + 16 * 8 + 1024;
+  const size_t smem_bytes = size_t(a_stages * nb_in_real + (nb_in_alloc - nb_in_real) + 2 * nb_out_alloc) * blk_bytes +
+                            (2 * MAX_WA_STAGES + 8) * 8 + 1024;
 
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {cuuint64_t(c_out), cuuint64_t(n_out)};
