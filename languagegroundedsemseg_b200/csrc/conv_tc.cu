@@ -1103,6 +1103,7 @@ struct WParams {
   int32_t tmem_cols;
   int64_t rows_per_chunk;  // multiple of R
   int32_t a_stages;        // gather ring depth
+  int32_t b_bufs;          // dY tile buffers (2 = double buffered, 1 when shared memory is tight)
   int32_t nb_in_real;      // channel blocks actually gathered per stage (the MMA may read up to MC*4 blocks: the tail
                            // aliases the next stage / buffer = finite garbage in accumulator rows >= c_in, never stored)
 };
@@ -1140,7 +1141,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
   // B (dY) buffers first, gather ring last: the MMA's over-read of a stage's missing tail blocks stays inside the ring
   // or runs into the barrier words / padding that follow it (finite garbage, see WParams::nb_in_real)
   uint8_t* b_smem = smem;
-  uint8_t* a_smem = smem + 2 * size_t(b_buf_bytes);
+  uint8_t* a_smem = smem + size_t(p.b_bufs) * size_t(b_buf_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + size_t(A_STAGES) * a_stage_bytes + size_t(p.nb_in - p.nb_in_real) * blk_bytes);
   uint64_t* afull = bars;                       // [MAX_WA_STAGES]
   uint64_t* aempty = bars + MAX_WA_STAGES;      // [MAX_WA_STAGES]
@@ -1161,7 +1162,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
       mbar_init(afull + s, 128);
       mbar_init(aempty + s, 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < p.b_bufs; ++s) {
       mbar_init(bfull + s, 1);
       mbar_init(bempty + s, 1);
     }
@@ -1279,8 +1280,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
       int s = 0;
       uint32_t ph = 0;
       for (int t = 0; t < n_tiles; ++t) {
-        const int bs = t & 1;
-        mbar_wait(bfull + bs, (t >> 1) & 1);
+        const int bs = p.b_bufs == 2 ? (t & 1) : 0;
+        mbar_wait(bfull + bs, (p.b_bufs == 2 ? (t >> 1) : t) & 1);
         const uint32_t b_lo32 = (((b_smem_base + uint32_t(bs) * uint32_t(b_buf_bytes)) >> 4) & 0x3FFF) | lbo16;
         for (int g = 0; g < g_count; ++g) {
           mbar_wait(afull + s, ph);
@@ -1315,8 +1316,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
     {
       const int kelems = KBLOCK_BYTES / (BF16 ? 2 : 4);
       for (int t = 0; t < n_tiles; ++t) {
-        const int bs = t & 1;
-        mbar_wait(bempty + bs, ((t >> 1) & 1) ^ 1);
+        const int bs = p.b_bufs == 2 ? (t & 1) : 0;
+        mbar_wait(bempty + bs, ((p.b_bufs == 2 ? (t >> 1) : t) & 1) ^ 1);
         const int64_t row0 = r_begin + int64_t(t) * p.R;
         if (elect_one()) {
           mbar_expect_tx(bfull + bs, uint32_t(b_buf_bytes));
@@ -1375,19 +1376,26 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
   // tile height R and gather-ring depth: want >= 3 stages in flight; the ring's last stage is followed by the blocks the
   // MMA may over-read (nb_in_alloc - nb_in), then the barriers
   const int nb_in_real = p.nb_in;
-  int R = 128, a_stages = 0;
-  for (; R >= 32; R >>= 1) {
-    const size_t blk = size_t(R) * KBLOCK_BYTES;
-    const size_t avail = 216 * 1024 - 2 * nb_out_alloc * blk - size_t(nb_in_alloc - nb_in_real) * blk;
-    if (2 * nb_out_alloc * blk + size_t(nb_in_alloc - nb_in_real) * blk >= 216 * 1024) continue;
-    a_stages = int(avail / (nb_in_real * blk));
-    if (const char* e = getenv("LGS_WG_R")) { if (R != atoi(e)) continue; if (a_stages >= 2) break; continue; }
-    if (a_stages >= 3 || (R == 32 && a_stages >= 2)) break;
+  // Per-step handshakes dominate, so the tallest tile wins: R = 128 with two gather stages beats R = 64 with six
+  // (0.34 vs 0.56 ms on the 96->96 L0 layer).  Try (R, dY buffers) from best to worst; need >= 2 gather stages.
+  int R = 0, a_stages = 0, b_bufs = 2;
+  const int cand[4][2] = {{128, 2}, {128, 1}, {64, 2}, {32, 2}};
+  for (int ci = 0; ci < 4 && R == 0; ++ci) {
+    const size_t blk = size_t(cand[ci][0]) * KBLOCK_BYTES;
+    const size_t fixed_b = size_t(cand[ci][1]) * nb_out_alloc * blk + size_t(nb_in_alloc - nb_in_real) * blk;
+    if (fixed_b >= 216 * 1024) continue;
+    const int st = int((216 * 1024 - fixed_b) / (nb_in_real * blk));
+    if (st >= 2) {
+      R = cand[ci][0];
+      b_bufs = cand[ci][1];
+      a_stages = st;
+    }
   }
   if (R < 32 || a_stages < 2) return LGS_E_UNSUPPORTED;
   if (a_stages > MAX_WA_STAGES) a_stages = MAX_WA_STAGES;
   p.R = R;
   p.a_stages = a_stages;
+  p.b_bufs = b_bufs;
   p.nb_in_real = nb_in_real;
   int G = 512 / (p.MC * p.n_cols);
   if (G < 1) return LGS_E_UNSUPPORTED;
@@ -1417,7 +1425,7 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
   // allocation counts and keep the number of gathered blocks implicit in in_row_bytes (col_ok masks the rest)
   q.nb_in = nb_in_alloc;
   q.nb_out = nb_out_alloc;
-  const size_t smem_bytes = size_t(a_stages * nb_in_real + (nb_in_alloc - nb_in_real) + 2 * nb_out_alloc) * blk_bytes +
+  const size_t smem_bytes = size_t(a_stages * nb_in_real + (nb_in_alloc - nb_in_real) + b_bufs * nb_out_alloc) * blk_bytes +
                             (2 * MAX_WA_STAGES + 8) * 8 + 1024;
 
   CUtensorMap tmap;
