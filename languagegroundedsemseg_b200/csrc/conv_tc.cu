@@ -831,33 +831,48 @@ bool tc_built() { return true; }
 // nsplit = 1: plain copy / transpose (bf16 or fp32 -> TF32 read by the hardware);
 // nsplit = 2: hi = RN_tf32(w), lo = RN_tf32(w - hi) for the 3xTF32 path.
 template <typename T>
+__device__ __forceinline__ void wp_store(T* fwd_or_bwd, int64_t idx, int64_t total, float v, int nsplit) {
+  if constexpr (sizeof(T) == 2) {
+    fwd_or_bwd[idx] = __float2bfloat16(v);
+  } else if (nsplit == 1) {
+    fwd_or_bwd[idx] = v;
+  } else {
+    uint32_t hb, lb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+    const float hi = __uint_as_float(hb);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
+    fwd_or_bwd[idx] = hi;
+    fwd_or_bwd[total + idx] = __uint_as_float(lb);
+  }
+}
+
+// grid = (ceil(c_out/32), ceil(c_in/32), K), block = (32, 8): 32x32 tile through shared memory so that both the
+// [c_in][c_out] reads and the transposed [c_out][c_in] writes are coalesced
+template <typename T>
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ w, int K, int c_in, int c_out,
                                                           int nsplit, T* __restrict__ fwd, T* __restrict__ bwd) {
+  __shared__ float tile[32][33];
+  const int k = blockIdx.z;
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 32;
   const int64_t total = int64_t(K) * c_in * c_out;
-  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (e >= total) return;
-  const int co = int(e % c_out);
-  const int ci = int((e / c_out) % c_in);
-  const int k = int(e / (int64_t(c_out) * c_in));
-  const float v = w[e];
-  const int64_t et = (int64_t(k) * c_out + co) * c_in + ci;
-  if constexpr (sizeof(T) == 2) {
-    const T b = __float2bfloat16(v);
-    if (fwd) fwd[et] = b;
-    if (bwd) bwd[e] = b;
-  } else {
-    if (nsplit == 1) {
-      if (fwd) fwd[et] = v;
-      if (bwd) bwd[e] = v;
-    } else {
-      uint32_t hb, lb;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-      const float hi = __uint_as_float(hb);
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
-      const float lo = __uint_as_float(lb);
-      if (fwd) { fwd[et] = hi; fwd[total + et] = lo; }
-      if (bwd) { bwd[e] = hi; bwd[total + e] = lo; }
+  const float* wk = w + int64_t(k) * c_in * c_out;
+#pragma unroll
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    float v = 0.f;
+    if (ci < c_in && co < c_out) {
+      v = wk[int64_t(ci) * c_out + co];
+      if (bwd) wp_store<T>(bwd, int64_t(k) * c_in * c_out + int64_t(ci) * c_out + co, total, v, nsplit);
     }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (!fwd) return;
+#pragma unroll
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    if (ci < c_in && co < c_out)
+      wp_store<T>(fwd, int64_t(k) * c_in * c_out + int64_t(co) * c_in + ci, total, tile[threadIdx.x][r], nsplit);
   }
 }
 
@@ -865,11 +880,13 @@ int weight_prep(const float* w, int K, int c_in, int c_out, int nsplit, void* fw
                 cudaStream_t stream) {
   const int64_t total = int64_t(K) * c_in * c_out;
   if (total == 0) return LGS_OK;
+  const dim3 grid{unsigned((c_out + 31) / 32), unsigned((c_in + 31) / 32), unsigned(K)};
+  const dim3 block{32u, 8u, 1u};
   if (dtype == LGS_BF16) {
-    LGS_LAUNCH(weight_prep_kernel<__nv_bfloat16>, unsigned(cdiv(total, 256)), 256, 0, stream, w, K, c_in, c_out, 1,
+    LGS_LAUNCH(weight_prep_kernel<__nv_bfloat16>, grid, block, 0, stream, w, K, c_in, c_out, 1,
                static_cast<__nv_bfloat16*>(fwd), static_cast<__nv_bfloat16*>(bwd));
   } else {
-    LGS_LAUNCH(weight_prep_kernel<float>, unsigned(cdiv(total, 256)), 256, 0, stream, w, K, c_in, c_out, nsplit,
+    LGS_LAUNCH(weight_prep_kernel<float>, grid, block, 0, stream, w, K, c_in, c_out, nsplit,
                static_cast<float*>(fwd), static_cast<float*>(bwd));
   }
   return LGS_OK;
@@ -882,7 +899,12 @@ int conv_tc_shape_ok(int c_in, int c_out, int dtype) {
   const int row_bytes = c_in * es;
   if (row_bytes % 16 != 0 || row_bytes < 16) return 0;
   if (dtype == LGS_BF16 ? (c_out % 2 != 0) : (c_out % 4 != 0)) return 0;
-  if (c_out > 256 && c_out % 256 != 0) return 0;
+  const int c_pad = ((c_out + 15) / 16) * 16;
+  if (c_pad > 256) {   // needs equal N tiles of <= 256 columns, each a multiple of 16
+    bool ok = false;
+    for (int nt = (c_pad + 255) / 256; nt <= c_pad / 16 && !ok; ++nt) ok = (c_pad % nt == 0) && ((c_pad / nt) % 16 == 0);
+    if (!ok) return 0;
+  }
   return 1;
 }
 
@@ -1007,8 +1029,9 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
   // no atomics.  Small maps (fewer tiles than SMs; the coarse U-Net levels, where the WEIGHTS are the traffic):
   // split the kernel offsets (and, if still short, the output channels) over CTAs; partial sums meet in global memory
   // through red.add on a zeroed output.
-  int n_tiles = (c_out + 255) / 256;
-  p.n_tile = n_tiles == 1 ? c_pad : 256;
+  int n_tiles = (c_pad + 255) / 256;
+  while (n_tiles > 1 && !((c_pad % n_tiles == 0) && ((c_pad / n_tiles) % 16 == 0))) ++n_tiles;   // equal tiles (384 -> 2 x 192)
+  p.n_tile = c_pad / n_tiles;
   int k_splits = 1;
   if (m_tiles * n_tiles <= 74) {
     int want = int(cdiv(148, m_tiles * n_tiles));
@@ -1025,10 +1048,6 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
         n_tiles = ns;
       }
     }
-  }
-  if (n_tiles > 1 && c_out % p.n_tile != 0 && p.n_tile == 256) {
-    // keep every N tile the same width: only multiples of 256 beyond 256 channels
-    return LGS_E_UNSUPPORTED;
   }
   p.k_per_split = (K + k_splits - 1) / k_splits;
   k_splits = (K + p.k_per_split - 1) / p.k_per_split;
@@ -1095,6 +1114,7 @@ struct WParams {
   int64_t n_out;
   int32_t K, c_in, c_out;
   float* gw;               // [K, c_in, c_out] fp32, pre-zeroed
+  int32_t n0_step;         // output-channel slice per CTA (blockIdx.z selects it); == n_cols unless channels are split
   int32_t R;               // rows per tile (32 / 64 / 128)
   int32_t nb_in, nb_out;   // 128-byte channel blocks of X / dY
   int32_t G;               // offsets per CTA
@@ -1154,6 +1174,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
   const int64_t r_begin = int64_t(blockIdx.x) * p.rows_per_chunk;
   const int64_t r_end = min(p.n_out, r_begin + p.rows_per_chunk);
   const int k0 = blockIdx.y * p.G;
+  const int n0 = blockIdx.z * p.n0_step;                  // first output channel of this CTA's slice
+  const int ncols_valid = min(p.n_cols, p.c_out - n0);
   const int g_count = min(p.G, p.K - k0);
   const int n_tiles = int((r_end - r_begin + p.R - 1) / p.R);
 
@@ -1241,19 +1263,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
       for (int mc = 0; mc < p.MC; ++mc) {
         const int ci = mc * 128 + warp * 32 + lane;
         const uint32_t col_base = uint32_t((g * p.MC + mc) * p.n_cols);
-        for (int c0 = 0; c0 < p.c_out; c0 += 32) {
+        for (int c0 = 0; c0 < ncols_valid; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + (uint32_t(warp * 32) << 16) + col_base + uint32_t(c0), v);
           if (ci < p.c_in) {
-            float* dst = p.gw + (size_t(k0 + g) * p.c_in + ci) * p.c_out + c0;
+            float* dst = p.gw + (size_t(k0 + g) * p.c_in + ci) * p.c_out + n0 + c0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              if (c0 + j + 3 < p.c_out) {
+              if (c0 + j + 3 < ncols_valid) {
                 red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                            __uint_as_float(v[j + 3]));
               } else {
                 for (int jj = j; jj < j + 4; ++jj)
-                  if (c0 + jj < p.c_out) atomicAdd(dst + jj, __uint_as_float(v[jj]));
+                  if (c0 + jj < ncols_valid) atomicAdd(dst + jj, __uint_as_float(v[jj]));
               }
             }
           }
@@ -1322,8 +1344,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
         if (elect_one()) {
           mbar_expect_tx(bfull + bs, uint32_t(b_buf_bytes));
           for (int kb = 0; kb < p.nb_out; ++kb)
-            tma_load_2d(smem_u32(b_smem + size_t(bs) * b_buf_bytes + kb * blk_bytes), &tmap_gy, bfull + bs, kb * kelems,
-                        int32_t(row0));
+            tma_load_2d(smem_u32(b_smem + size_t(bs) * b_buf_bytes + kb * blk_bytes), &tmap_gy, bfull + bs,
+                        n0 + kb * kelems, int32_t(row0));
         }
         __syncwarp();
       }
@@ -1348,7 +1370,7 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
   const int es = dtype == LGS_BF16 ? 2 : 4;
   const int in_row_bytes = c_in * es, out_row_bytes = c_out * es;
   if (in_row_bytes % 16 != 0 || out_row_bytes % 16 != 0) return LGS_E_UNSUPPORTED;
-  if (c_out % 4 != 0 || c_out > 256 || c_in > 512) return LGS_E_UNSUPPORTED;
+  if (c_out % 4 != 0 || c_in > 512) return LGS_E_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(gout) & 15) ||
       (reinterpret_cast<uintptr_t>(gw) & 15))
     return LGS_E_UNSUPPORTED;
@@ -1368,7 +1390,18 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
   p.nb_in = (in_row_bytes + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
   p.nb_out = (out_row_bytes + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
   p.MC = (c_in + 127) / 128;
-  p.n_cols = ((c_out + 15) / 16) * 16;
+  // output channels per CTA: all of them unless MC accumulators of that width exceed TMEM's 512 columns (or N > 256)
+  int n_splits = 1;
+  {
+    const int c_pad_all = ((c_out + 15) / 16) * 16;
+    while (n_splits <= c_pad_all / 16 &&
+           !((c_pad_all % n_splits == 0) && ((c_pad_all / n_splits) % 16 == 0) && (c_pad_all / n_splits) <= 256 &&
+             p.MC * (c_pad_all / n_splits) <= 512))
+      ++n_splits;
+    if (n_splits > c_pad_all / 16) return LGS_E_UNSUPPORTED;
+    p.n_cols = c_pad_all / n_splits;
+    p.n0_step = p.n_cols;
+  }
   // the MMA reads whole 128-lane chunks (and, for M = 64, 64 lanes) of channel blocks: make the stage cover them
   const int blocks_per_mc = 128 * es / KBLOCK_BYTES;   // 4 (fp32) / 2 (bf16)
   const int nb_in_alloc = p.MC * blocks_per_mc;
@@ -1411,7 +1444,7 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
   LGS_CUDA(cudaMemsetAsync(gw, 0, size_t(K) * c_in * c_out * sizeof(float), stream));
   if (n_out == 0) return LGS_OK;
 
-  int64_t chunks = (148 * 2) / groups;   // <= two CTAs' worth of work per SM, one resident at a time (TMEM)
+  int64_t chunks = (148 * 2) / (groups * n_splits);   // <= two CTAs' worth of work per SM, one resident at a time (TMEM)
   const int64_t max_chunks = cdiv(n_out, int64_t(R) * 4);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
@@ -1449,7 +1482,7 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
   });
   if (attr_err != cudaSuccess) return fail(LGS_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
 
-  const dim3 grid{unsigned(chunks), unsigned(groups), 1u};
+  const dim3 grid{unsigned(chunks), unsigned(groups), unsigned(n_splits)};
   if (dtype == LGS_BF16) {
     LGS_LAUNCH(wgrad_tc_kernel<true>, grid, THREADS, smem_bytes, stream, tmap, q);
   } else {
