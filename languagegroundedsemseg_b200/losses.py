@@ -15,7 +15,7 @@ from . import _lib
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 class _ClipCEFn(torch.autograd.Function):

@@ -57,9 +57,27 @@ def profile_end():
     return rec
 
 
+class _NoTimer:
+    __slots__ = ()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_TIMER = _NoTimer()
+
+
 class _Timed:
     """context manager: CUDA events around one C-ABI launch when profiling is on"""
     __slots__ = ("meta", "ev")
+
+    def __new__(cls, *a):
+        if _state["profile"] is None:
+            return _NO_TIMER
+        return object.__new__(cls)
 
     def __init__(self, kind, K, c_in, c_out, n_in, n_out, km, dtype):
         self.meta = (kind, K, c_in, c_out, n_in, n_out, km, dtype)
@@ -87,7 +105,19 @@ def get_conv_algo() -> str:
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # torch.cuda.current_stream() costs ~16 us per call (device-index plumbing); the raw getter is ~0.3 us
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+
+
+_tc_ok_cache = {}
+
+
+def _tc_supported(lib, c_in, c_out, dt):
+    key = (c_in, c_out, dt)
+    r = _tc_ok_cache.get(key)
+    if r is None:
+        r = _tc_ok_cache[key] = bool(lib.lgs_conv_tc_supported(c_in, c_out, dt))
+    return r
 
 
 def _dtype_code(t: torch.Tensor) -> int:
@@ -202,6 +232,14 @@ def _build_coordmap(coords: torch.Tensor, quant: int, want_maps: bool):
 
 
 class CoordinateManager:
+    # Map requests seen on earlier managers (tensor strides / kernel maps a network asks for, in order).  A strided map
+    # build needs one host sync (the row count sizes the next buffers); done lazily inside the forward pass each sync
+    # drains the launch queue.  New managers therefore pre-build everything previous ones were asked for right at
+    # SparseTensor creation — ME's manager also caches per (key, stride, kernel) but builds on first use.
+    _learned_strides = []      # [(from tensor stride, factor)]
+    _learned_kmaps = []        # [(in stride, out stride, ks, dilation, transpose)]
+    prebuild = True
+
     def __init__(self, D=3):
         if D != 3:
             raise NotImplementedError("lgs_b200 implements D = 3")
@@ -209,16 +247,32 @@ class CoordinateManager:
         self._maps = {}
         self._kmaps = {}
 
+    def _prebuild(self):
+        if not CoordinateManager.prebuild:
+            return
+        for ts, factor in list(CoordinateManager._learned_strides):
+            k = CoordinateMapKey(ts)
+            if k in self._maps:
+                self.stride(k, factor)
+        for in_ts, out_ts, ks, dil, tr in list(CoordinateManager._learned_kmaps):
+            ik, ok = CoordinateMapKey(in_ts), CoordinateMapKey(out_ts)
+            if ik in self._maps and ok in self._maps:
+                self.kernel_map(ik, ok, [ks] * 3, [dil] * 3, tr)
+
     # -- coordinate maps --------------------------------------------------------------------------------
     def insert_and_map(self, coords: torch.Tensor, tensor_stride=(1, 1, 1)):
         key = CoordinateMapKey(tensor_stride)
         cm, uidx, inv = _build_coordmap(coords, 1, True)
         self._maps[key] = cm
+        self._prebuild()
         return key, uidx, inv
 
     def stride(self, key, stride):
         s = _as_list(stride, self.D)
         nkey = CoordinateMapKey([t * q for t, q in zip(key.tensor_stride, s)])
+        req = (key.tensor_stride, tuple(s))
+        if req not in CoordinateManager._learned_strides:
+            CoordinateManager._learned_strides.append(req)
         if nkey not in self._maps:
             self._maps[nkey] = _build_coordmap(self._maps[key].coords, _uniform(list(nkey.tensor_stride), "stride"),
                                                False)
@@ -261,6 +315,9 @@ class CoordinateManager:
         km = self._kmaps.get(ck)
         if km is not None:
             return km
+        req = (in_key.tensor_stride, out_key.tensor_stride, ks, dil, bool(is_transpose))
+        if req not in CoordinateManager._learned_kmaps:
+            CoordinateManager._learned_kmaps.append(req)
         km = KernelMap()
         km.K = ks ** 3
         if is_transpose:
@@ -402,8 +459,8 @@ class _SparseConvFn(torch.autograd.Function):
             w32 = torch.nn.functional.pad(w32, (0, 0, 0, c_in - c_in_true))
         # tensor-core operand forms of the weights (one launch); a direction the TC kernels do not take (e.g. c_in = 3)
         # runs on the exact SIMT kernel with the parameter itself
-        fwd_tc = algo != _lib.ALGO_SIMT and bool(lib.lgs_conv_tc_supported(c_in, c_out, dt))
-        bwd_tc = algo != _lib.ALGO_SIMT and need_dgrad and bool(lib.lgs_conv_tc_supported(c_out, c_in, dt))
+        fwd_tc = algo != _lib.ALGO_SIMT and _tc_supported(lib, c_in, c_out, dt)
+        bwd_tc = algo != _lib.ALGO_SIMT and need_dgrad and _tc_supported(lib, c_out, c_in, dt)
         nsplit = 2 if algo == _lib.ALGO_TC3 else 1
         w_fwd = w_bwd = None
         if fwd_tc or bwd_tc:
