@@ -128,6 +128,22 @@ int lgs_conv_wgrad(const void* d_in, int64_t n_in, int32_t c_in,
                    float* d_grad_w, int32_t dtype, int32_t algo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Fused training-mode BatchNorm (+ residual add) (+ ReLU) on feature rows [n,c] fp32, c % 4 == 0.
+ *   Replaces the ATen kernels under ME.MinkowskiBatchNorm (= nn.BatchNorm1d on .F, models/modules/common.py:17-19),
+ *   MinkowskiReLU (models/res16unet.py:194) and `out += residual` (models/modules/resnet_block.py:54)   [SURVEY §8 f-1]
+ *   fwd: z = relu?( gamma * (x - mean_batch) / sqrt(var_batch + eps) + beta [+ residual] ); running stats (may be NULL)
+ *        updated in place with `momentum` (biased variance normalises, unbiased variance feeds the running estimate).
+ *   bwd: dy = dz * (z > 0)?;  dx (BatchNorm backward through the batch statistics), d_residual = dy (may be NULL),
+ *        dgamma, dbeta.   d_scratch: 2c doubles.
+ * --------------------------------------------------------------------------------------------------------- */
+int lgs_bn_fwd(const float* d_x, const float* d_residual, int64_t n, int32_t c, const float* d_gamma, const float* d_beta,
+               float eps, float momentum, int32_t relu, float* d_running_mean, float* d_running_var, float* d_z,
+               float* d_save_mean, float* d_save_invstd, double* d_scratch, void* stream);
+int lgs_bn_bwd(const float* d_x, const float* d_z, const float* d_dz, int64_t n, int32_t c, const float* d_gamma,
+               const float* d_save_mean, const float* d_save_invstd, int32_t relu, float* d_dx, float* d_dresidual,
+               float* d_dgamma, float* d_dbeta, double* d_scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * CLIP text-anchor loss.   Replaces lib/losses/ContrastiveLanguageLoss.py:224-237 (+ feat_dist :206-222) and
  * lib/losses/utils.py:99-103 (feature_sim argmax), fused:
  *   S = normalize(F) @ An^T  (An already L2-normalised, [a,c]);  loss_i = CE(S_i, y_i), 0 where y_i == ignore;

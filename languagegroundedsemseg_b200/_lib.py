@@ -29,6 +29,8 @@ SIGNATURES = {
     "lgs_weight_prep": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _i32, _p]),
     "lgs_conv_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i32, _p, _i64, _i32, _p, _p, _i32, _i32, _p]),
     "lgs_conv_wgrad": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _p, _i32, _p, _i32, _i32, _p]),
+    "lgs_bn_fwd": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _f32, _f32, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "lgs_bn_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
     "lgs_clip_ce": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _i64, _p, _p, _p, _p, _p]),
     "lgs_clip_hinge": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _p, _i32, _i64, _f32, _f32, _f32, _p, _p, _p, _p]),
     "lgs_voxelize_affine": (C.c_int, [_p, _i64, C.POINTER(C.c_double), _i32, _p, _p]),

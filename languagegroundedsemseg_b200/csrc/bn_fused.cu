@@ -1,0 +1,225 @@
+// Fused training-mode BatchNorm (+ residual add) (+ ReLU) over the rows of a feature matrix [n, c] (SURVEY.md §8 f,
+// rank 1).  Replaces, per layer, ATen's collect_statistics + transform_input + relu (+ add) in forward and
+// threshold_backward + backward_reduce + backward_elemt (+ add) in backward by 2 + 2 launches that each read the
+// feature matrix once:
+//   fwd  (1) column sums / sums of squares (fp32 per thread -> fp64 atomics per block)
+//        (2) z = relu?( gamma * (x - mean) * invstd + beta [+ residual] ),  running stats updated by block 0
+//   bwd  (3) dy = dz * (z > 0)?;  column sums of dy and dy * xhat
+//        (4) dx = gamma * invstd * (dy - mean(dy) - xhat * mean(dy * xhat));  d_residual = dy
+// Reference semantics: ME.MinkowskiBatchNorm = nn.BatchNorm1d on .F (models/modules/common.py:17-19), eps 1e-5,
+// biased variance for normalisation, unbiased for the running estimate.
+#include "common.cuh"
+
+namespace lgs {
+
+constexpr int BN_ROWS = 256;    // rows per block of the reduction kernels
+constexpr int BN_MAXT = 256;    // threads per block (rounded down to a multiple of c/4)
+
+// Column reductions stream the [rows, c] slab as one contiguous float4 array: thread t owns channel group t % (c/4)
+// (block size is a multiple of c/4), so every warp request is 512 contiguous bytes.
+__device__ __forceinline__ void bn_block_reduce(float4 a, float4 b, int cg, int c4, int c, double* sums) {
+  __shared__ float4 sa[BN_MAXT], sb[BN_MAXT];
+  sa[threadIdx.x] = a;
+  sb[threadIdx.x] = b;
+  __syncthreads();
+  if (int(threadIdx.x) < c4) {
+    double da[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};
+    for (int t = threadIdx.x; t < int(blockDim.x); t += c4) {
+      da[0] += sa[t].x; da[1] += sa[t].y; da[2] += sa[t].z; da[3] += sa[t].w;
+      db[0] += sb[t].x; db[1] += sb[t].y; db[2] += sb[t].z; db[3] += sb[t].w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(sums + cg * 4 + j, da[j]);
+      atomicAdd(sums + c + cg * 4 + j, db[j]);
+    }
+  }
+}
+
+// grid = ceil(n / BN_ROWS); block = multiple of c/4
+__global__ void __launch_bounds__(BN_MAXT)
+bn_stats_kernel(const float* __restrict__ x, int64_t n, int c, double* __restrict__ sums /*[2c]*/) {
+  const int c4 = c >> 2;
+  const int cg = threadIdx.x % c4;
+  const int64_t r0 = int64_t(blockIdx.x) * BN_ROWS, r1 = min(n, r0 + BN_ROWS);
+  const float4* p = reinterpret_cast<const float4*>(x) + r0 * c4;
+  const int64_t cnt = (r1 - r0) * c4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const float4 v = __ldg(p + i);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    b.x = fmaf(v.x, v.x, b.x); b.y = fmaf(v.y, v.y, b.y); b.z = fmaf(v.z, v.z, b.z); b.w = fmaf(v.w, v.w, b.w);
+  }
+  bn_block_reduce(a, b, cg, c4, c, sums);
+}
+
+// mean / invstd from the sums; block (0,0) also updates the running statistics
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, int64_t n, int c,
+                const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float eps, int relu, float* __restrict__ z, float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                float* running_mean, float* running_var, float momentum) {
+  extern __shared__ float sh[];   // scale[c], shift[c]
+  float* scale = sh;
+  float* shift = sh + c;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    const double mean = sums[ch] / double(n);
+    double var = sums[c + ch] / double(n) - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = float(1.0 / sqrt(var + double(eps)));
+    const float g = gamma ? gamma[ch] : 1.f, bta = beta ? beta[ch] : 0.f;
+    scale[ch] = g * invstd;
+    shift[ch] = bta - float(mean) * g * invstd;
+    if (blockIdx.x == 0) {
+      save_mean[ch] = float(mean);
+      save_invstd[ch] = invstd;
+      if (running_mean) {
+        const double unbiased = n > 1 ? var * double(n) / double(n - 1) : var;
+        running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * float(mean);
+        running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * float(unbiased);
+      }
+    }
+  }
+  __syncthreads();
+  const int64_t total4 = (n * int64_t(c)) >> 2;   // c % 4 == 0 (checked by the caller)
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total4; i += int64_t(gridDim.x) * blockDim.x) {
+    const int ch = int((i << 2) % c);
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    v.x = fmaf(v.x, scale[ch], shift[ch]);
+    v.y = fmaf(v.y, scale[ch + 1], shift[ch + 1]);
+    v.z = fmaf(v.z, scale[ch + 2], shift[ch + 2]);
+    v.w = fmaf(v.w, scale[ch + 3], shift[ch + 3]);
+    if (res) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(res) + i);
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (relu) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    }
+    reinterpret_cast<float4*>(z)[i] = v;
+  }
+}
+
+// sums of dy and dy * xhat, dy = dz * (z > 0) when relu
+__global__ void __launch_bounds__(BN_MAXT)
+bn_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ z, const float* __restrict__ dz, int64_t n, int c,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                    double* __restrict__ sums /*[2c]: sum dy, sum dy*xhat*/) {
+  const int c4 = c >> 2;
+  const int cg = threadIdx.x % c4;
+  const int64_t r0 = int64_t(blockIdx.x) * BN_ROWS, r1 = min(n, r0 + BN_ROWS);
+  const int64_t off = r0 * c4, cnt = (r1 - r0) * c4;
+  const float4* px = reinterpret_cast<const float4*>(x) + off;
+  const float4* pz = reinterpret_cast<const float4*>(z) + off;
+  const float4* pg = reinterpret_cast<const float4*>(dz) + off;
+  const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + cg), is = __ldg(reinterpret_cast<const float4*>(invstd) + cg);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+    float4 g = __ldg(pg + i);
+    if (relu) {
+      const float4 zz = __ldg(pz + i);
+      if (!(zz.x > 0.f)) g.x = 0.f;
+      if (!(zz.y > 0.f)) g.y = 0.f;
+      if (!(zz.z > 0.f)) g.z = 0.f;
+      if (!(zz.w > 0.f)) g.w = 0.f;
+    }
+    const float4 v = __ldg(px + i);
+    a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+    b.x = fmaf(g.x, (v.x - m.x) * is.x, b.x);
+    b.y = fmaf(g.y, (v.y - m.y) * is.y, b.y);
+    b.z = fmaf(g.z, (v.z - m.z) * is.z, b.z);
+    b.w = fmaf(g.w, (v.w - m.w) * is.w, b.w);
+  }
+  bn_block_reduce(a, b, cg, c4, c, sums);
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ z, const float* __restrict__ dz, int64_t n, int c,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const double* __restrict__ sums, int relu, float* __restrict__ dx, float* __restrict__ dres,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float sh[];   // k1[c] = gamma*invstd, k2[c] = mean(dy), k3[c] = mean(dy*xhat), m[c], is[c]
+  float* k1 = sh;
+  float* k2 = sh + c;
+  float* k3 = sh + 2 * c;
+  float* mm = sh + 3 * c;
+  float* is = sh + 4 * c;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    const float g = gamma ? gamma[ch] : 1.f;
+    k1[ch] = g * invstd[ch];
+    k2[ch] = float(sums[ch] / double(n));
+    k3[ch] = float(sums[c + ch] / double(n));
+    mm[ch] = mean[ch];
+    is[ch] = invstd[ch];
+    if (blockIdx.x == 0) {
+      if (dgamma) dgamma[ch] = float(sums[c + ch]);
+      if (dbeta) dbeta[ch] = float(sums[ch]);
+    }
+  }
+  __syncthreads();
+  const int64_t total4 = (n * int64_t(c)) >> 2;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total4; i += int64_t(gridDim.x) * blockDim.x) {
+    const int ch = int((i << 2) % c);
+    float4 g = __ldg(reinterpret_cast<const float4*>(dz) + i);
+    if (relu) {
+      const float4 zz = __ldg(reinterpret_cast<const float4*>(z) + i);
+      if (!(zz.x > 0.f)) g.x = 0.f;
+      if (!(zz.y > 0.f)) g.y = 0.f;
+      if (!(zz.z > 0.f)) g.z = 0.f;
+      if (!(zz.w > 0.f)) g.w = 0.f;
+    }
+    if (dres) reinterpret_cast<float4*>(dres)[i] = g;
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float4 o;
+    o.x = k1[ch] * (g.x - k2[ch] - (xv.x - mm[ch]) * is[ch] * k3[ch]);
+    o.y = k1[ch + 1] * (g.y - k2[ch + 1] - (xv.y - mm[ch + 1]) * is[ch + 1] * k3[ch + 1]);
+    o.z = k1[ch + 2] * (g.z - k2[ch + 2] - (xv.z - mm[ch + 2]) * is[ch + 2] * k3[ch + 2]);
+    o.w = k1[ch + 3] * (g.w - k2[ch + 3] - (xv.w - mm[ch + 3]) * is[ch + 3] * k3[ch + 3]);
+    reinterpret_cast<float4*>(dx)[i] = o;
+  }
+}
+
+}  // namespace lgs
+
+using namespace lgs;
+
+extern "C" {
+
+int lgs_bn_fwd(const float* d_x, const float* d_residual, int64_t n, int32_t c, const float* d_gamma, const float* d_beta,
+               float eps, float momentum, int32_t relu, float* d_running_mean, float* d_running_var, float* d_z,
+               float* d_save_mean, float* d_save_invstd, double* d_scratch /*[2c]*/, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n < 1 || c < 4 || (c & 3) || c > 1024) return fail(LGS_E_UNSUPPORTED, "lgs_bn_fwd: n=%lld c=%d (need c %% 4 == 0, c <= 1024)", (long long)n, c);
+  if (!d_x || !d_z || !d_save_mean || !d_save_invstd || !d_scratch) return fail(LGS_E_INVALID, "lgs_bn_fwd: null pointer");
+  LGS_CUDA(cudaMemsetAsync(d_scratch, 0, size_t(2 * c) * sizeof(double), stream));
+  const int red_threads = (BN_MAXT / (c / 4)) * (c / 4);
+  LGS_LAUNCH(bn_stats_kernel, unsigned(cdiv(n, BN_ROWS)), red_threads, 0, stream, d_x, n, c, d_scratch);
+  const int64_t total4 = n * c / 4;
+  int blocks = int(cdiv(total4, 256 * 4));
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  LGS_LAUNCH(bn_apply_kernel, blocks, 256, size_t(2 * c) * sizeof(float), stream, d_x, d_residual, n, c, d_scratch, d_gamma, d_beta,
+             eps, relu, d_z, d_save_mean, d_save_invstd, d_running_mean, d_running_var, momentum);
+  return LGS_OK;
+}
+
+int lgs_bn_bwd(const float* d_x, const float* d_z, const float* d_dz, int64_t n, int32_t c, const float* d_gamma,
+               const float* d_save_mean, const float* d_save_invstd, int32_t relu, float* d_dx, float* d_dresidual,
+               float* d_dgamma, float* d_dbeta, double* d_scratch /*[2c]*/, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n < 1 || c < 4 || (c & 3) || c > 1024) return fail(LGS_E_UNSUPPORTED, "lgs_bn_bwd: n=%lld c=%d", (long long)n, c);
+  if (!d_x || !d_dz || !d_dx || !d_save_mean || !d_save_invstd || !d_scratch || (relu && !d_z))
+    return fail(LGS_E_INVALID, "lgs_bn_bwd: null pointer");
+  LGS_CUDA(cudaMemsetAsync(d_scratch, 0, size_t(2 * c) * sizeof(double), stream));
+  const int red_threads = (BN_MAXT / (c / 4)) * (c / 4);
+  LGS_LAUNCH(bn_bwd_stats_kernel, unsigned(cdiv(n, BN_ROWS)), red_threads, 0, stream, d_x, d_z, d_dz, n, c, d_save_mean, d_save_invstd, relu, d_scratch);
+  const int64_t total4 = n * c / 4;
+  int blocks = int(cdiv(total4, 256 * 4));
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  LGS_LAUNCH(bn_bwd_apply_kernel, blocks, 256, size_t(5 * c) * sizeof(float), stream, d_x, d_z, d_dz, n, c, d_save_mean,
+             d_save_invstd, d_gamma, d_scratch, relu, d_dx, d_dresidual, d_dgamma, d_dbeta);
+  return LGS_OK;
+}
+
+}  // extern "C"

@@ -43,7 +43,7 @@ for _n in ("Sequence", "Iterable"):
 # 'tc'    tcgen05 tensor cores, parity-grade: 3xTF32 products for fp32 features (bf16 MMA for bf16 features)  [default]
 # 'tf32'  tcgen05 single-pass TF32 (fast, ~7e-4 relative error per layer)
 _ALGO = {"simt": _lib.ALGO_SIMT, "tc": _lib.ALGO_TC3, "tf32": _lib.ALGO_TC}
-_state = {"algo": _lib.ALGO_TC3, "profile": None}
+_state = {"algo": _lib.ALGO_TC3, "profile": None, "fuse_bn": True}
 
 
 def profile_begin():
@@ -348,9 +348,20 @@ class CoordinateManager:
 # ----------------------------------------------------------------------------------------------------------
 # SparseTensor
 # ----------------------------------------------------------------------------------------------------------
+class _PendingBN:
+    """A BatchNorm whose application is deferred so that a following `+= residual` and ReLU fuse into one kernel pair
+    (lgs_bn_fwd / lgs_bn_bwd).  The reference calls bn -> (+= residual) -> relu as separate modules
+    (models/modules/resnet_block.py:41-57, models/res16unet.py:196-270); nothing in the model code changes."""
+    __slots__ = ("bn", "x", "res", "plain", "consumed")
+
+    def __init__(self, bn, x):
+        self.bn, self.x, self.res, self.plain, self.consumed = bn, x, None, None, False
+
+
 class SparseTensor:
     def __init__(self, features, coordinates=None, coordinate_map_key=None, coordinate_manager=None,
-                 tensor_stride=1, device=None, **_ignored):
+                 tensor_stride=1, device=None, _pending=None, **_ignored):
+        self._pending = _pending
         if coordinate_map_key is None:
             if coordinates is None:
                 raise ValueError("SparseTensor needs coordinates or a coordinate_map_key")
@@ -376,6 +387,11 @@ class SparseTensor:
 
     @property
     def F(self):
+        p = self._pending
+        if p is not None:            # materialise the deferred BatchNorm (+ residual), no ReLU
+            if p.plain is None:
+                p.plain = _bn_act(p, relu=False)
+            self._F, self._pending = p.plain, None
         return self._F
 
     feats = F
@@ -392,7 +408,7 @@ class SparseTensor:
 
     @property
     def device(self):
-        return self._F.device
+        return (self._pending.x if self._pending is not None else self._F).device
 
     @property
     def D(self):
@@ -400,10 +416,10 @@ class SparseTensor:
 
     @property
     def shape(self):
-        return self._F.shape
+        return self.F.shape
 
     def __len__(self):
-        return self._F.shape[0]
+        return self.F.shape[0]
 
     def _same(self, o):
         if o.coordinate_map_key != self.coordinate_map_key or o.coordinate_manager is not self.coordinate_manager:
@@ -414,11 +430,15 @@ class SparseTensor:
 
     def __add__(self, o):
         self._same(o)
-        return self._like(self._F + o._F)
+        return self._like(self.F + o.F)
 
-    def __iadd__(self, o):  # models/modules/resnet_block.py:54
+    def __iadd__(self, o):  # models/modules/resnet_block.py:54  `out += residual`
         self._same(o)
-        self._F = self._F + o._F
+        p = self._pending
+        if p is not None and p.res is None and p.plain is None:
+            p.res = o.F              # fused into the deferred BatchNorm's epilogue
+            return self
+        self._F = self.F + o.F
         return self
 
 
@@ -426,6 +446,64 @@ def cat(*sts):
     for s in sts[1:]:
         sts[0]._same(s)
     return sts[0]._like(torch.cat([s.F for s in sts], 1))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# fused BatchNorm (+ residual) (+ ReLU)
+# ----------------------------------------------------------------------------------------------------------
+class _BNActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, bn, relu, update_running):
+        lib = _lib.load()
+        x = x.contiguous()
+        n, c = x.shape
+        if res is not None:
+            res = res.contiguous()
+        z = torch.empty_like(x)
+        stats = torch.empty((2, c), dtype=torch.float32, device=x.device)       # save_mean, save_invstd
+        scratch = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        rm = bn.running_mean if update_running else None
+        rv = bn.running_var if update_running else None
+        _lib.check(lib.lgs_bn_fwd(_lib.ptr(x), _lib.ptr(res), n, c, _lib.ptr(gamma), _lib.ptr(beta), float(bn.eps),
+                                  float(bn.momentum), 1 if relu else 0, _lib.ptr(rm), _lib.ptr(rv), _lib.ptr(z),
+                                  _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(scratch), _stream()))
+        if update_running:
+            bn.num_batches_tracked.add_(1)
+        ctx.save_for_backward(x, z if relu else None, gamma, stats)
+        ctx.relu, ctx.has_res = relu, res is not None
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        lib = _lib.load()
+        x, z, gamma, stats = ctx.saved_tensors
+        dz = dz.contiguous()
+        n, c = x.shape
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if (ctx.has_res and ctx.needs_input_grad[1]) else None
+        dgb = torch.empty((2, c), dtype=torch.float32, device=x.device)
+        scratch = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        _lib.check(lib.lgs_bn_bwd(_lib.ptr(x), _lib.ptr(z), _lib.ptr(dz), n, c, _lib.ptr(gamma), _lib.ptr(stats[0]),
+                                  _lib.ptr(stats[1]), 1 if ctx.relu else 0, _lib.ptr(dx), _lib.ptr(dres), _lib.ptr(dgb[0]),
+                                  _lib.ptr(dgb[1]), _lib.ptr(scratch), _stream()))
+        return dx, dres, dgb[0], dgb[1], None, None, None
+
+
+def _bn_act(p: _PendingBN, relu: bool):
+    out = _BNActFn.apply(p.x, p.res, p.bn.weight, p.bn.bias, p.bn, relu, not p.consumed)
+    p.consumed = True          # running statistics are updated once per BatchNorm call
+    return out
+
+
+def _bn_fusable(bn, F):
+    return (_state["fuse_bn"] and type(bn) is nn.BatchNorm1d and bn.training and bn.track_running_stats and bn.affine
+            and bn.momentum is not None and F.is_cuda and F.dtype == torch.float32 and F.dim() == 2
+            and F.shape[0] >= 1 and F.shape[1] % 4 == 0 and F.shape[1] <= 1024)
+
+
+def set_bn_fusion(flag: bool):
+    """Deferred BatchNorm -> (+ residual) -> ReLU fusion (default on); off = plain ATen ops per module."""
+    _state["fuse_bn"] = bool(flag)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -601,7 +679,11 @@ class MinkowskiBatchNorm(nn.Module):
                                  track_running_stats=track_running_stats)
 
     def forward(self, x: SparseTensor):
-        return x._like(self.bn(x.F))
+        F = x.F
+        if _bn_fusable(self.bn, F):
+            return SparseTensor(None, coordinate_map_key=x.coordinate_map_key, coordinate_manager=x.coordinate_manager,
+                                _pending=_PendingBN(self.bn, F))
+        return x._like(self.bn(F))
 
 
 class MinkowskiSyncBatchNorm(MinkowskiBatchNorm):
@@ -621,6 +703,9 @@ class MinkowskiReLU(nn.Module):
         self.inplace = inplace
 
     def forward(self, x: SparseTensor):
+        p = x._pending
+        if p is not None and p.plain is None:
+            return x._like(_bn_act(p, relu=True))      # BatchNorm (+ residual) + ReLU in one kernel pair
         return x._like(torch.relu(x.F))
 
 
