@@ -91,10 +91,10 @@ def make_scene(seed, target=TARGET_VOXELS, voxel_size=0.02):
     return scenes.synthetic_voxel_scene(seed=seed, target_voxels=target, voxel_size=voxel_size)
 
 
-def build_net(engine, device, dtype):
+def build_net(engine, device, dtype, model=None):
     from languagegroundedsemseg_b200 import nets
     torch.manual_seed(42)
-    net = nets.build_model(MODEL, 3, 200, nets.DefaultConfig(), engine=engine).to(device).train()
+    net = nets.build_model(model or MODEL, 3, 200, nets.DefaultConfig(), engine=engine).to(device).train()
     # stock torch SGD with the reference's hyper-parameters (lib/solvers.py:58-63); fused=True is torch's own single-
     # kernel implementation of the same update (CUDA only)
     kw = {"fused": True} if str(device).startswith("cuda") else {}
@@ -149,7 +149,8 @@ def run_engine(args, rank, world, local_rank):
     fdtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
 
     from languagegroundedsemseg_b200.ddp import shard_scenes
-    coords_np, feats_np, labels_np = make_scene(seed=shard_scenes(world, world, rank)[0])   # one scene per rank
+    coords_np, feats_np, labels_np = make_scene(seed=shard_scenes(world, world, rank)[0], target=args.voxels,
+                                                voxel_size=args.voxel_size)   # one scene per rank
     n_vox = coords_np.shape[0]
     # host (pinned) copies for the e2e leg; device-resident copies for `value`
     h_coords = torch.from_numpy(coords_np).pin_memory()
@@ -157,7 +158,7 @@ def run_engine(args, rank, world, local_rank):
     h_labels = torch.from_numpy(labels_np).pin_memory()
     d_coords, d_feats, d_labels = h_coords.to(dev), h_feats.to(dev).to(fdtype), h_labels.to(dev)
 
-    net, opt = build_net(None, dev, fdtype)
+    net, opt = build_net(None, dev, fdtype, args.model)
     if args.dtype == "bf16":
         # bf16 features; parameters stay fp32 (master weights), BN in fp32 statistics via autocast-free mixed dtype
         pass
@@ -313,8 +314,8 @@ def run_engine(args, rank, world, local_rank):
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.dtype == "f32" else "bf16", "data": "synthetic",
-        "config": {"workload": f"{MODEL} fwd+bwd+SGD, 1 synthetic ScanNet-shaped scene/GPU, {n_vox} voxels @2cm, 200 classes "
-                               "(BASELINE configs[1])", "voxels_per_gpu": n_vox, "algo": args.algo,
+        "config": {"workload": f"{args.model} fwd+bwd+SGD, 1 synthetic ScanNet-shaped scene/GPU, {n_vox} voxels @{args.voxel_size * 100:g}cm, "
+                               f"200 classes{' (BASELINE configs[1])' if (args.model == MODEL and args.voxels == TARGET_VOXELS) else ''}", "voxels_per_gpu": n_vox, "algo": args.algo,
                    "math": {"tc": "tcgen05 3xTF32 products (fp32-grade) fwd/dgrad, TF32 wgrad, fp32 accumulate in TMEM",
                             "tf32": "tcgen05 single-pass TF32, fp32 accumulate", "simt": "fp32 FMA"}[args.algo]
                    if args.dtype == "f32" else "tcgen05 bf16 products, fp32 accumulate in TMEM",
@@ -374,6 +375,9 @@ def main():
     ap.add_argument("--algo", default="tc", choices=["tc", "tf32", "simt"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--cpu-sample-voxels", type=int, default=60_000)
+    ap.add_argument("--model", default=MODEL, help="topology (default: the BASELINE metric's Res16UNet34C)")
+    ap.add_argument("--voxels", type=int, default=TARGET_VOXELS)
+    ap.add_argument("--voxel-size", type=float, default=0.02)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-run", action="store_true",
                     help="for ncu launch lists: allow fewer warm-up steps and skip the e2e / map-build / roofline legs")

@@ -134,7 +134,7 @@ int lgs_conv_wgrad(const void* d_in, int64_t n_in, int32_t c_in,
  *   fwd: z = relu?( gamma * (x - mean_batch) / sqrt(var_batch + eps) + beta [+ residual] ); running stats (may be NULL)
  *        updated in place with `momentum` (biased variance normalises, unbiased variance feeds the running estimate).
  *   bwd: dy = dz * (z > 0)?;  dx (BatchNorm backward through the batch statistics), d_residual = dy (may be NULL),
- *        dgamma, dbeta.   d_scratch: 2c doubles.
+ *        dgamma, dbeta.   d_scratch: 16c doubles (8 interleaved copies of the 2c column sums).
  * --------------------------------------------------------------------------------------------------------- */
 int lgs_bn_fwd(const float* d_x, const float* d_residual, int64_t n, int32_t c, const float* d_gamma, const float* d_beta,
                float eps, float momentum, int32_t relu, float* d_running_mean, float* d_running_var, float* d_z,

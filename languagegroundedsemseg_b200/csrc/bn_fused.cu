@@ -8,49 +8,57 @@
 //        (4) dx = gamma * invstd * (dy - mean(dy) - xhat * mean(dy * xhat));  d_residual = dy
 // Reference semantics: ME.MinkowskiBatchNorm = nn.BatchNorm1d on .F (models/modules/common.py:17-19), eps 1e-5,
 // biased variance for normalisation, unbiased for the running estimate.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lgs {
 
-constexpr int BN_ROWS = 256;    // rows per block of the reduction kernels
-constexpr int BN_MAXT = 256;    // threads per block (rounded down to a multiple of c/4)
+constexpr int BN_TX = 32;     // channels per block (x): one warp reads 128 contiguous bytes of a row
+constexpr int BN_TY = 8;      // row lanes per block (y)
+constexpr int BN_ROWS = 256;  // rows per block
+constexpr int BN_COPIES = 8;  // interleaved copies of the fp64 accumulators (block b adds into copy b % 8): less contention
 
-// Column reductions stream the [rows, c] slab as one contiguous float4 array: thread t owns channel group t % (c/4)
-// (block size is a multiple of c/4), so every warp request is 512 contiguous bytes.
-__device__ __forceinline__ void bn_block_reduce(float4 a, float4 b, int cg, int c4, int c, double* sums) {
-  __shared__ float4 sa[BN_MAXT], sb[BN_MAXT];
-  sa[threadIdx.x] = a;
-  sb[threadIdx.x] = b;
+__device__ __forceinline__ void bn_block_reduce(float a, float b, int ch, int c, double* sums) {
+  __shared__ float s1[BN_TY][BN_TX + 1], s2[BN_TY][BN_TX + 1];
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
   __syncthreads();
-  if (int(threadIdx.x) < c4) {
-    double da[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};
-    for (int t = threadIdx.x; t < int(blockDim.x); t += c4) {
-      da[0] += sa[t].x; da[1] += sa[t].y; da[2] += sa[t].z; da[3] += sa[t].w;
-      db[0] += sb[t].x; db[1] += sb[t].y; db[2] += sb[t].z; db[3] += sb[t].w;
-    }
+  if (threadIdx.y == 0 && ch < c) {
+    double da = 0.0, db = 0.0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      atomicAdd(sums + cg * 4 + j, da[j]);
-      atomicAdd(sums + c + cg * 4 + j, db[j]);
+    for (int j = 0; j < BN_TY; ++j) {
+      da += s1[j][threadIdx.x];
+      db += s2[j][threadIdx.x];
     }
+    double* dst = sums + size_t(blockIdx.y % BN_COPIES) * 2 * c;
+    atomicAdd(dst + ch, da);
+    atomicAdd(dst + c + ch, db);
   }
 }
 
-// grid = ceil(n / BN_ROWS); block = multiple of c/4
-__global__ void __launch_bounds__(BN_MAXT)
-bn_stats_kernel(const float* __restrict__ x, int64_t n, int c, double* __restrict__ sums /*[2c]*/) {
-  const int c4 = c >> 2;
-  const int cg = threadIdx.x % c4;
-  const int64_t r0 = int64_t(blockIdx.x) * BN_ROWS, r1 = min(n, r0 + BN_ROWS);
-  const float4* p = reinterpret_cast<const float4*>(x) + r0 * c4;
-  const int64_t cnt = (r1 - r0) * c4;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const float4 v = __ldg(p + i);
-    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-    b.x = fmaf(v.x, v.x, b.x); b.y = fmaf(v.y, v.y, b.y); b.z = fmaf(v.z, v.z, b.z); b.w = fmaf(v.w, v.w, b.w);
+// grid (ceil(c/32), ceil(n/BN_ROWS)); block (32, 8); U independent row loads in flight per thread
+template <int U>
+__global__ void __launch_bounds__(BN_TX * BN_TY)
+bn_stats_kernel(const float* __restrict__ x, int64_t n, int c, double* __restrict__ sums /*[BN_COPIES][2c]*/) {
+  const int ch = blockIdx.x * BN_TX + threadIdx.x;
+  const int64_t r0 = int64_t(blockIdx.y) * BN_ROWS + threadIdx.y;
+  const int64_t r1 = min(n, int64_t(blockIdx.y + 1) * BN_ROWS);
+  float a = 0.f, b = 0.f;
+  if (ch < c) {
+    const float* p = x + ch;
+    for (int64_t r = r0; r < r1; r += U * BN_TY) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = (r + u * BN_TY < r1) ? __ldg(p + (r + u * BN_TY) * c) : 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        a += v[u];
+        b = fmaf(v[u], v[u], b);
+      }
+    }
   }
-  bn_block_reduce(a, b, cg, c4, c, sums);
+  bn_block_reduce(a, b, ch, c, sums);
 }
 
 // mean / invstd from the sums; block (0,0) also updates the running statistics
@@ -63,8 +71,14 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, int6
   float* scale = sh;
   float* shift = sh + c;
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    const double mean = sums[ch] / double(n);
-    double var = sums[c + ch] / double(n) - mean * mean;
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < BN_COPIES; ++j) {
+      s1 += sums[size_t(j) * 2 * c + ch];
+      s2 += sums[size_t(j) * 2 * c + c + ch];
+    }
+    const double mean = s1 / double(n);
+    double var = s2 / double(n) - mean * mean;
     if (var < 0.0) var = 0.0;
     const float invstd = float(1.0 / sqrt(var + double(eps)));
     const float g = gamma ? gamma[ch] : 1.f, bta = beta ? beta[ch] : 0.f;
@@ -101,36 +115,36 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, int6
 }
 
 // sums of dy and dy * xhat, dy = dz * (z > 0) when relu
-__global__ void __launch_bounds__(BN_MAXT)
+template <int U>
+__global__ void __launch_bounds__(BN_TX * BN_TY)
 bn_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ z, const float* __restrict__ dz, int64_t n, int c,
                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
-                    double* __restrict__ sums /*[2c]: sum dy, sum dy*xhat*/) {
-  const int c4 = c >> 2;
-  const int cg = threadIdx.x % c4;
-  const int64_t r0 = int64_t(blockIdx.x) * BN_ROWS, r1 = min(n, r0 + BN_ROWS);
-  const int64_t off = r0 * c4, cnt = (r1 - r0) * c4;
-  const float4* px = reinterpret_cast<const float4*>(x) + off;
-  const float4* pz = reinterpret_cast<const float4*>(z) + off;
-  const float4* pg = reinterpret_cast<const float4*>(dz) + off;
-  const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + cg), is = __ldg(reinterpret_cast<const float4*>(invstd) + cg);
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-    float4 g = __ldg(pg + i);
-    if (relu) {
-      const float4 zz = __ldg(pz + i);
-      if (!(zz.x > 0.f)) g.x = 0.f;
-      if (!(zz.y > 0.f)) g.y = 0.f;
-      if (!(zz.z > 0.f)) g.z = 0.f;
-      if (!(zz.w > 0.f)) g.w = 0.f;
+                    double* __restrict__ sums /*[BN_COPIES][2c]: sum dy, sum dy*xhat*/) {
+  const int ch = blockIdx.x * BN_TX + threadIdx.x;
+  const int64_t r0 = int64_t(blockIdx.y) * BN_ROWS + threadIdx.y;
+  const int64_t r1 = min(n, int64_t(blockIdx.y + 1) * BN_ROWS);
+  float a = 0.f, b = 0.f;
+  if (ch < c) {
+    const float m = mean[ch], is = invstd[ch];
+    for (int64_t r = r0; r < r1; r += U * BN_TY) {
+      float g[U], zz[U], v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool ok = r + u * BN_TY < r1;
+        const int64_t i = (r + u * BN_TY) * c + ch;
+        g[u] = ok ? __ldg(dz + i) : 0.f;
+        zz[u] = (ok && relu) ? __ldg(z + i) : 1.f;
+        v[u] = ok ? __ldg(x + i) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float dy = zz[u] > 0.f ? g[u] : 0.f;
+        a += dy;
+        b = fmaf(dy, (v[u] - m) * is, b);
+      }
     }
-    const float4 v = __ldg(px + i);
-    a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
-    b.x = fmaf(g.x, (v.x - m.x) * is.x, b.x);
-    b.y = fmaf(g.y, (v.y - m.y) * is.y, b.y);
-    b.z = fmaf(g.z, (v.z - m.z) * is.z, b.z);
-    b.w = fmaf(g.w, (v.w - m.w) * is.w, b.w);
   }
-  bn_block_reduce(a, b, cg, c4, c, sums);
+  bn_block_reduce(a, b, ch, c, sums);
 }
 
 __global__ void __launch_bounds__(256)
@@ -147,13 +161,19 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ z, co
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     const float g = gamma ? gamma[ch] : 1.f;
     k1[ch] = g * invstd[ch];
-    k2[ch] = float(sums[ch] / double(n));
-    k3[ch] = float(sums[c + ch] / double(n));
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < BN_COPIES; ++j) {
+      s1 += sums[size_t(j) * 2 * c + ch];
+      s2 += sums[size_t(j) * 2 * c + c + ch];
+    }
+    k2[ch] = float(s1 / double(n));
+    k3[ch] = float(s2 / double(n));
     mm[ch] = mean[ch];
     is[ch] = invstd[ch];
     if (blockIdx.x == 0) {
-      if (dgamma) dgamma[ch] = float(sums[c + ch]);
-      if (dbeta) dbeta[ch] = float(sums[ch]);
+      if (dgamma) dgamma[ch] = float(s2);
+      if (dbeta) dbeta[ch] = float(s1);
     }
   }
   __syncthreads();
@@ -187,13 +207,18 @@ extern "C" {
 
 int lgs_bn_fwd(const float* d_x, const float* d_residual, int64_t n, int32_t c, const float* d_gamma, const float* d_beta,
                float eps, float momentum, int32_t relu, float* d_running_mean, float* d_running_var, float* d_z,
-               float* d_save_mean, float* d_save_invstd, double* d_scratch /*[2c]*/, void* stream_) {
+               float* d_save_mean, float* d_save_invstd, double* d_scratch /*[16c]*/, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n < 1 || c < 4 || (c & 3) || c > 1024) return fail(LGS_E_UNSUPPORTED, "lgs_bn_fwd: n=%lld c=%d (need c %% 4 == 0, c <= 1024)", (long long)n, c);
   if (!d_x || !d_z || !d_save_mean || !d_save_invstd || !d_scratch) return fail(LGS_E_INVALID, "lgs_bn_fwd: null pointer");
-  LGS_CUDA(cudaMemsetAsync(d_scratch, 0, size_t(2 * c) * sizeof(double), stream));
-  const int red_threads = (BN_MAXT / (c / 4)) * (c / 4);
-  LGS_LAUNCH(bn_stats_kernel, unsigned(cdiv(n, BN_ROWS)), red_threads, 0, stream, d_x, n, c, d_scratch);
+  LGS_CUDA(cudaMemsetAsync(d_scratch, 0, size_t(BN_COPIES) * 2 * c * sizeof(double), stream));
+  const dim3 grid{unsigned((c + BN_TX - 1) / BN_TX), unsigned(cdiv(n, BN_ROWS)), 1u}, block{BN_TX, BN_TY, 1u};
+  static const int unroll = getenv("LGS_BN_UNROLL") ? atoi(getenv("LGS_BN_UNROLL")) : 4;
+  if (unroll == 1) {
+    LGS_LAUNCH(bn_stats_kernel<1>, grid, block, 0, stream, d_x, n, c, d_scratch);
+  } else {
+    LGS_LAUNCH(bn_stats_kernel<4>, grid, block, 0, stream, d_x, n, c, d_scratch);
+  }
   const int64_t total4 = n * c / 4;
   int blocks = int(cdiv(total4, 256 * 4));
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -205,14 +230,19 @@ int lgs_bn_fwd(const float* d_x, const float* d_residual, int64_t n, int32_t c, 
 
 int lgs_bn_bwd(const float* d_x, const float* d_z, const float* d_dz, int64_t n, int32_t c, const float* d_gamma,
                const float* d_save_mean, const float* d_save_invstd, int32_t relu, float* d_dx, float* d_dresidual,
-               float* d_dgamma, float* d_dbeta, double* d_scratch /*[2c]*/, void* stream_) {
+               float* d_dgamma, float* d_dbeta, double* d_scratch /*[16c]*/, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n < 1 || c < 4 || (c & 3) || c > 1024) return fail(LGS_E_UNSUPPORTED, "lgs_bn_bwd: n=%lld c=%d", (long long)n, c);
   if (!d_x || !d_dz || !d_dx || !d_save_mean || !d_save_invstd || !d_scratch || (relu && !d_z))
     return fail(LGS_E_INVALID, "lgs_bn_bwd: null pointer");
-  LGS_CUDA(cudaMemsetAsync(d_scratch, 0, size_t(2 * c) * sizeof(double), stream));
-  const int red_threads = (BN_MAXT / (c / 4)) * (c / 4);
-  LGS_LAUNCH(bn_bwd_stats_kernel, unsigned(cdiv(n, BN_ROWS)), red_threads, 0, stream, d_x, d_z, d_dz, n, c, d_save_mean, d_save_invstd, relu, d_scratch);
+  LGS_CUDA(cudaMemsetAsync(d_scratch, 0, size_t(BN_COPIES) * 2 * c * sizeof(double), stream));
+  const dim3 grid{unsigned((c + BN_TX - 1) / BN_TX), unsigned(cdiv(n, BN_ROWS)), 1u}, block{BN_TX, BN_TY, 1u};
+  static const int unroll = getenv("LGS_BN_UNROLL") ? atoi(getenv("LGS_BN_UNROLL")) : 4;
+  if (unroll == 1) {
+    LGS_LAUNCH(bn_bwd_stats_kernel<1>, grid, block, 0, stream, d_x, d_z, d_dz, n, c, d_save_mean, d_save_invstd, relu, d_scratch);
+  } else {
+    LGS_LAUNCH(bn_bwd_stats_kernel<4>, grid, block, 0, stream, d_x, d_z, d_dz, n, c, d_save_mean, d_save_invstd, relu, d_scratch);
+  }
   const int64_t total4 = n * c / 4;
   int blocks = int(cdiv(total4, 256 * 4));
   if (blocks > 148 * 8) blocks = 148 * 8;

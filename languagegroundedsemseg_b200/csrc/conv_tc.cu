@@ -509,7 +509,7 @@ struct Params2 {
   const float* bias;
   void* out;
   int32_t num_kb;
-  int32_t n_tile;        // == padded c_out (this kernel does not split channels)
+  int32_t n_tile;        // output channels per CTA: padded c_out, or an equal slice of it when c_out > 256 (blockIdx.y)
   int32_t TM;            // tiles per CTA
   int32_t a_stages, b_stages;
   int32_t tmem_cols;
@@ -542,6 +542,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t m0 = int64_t(blockIdx.x) * (int64_t(TM) * BM);
+  const int n0 = blockIdx.y * p.n_tile;          // output-channel slice of this CTA (c_out > 256 is sliced)
   const int K = p.K, num_kb = p.num_kb;
 
   if (tid == 0) {
@@ -635,7 +636,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
     // =================================== epilogue ===================================
     mbar_wait(acc_bar, 0);
     tc_fence_after();
-    const int ncols = p.c_out;
+    const int ncols = min(p.n_tile, p.c_out - n0);
     const int lq = warp & 3;                       // TMEM lane quadrant this warp may read
     for (int t = warp >> 2; t < TM; t += T2_PROD_WARPS / 4) {
       const int64_t o = m0 + int64_t(t) * BM + lq * 32 + lane;
@@ -644,31 +645,31 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
         tmem_ld32(tmem_base + (uint32_t(lq * 32) << 16) + uint32_t(t * p.n_tile + c0), v);
         if (o < p.n_out) {
           if constexpr (BF16) {
-            __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out) + size_t(o) * p.c_out + c0;
+            __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out) + size_t(o) * p.c_out + n0 + c0;
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               if (c0 + j + 1 < ncols) {
-                const float x0 = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
-                const float x1 = __uint_as_float(v[j + 1]) + (p.bias ? __ldg(p.bias + c0 + j + 1) : 0.f);
+                const float x0 = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
+                const float x1 = __uint_as_float(v[j + 1]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 1) : 0.f);
                 *reinterpret_cast<__nv_bfloat162*>(orow + j) = __floats2bfloat162_rn(x0, x1);
               } else if (c0 + j < ncols) {
-                orow[j] = __float2bfloat16(__uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f));
+                orow[j] = __float2bfloat16(__uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f));
               }
             }
           } else {
-            float* orow = static_cast<float*>(p.out) + size_t(o) * p.c_out + c0;
+            float* orow = static_cast<float*>(p.out) + size_t(o) * p.c_out + n0 + c0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (c0 + j + 3 < ncols) {
                 float4 x;
-                x.x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
-                x.y = __uint_as_float(v[j + 1]) + (p.bias ? __ldg(p.bias + c0 + j + 1) : 0.f);
-                x.z = __uint_as_float(v[j + 2]) + (p.bias ? __ldg(p.bias + c0 + j + 2) : 0.f);
-                x.w = __uint_as_float(v[j + 3]) + (p.bias ? __ldg(p.bias + c0 + j + 3) : 0.f);
+                x.x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
+                x.y = __uint_as_float(v[j + 1]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 1) : 0.f);
+                x.z = __uint_as_float(v[j + 2]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 2) : 0.f);
+                x.w = __uint_as_float(v[j + 3]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 3) : 0.f);
                 *reinterpret_cast<float4*>(orow + j) = x;
               } else {
                 for (int jj = j; jj < j + 4; ++jj)
-                  if (c0 + jj < ncols) orow[jj] = __uint_as_float(v[jj]) + (p.bias ? __ldg(p.bias + c0 + jj) : 0.f);
+                  if (c0 + jj < ncols) orow[jj] = __uint_as_float(v[jj]) + (p.bias ? __ldg(p.bias + n0 + c0 + jj) : 0.f);
               }
             }
           }
@@ -739,7 +740,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
       int sb = 0;
       uint32_t phb = 0;
       for (int k = 0; k < K; ++k) {
-        const int row = k * p.c_out;
+        const int row = k * p.c_out + n0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(b_empty + sb, phb ^ 1);
           const uint32_t b_dst = b_ring_base + uint32_t(sb) * b_bytes;
@@ -899,12 +900,6 @@ int conv_tc_shape_ok(int c_in, int c_out, int dtype) {
   const int row_bytes = c_in * es;
   if (row_bytes % 16 != 0 || row_bytes < 16) return 0;
   if (dtype == LGS_BF16 ? (c_out % 2 != 0) : (c_out % 4 != 0)) return 0;
-  const int c_pad = ((c_out + 15) / 16) * 16;
-  if (c_pad > 256) {   // needs equal N tiles of <= 256 columns, each a multiple of 16
-    bool ok = false;
-    for (int nt = (c_pad + 255) / 256; nt <= c_pad / 16 && !ok; ++nt) ok = (c_pad % nt == 0) && ((c_pad / nt) % 16 == 0);
-    if (!ok) return 0;
-  }
   return 1;
 }
 
@@ -940,15 +935,19 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
 
   // ---- large maps: multi-tile CTAs sharing each weight block across TM row tiles --------------------------------
   {
-    const int c_pad2 = ((c_out + 15) / 16) * 16;
+    const int c_pad_all = ((c_out + 15) / 16) * 16;
+    // output-channel slices of <= 256 columns (multiples of 16); the last slice may be narrower (544 = 192 + 192 + 160):
+    // its surplus MMA columns read the next offset's weight rows / TMA zero fill and are never stored
+    const int n_slices = (c_pad_all + 255) / 256;
+    const int c_pad2 = ((((c_pad_all + n_slices - 1) / n_slices) + 15) / 16) * 16;     // columns per CTA
     const int64_t tiles = cdiv(n_out, BM);
     int TM = 0;
-    if (c_pad2 <= 256 && tiles >= 148 && n_in > 0 && !getenv("LGS_TC_NO_MULTI")) {
+    if (tiles * n_slices >= 148 && n_in > 0 && !getenv("LGS_TC_NO_MULTI")) {
       // pick TM in {4,2,1} minimising waves*TM (ties -> larger TM: less weight traffic)
       int64_t best = -1;
       for (int tm = 1; tm <= 4; tm *= 2) {
         if (tm * c_pad2 > 512) break;
-        const int64_t cost = cdiv(cdiv(tiles, tm), 148) * tm;
+        const int64_t cost = cdiv(cdiv(tiles, tm) * n_slices, 148) * tm;
         if (best < 0 || cost <= best) {
           best = cost;
           TM = tm;
@@ -998,7 +997,7 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr2 != CUDA_SUCCESS) return fail(LGS_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(cr2));
-        const dim3 grid2{unsigned(cdiv(tiles, TM)), 1u, 1u};
+        const dim3 grid2{unsigned(cdiv(tiles, TM)), unsigned(n_slices), 1u};
         if (dtype == LGS_BF16) {
           LGS_LAUNCH((conv_tc2_kernel<true, false>), grid2, T2_THREADS, smem2, stream, tmap2, q);
         } else if (precise) {
@@ -1030,8 +1029,7 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
   // split the kernel offsets (and, if still short, the output channels) over CTAs; partial sums meet in global memory
   // through red.add on a zeroed output.
   int n_tiles = (c_pad + 255) / 256;
-  while (n_tiles > 1 && !((c_pad % n_tiles == 0) && ((c_pad / n_tiles) % 16 == 0))) ++n_tiles;   // equal tiles (384 -> 2 x 192)
-  p.n_tile = c_pad / n_tiles;
+  p.n_tile = ((((c_pad + n_tiles - 1) / n_tiles) + 15) / 16) * 16;   // <= 256; the last slice may be narrower (544 = 192+192+160)
   int k_splits = 1;
   if (m_tiles * n_tiles <= 74) {
     int want = int(cdiv(148, m_tiles * n_tiles));
@@ -1118,7 +1116,9 @@ struct WParams {
   int32_t R;               // rows per tile (32 / 64 / 128)
   int32_t nb_in, nb_out;   // 128-byte channel blocks of X / dY
   int32_t G;               // offsets per CTA
-  int32_t MC;              // 128-lane chunks of c_in
+  int32_t MC;              // 128-lane chunks of c_in handled by one CTA
+  int32_t MC_total;        // all chunks of c_in (blockIdx.z / n_splits selects the CTA's first chunk)
+  int32_t n_splits;        // output-channel slices
   int32_t n_cols;          // accumulator columns (c_out padded to 16)
   int32_t tmem_cols;
   int64_t rows_per_chunk;  // multiple of R
@@ -1174,7 +1174,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
   const int64_t r_begin = int64_t(blockIdx.x) * p.rows_per_chunk;
   const int64_t r_end = min(p.n_out, r_begin + p.rows_per_chunk);
   const int k0 = blockIdx.y * p.G;
-  const int n0 = blockIdx.z * p.n0_step;                  // first output channel of this CTA's slice
+  const int n0 = (blockIdx.z % p.n_splits) * p.n0_step;   // first output channel of this CTA's slice
+  const int mc0 = (blockIdx.z / p.n_splits) * p.MC;       // first 128-channel chunk of the input channels it owns
+  const int mc_cnt = min(p.MC, p.MC_total - mc0);
+  const int in_col0 = mc0 * 128 * (BF16 ? 2 : 4);         // byte offset of that chunk inside a feature row
   const int ncols_valid = min(p.n_cols, p.c_out - n0);
   const int g_count = min(p.G, p.K - k0);
   const int n_tiles = int((r_end - r_begin + p.R - 1) / p.R);
@@ -1214,7 +1217,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
       dst_off[i] = uint32_t(r * KBLOCK_BYTES) + (mn_chunk_pos<BF16>(chunk, r) << 4);
     }
     const int row_bytes = p.in_row_bytes;
-    const uint8_t* in_chunk = p.in + chunk * 16;
+    const uint8_t* in_chunk = p.in + in_col0 + chunk * 16;
     const uint32_t a_smem_base = smem_u32(a_smem);
     int s = 0;
     uint32_t ph = 0;
@@ -1238,7 +1241,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
         uint32_t a_base = a_smem_base + uint32_t(s) * uint32_t(a_stage_bytes);
         int col = chunk * 16;
         for (int kb = 0; kb < p.nb_in_real; ++kb, col += KBLOCK_BYTES, a_base += blk_bytes) {
-          const bool col_ok = col < row_bytes;
+          const bool col_ok = in_col0 + col < row_bytes;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (i < passes) {
@@ -1260,8 +1263,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     for (int g = 0; g < (n_tiles > 0 ? g_count : 0); ++g) {
-      for (int mc = 0; mc < p.MC; ++mc) {
-        const int ci = mc * 128 + warp * 32 + lane;
+      for (int mc = 0; mc < mc_cnt; ++mc) {
+        const int ci = (mc0 + mc) * 128 + warp * 32 + lane;
         const uint32_t col_base = uint32_t((g * p.MC + mc) * p.n_cols);
         for (int c0 = 0; c0 < ncols_valid; c0 += 32) {
           uint32_t v[32];
@@ -1311,7 +1314,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
           tc_fence_after();
           const uint32_t a_base = a_smem_base + uint32_t(s) * uint32_t(a_stage_bytes);
           if (elect_one()) {
-            for (int mc = 0; mc < p.MC; ++mc) {
+            for (int mc = 0; mc < mc_cnt; ++mc) {
               const uint32_t d_addr = tmem_base + uint32_t((g * p.MC + mc) * p.n_cols);
               const uint32_t a_lo32 = (((a_base + uint32_t(mc * mc_blocks) * uint32_t(blk_bytes)) >> 4) & 0x3FFF) | lbo16;
 #pragma unroll 4
@@ -1370,7 +1373,7 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
   const int es = dtype == LGS_BF16 ? 2 : 4;
   const int in_row_bytes = c_in * es, out_row_bytes = c_out * es;
   if (in_row_bytes % 16 != 0 || out_row_bytes % 16 != 0) return LGS_E_UNSUPPORTED;
-  if (c_out % 4 != 0 || c_in > 512) return LGS_E_UNSUPPORTED;
+  if (c_out % 4 != 0) return LGS_E_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(gout) & 15) ||
       (reinterpret_cast<uintptr_t>(gw) & 15))
     return LGS_E_UNSUPPORTED;
@@ -1389,41 +1392,49 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
   p.gw = gw;
   p.nb_in = (in_row_bytes + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
   p.nb_out = (out_row_bytes + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
-  p.MC = (c_in + 127) / 128;
-  // output channels per CTA: all of them unless MC accumulators of that width exceed TMEM's 512 columns (or N > 256)
-  int n_splits = 1;
-  {
-    const int c_pad_all = ((c_out + 15) / 16) * 16;
-    while (n_splits <= c_pad_all / 16 &&
-           !((c_pad_all % n_splits == 0) && ((c_pad_all / n_splits) % 16 == 0) && (c_pad_all / n_splits) <= 256 &&
-             p.MC * (c_pad_all / n_splits) <= 512))
-      ++n_splits;
-    if (n_splits > c_pad_all / 16) return LGS_E_UNSUPPORTED;
-    p.n_cols = c_pad_all / n_splits;
-    p.n0_step = p.n_cols;
-  }
-  // the MMA reads whole 128-lane chunks (and, for M = 64, 64 lanes) of channel blocks: make the stage cover them
-  const int blocks_per_mc = 128 * es / KBLOCK_BYTES;   // 4 (fp32) / 2 (bf16)
-  const int nb_in_alloc = p.MC * blocks_per_mc;
+  // Decomposition over channels: output channels in slices of <= 256 columns (MMA N), input channels in groups of MC
+  // 128-lane chunks with MC * n_cols <= 512 TMEM columns.  Slicing the INPUT channels is preferred: each CTA then gathers
+  // only its own channels (the gather is the expensive stream; the dY tile is a plain TMA load).
+  p.MC_total = (c_in + 127) / 128;
+  const int c_pad_all = ((c_out + 15) / 16) * 16;
+  const int n_splits = (c_pad_all + 255) / 256;
+  p.n_cols = ((((c_pad_all + n_splits - 1) / n_splits) + 15) / 16) * 16;
+  p.n0_step = p.n_cols;
+  p.n_splits = n_splits;
+  const int blocks_per_mc = 128 * es / KBLOCK_BYTES;   // channel blocks per 128-lane chunk: 4 (fp32) / 2 (bf16)
   const int nb_out_alloc = (p.n_cols * es + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
-  // tile height R and gather-ring depth: want >= 3 stages in flight; the ring's last stage is followed by the blocks the
-  // MMA may over-read (nb_in_alloc - nb_in), then the barriers
-  const int nb_in_real = p.nb_in;
-  // Per-step handshakes dominate, so the tallest tile wins: R = 128 with two gather stages beats R = 64 with six
-  // (0.34 vs 0.56 ms on the 96->96 L0 layer).  Try (R, dY buffers) from best to worst; need >= 2 gather stages.
-  int R = 0, a_stages = 0, b_bufs = 2;
+  // Choose (MC, R, dY buffers): per-step handshakes dominate, so the tallest row tile wins (R = 128 with two gather stages
+  // beats R = 64 with six: 0.34 vs 0.56 ms on the 96->96 L0 layer); ties go to the larger MC.  The MMA reads whole
+  // 128-lane chunks; blocks a CTA does not gather (c_in not a multiple of 128) alias the next stage: finite garbage in
+  // accumulator rows >= c_in, never stored.
+  int mc_max = 512 / p.n_cols;
+  if (mc_max > p.MC_total) mc_max = p.MC_total;
+  if (mc_max > 4) mc_max = 4;
+  int R = 0, a_stages = 0, b_bufs = 2, nb_in_alloc = 0, nb_in_real = 0;
+  p.MC = 0;
   const int cand[4][2] = {{128, 2}, {128, 1}, {64, 2}, {32, 2}};
-  for (int ci = 0; ci < 4 && R == 0; ++ci) {
-    const size_t blk = size_t(cand[ci][0]) * KBLOCK_BYTES;
-    const size_t fixed_b = size_t(cand[ci][1]) * nb_out_alloc * blk + size_t(nb_in_alloc - nb_in_real) * blk;
-    if (fixed_b >= 216 * 1024) continue;
-    const int st = int((216 * 1024 - fixed_b) / (nb_in_real * blk));
-    if (st >= 2) {
-      R = cand[ci][0];
-      b_bufs = cand[ci][1];
-      a_stages = st;
+  for (int mc = mc_max; mc >= 1; --mc) {
+    const int alloc = mc * blocks_per_mc;
+    const int real = p.nb_in < alloc ? p.nb_in : alloc;
+    for (int ci = 0; ci < 4; ++ci) {
+      const size_t blk = size_t(cand[ci][0]) * KBLOCK_BYTES;
+      const size_t fixed_b = size_t(cand[ci][1]) * nb_out_alloc * blk + size_t(alloc - real) * blk;
+      if (fixed_b >= 216 * 1024) continue;
+      const int st = int((216 * 1024 - fixed_b) / (real * blk));
+      if (st < 2) continue;
+      if (cand[ci][0] > R) {
+        R = cand[ci][0];
+        b_bufs = cand[ci][1];
+        a_stages = st;
+        p.MC = mc;
+        nb_in_alloc = alloc;
+        nb_in_real = real;
+      }
+      break;   // first (tallest) candidate that fits for this mc
     }
   }
+  if (p.MC == 0) return LGS_E_UNSUPPORTED;
+  const int m_slices = (p.MC_total + p.MC - 1) / p.MC;
   if (R < 32 || a_stages < 2) return LGS_E_UNSUPPORTED;
   if (a_stages > MAX_WA_STAGES) a_stages = MAX_WA_STAGES;
   p.R = R;
@@ -1444,7 +1455,7 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
   LGS_CUDA(cudaMemsetAsync(gw, 0, size_t(K) * c_in * c_out * sizeof(float), stream));
   if (n_out == 0) return LGS_OK;
 
-  int64_t chunks = (148 * 2) / (groups * n_splits);   // <= two CTAs' worth of work per SM, one resident at a time (TMEM)
+  int64_t chunks = (148 * 2) / (groups * n_splits * m_slices);   // <= two CTAs' worth of work per SM, one resident at a time (TMEM)
   const int64_t max_chunks = cdiv(n_out, int64_t(R) * 4);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
@@ -1482,7 +1493,7 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
   });
   if (attr_err != cudaSuccess) return fail(LGS_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
 
-  const dim3 grid{unsigned(chunks), unsigned(groups), unsigned(n_splits)};
+  const dim3 grid{unsigned(chunks), unsigned(groups), unsigned(n_splits * m_slices)};
   if (dtype == LGS_BF16) {
     LGS_LAUNCH(wgrad_tc_kernel<true>, grid, THREADS, smem_bytes, stream, tmap, q);
   } else {

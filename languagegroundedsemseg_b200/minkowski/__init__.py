@@ -461,7 +461,7 @@ class _BNActFn(torch.autograd.Function):
             res = res.contiguous()
         z = torch.empty_like(x)
         stats = torch.empty((2, c), dtype=torch.float32, device=x.device)       # save_mean, save_invstd
-        scratch = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        scratch = torch.empty(16 * c, dtype=torch.float64, device=x.device)
         rm = bn.running_mean if update_running else None
         rv = bn.running_var if update_running else None
         _lib.check(lib.lgs_bn_fwd(_lib.ptr(x), _lib.ptr(res), n, c, _lib.ptr(gamma), _lib.ptr(beta), float(bn.eps),
@@ -482,7 +482,7 @@ class _BNActFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if (ctx.has_res and ctx.needs_input_grad[1]) else None
         dgb = torch.empty((2, c), dtype=torch.float32, device=x.device)
-        scratch = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        scratch = torch.empty(16 * c, dtype=torch.float64, device=x.device)
         _lib.check(lib.lgs_bn_bwd(_lib.ptr(x), _lib.ptr(z), _lib.ptr(dz), n, c, _lib.ptr(gamma), _lib.ptr(stats[0]),
                                   _lib.ptr(stats[1]), 1 if ctx.relu else 0, _lib.ptr(dx), _lib.ptr(dres), _lib.ptr(dgb[0]),
                                   _lib.ptr(dgb[1]), _lib.ptr(scratch), _stream()))

@@ -64,6 +64,8 @@ CASES = [
     (96, 200, 1, 1, False, True),     # final
     (128, 96, 1, 1, False, False),    # block downsample branch
     (5, 7, 3, 1, False, True),        # ragged channel counts
+    (136, 264, 3, 1, False, False),   # > 256 output channels: unequal slices (144 + 120); dgrad 264 -> 136
+    (264, 136, 3, 1, False, True),    # wgrad with 3 lane chunks of input channels
 ]
 
 
