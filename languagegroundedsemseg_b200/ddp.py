@@ -37,3 +37,31 @@ def wrap_ddp(net, local_rank=None):
     if next(net.parameters()).is_cuda:
         return DDP(net, device_ids=[local_rank], find_unused_parameters=False, gradient_as_bucket_view=True)
     return DDP(net, find_unused_parameters=False)
+
+
+class GradAllReducer:
+    """The path's only collective, done once per step on ONE flat buffer: concat the gradients, NCCL all-reduce (mean),
+    scatter back.  Replaces DistributedDataParallel's per-parameter autograd hooks and bucketing, whose host cost
+    (~4.5 ms per step for the 374 parameter tensors of Res16UNet34C) lands on the critical path of a host-bound step;
+    the 151 MB all-reduce itself takes ~0.4 ms over NVLink/NVSwitch.  Parameters must start identical on every rank
+    (same seed, or call `broadcast_parameters`)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        self.sizes = [p.numel() for p in self.params]
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def broadcast_parameters(self, src=0):
+        if self.world > 1:
+            for p in self.params:
+                dist.broadcast(p.data, src)
+
+    def __call__(self):
+        if self.world == 1:
+            return
+        grads = [p.grad.view(-1) for p in self.params]
+        flat = torch.cat(grads)
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG if flat.is_cuda else dist.ReduceOp.SUM)
+        if not flat.is_cuda:
+            flat.div_(self.world)          # gloo has no AVG
+        torch._foreach_copy_(grads, list(flat.split(self.sizes)))

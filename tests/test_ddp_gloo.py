@@ -39,10 +39,16 @@ def _worker(rank, world, port, out_dir):
     r, w, _ = ddp.init_process_group("gloo")
     assert (r, w) == (rank, world)
     net, coords, feats, labels = _scene_grads(rank, me_cpu)
-    model = ddp.wrap_ddp(net)
+    if os.environ.get("LGS_TEST_USE_DDP"):
+        model = ddp.wrap_ddp(net)                       # stock DistributedDataParallel
+        reducer = None
+    else:
+        model, reducer = net, ddp.GradAllReducer(net.parameters())   # bench.py's path: one flat all-reduce
     out, _ = model(me_cpu.SparseTensor(torch.from_numpy(feats), torch.from_numpy(coords)))
     loss = torch.nn.functional.cross_entropy(out.F, torch.from_numpy(labels), ignore_index=-1)
     loss.backward()
+    if reducer is not None:
+        reducer()
     torch.save({k: p.grad.clone() for k, p in net.named_parameters()}, os.path.join(out_dir, f"g{rank}.pt"))
     n = torch.tensor([coords.shape[0]], dtype=torch.float64)
     dist.all_reduce(n)                                  # bench.py's voxel total over ranks
@@ -51,7 +57,12 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_ddp_gloo_two_ranks(tmp_path):
+@pytest.mark.parametrize("use_ddp", [False, True])
+def test_ddp_gloo_two_ranks(tmp_path, use_ddp, monkeypatch):
+    if use_ddp:
+        monkeypatch.setenv("LGS_TEST_USE_DDP", "1")
+    else:
+        monkeypatch.delenv("LGS_TEST_USE_DDP", raising=False)
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
