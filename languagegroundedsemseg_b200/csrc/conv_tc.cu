@@ -144,6 +144,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// TS form: A operand (128 rows x 8 tf32) read from TMEM (lane = row, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 struct Params {
   const uint8_t* in;        // [n_in, c_in] features (fp32 or bf16)
   int64_t n_in;
@@ -514,9 +534,11 @@ struct Params2 {
   int32_t a_stages, b_stages;
   int32_t tmem_cols;
   int32_t b_stage_bytes;
+  int32_t ta_stages;     // PRECISE: TMEM ring of split A operands (64 columns each: hi | lo), after the TM accumulators
+  int32_t ta_col0;       // first TMEM column of that ring
 };
 
-constexpr int MAX_A_STAGES = 12, MAX_B_STAGES = 4;
+constexpr int MAX_A_STAGES = 12, MAX_B_STAGES = 4, MAX_TA_STAGES = 4;
 constexpr int T2_PROD_WARPS = 8;                       // gather producers (and epilogue)
 constexpr int T2_THREADS = (T2_PROD_WARPS + 2) * 32;    // + MMA issuer warp + weight TMA warp
 
@@ -526,7 +548,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int NSPLIT = PRECISE ? 2 : 1;
-  constexpr uint32_t A_BYTES = NSPLIT * A_STAGE_BYTES;          // [A hi | A lo]
+  constexpr uint32_t A_BYTES = A_STAGE_BYTES;                   // raw gathered tile; PRECISE: its hi/lo split lives in TMEM
   const uint32_t b_bytes = NSPLIT * p.b_stage_bytes;             // [B hi | B lo]
   const int SA = p.a_stages, SB = p.b_stages, TM = p.TM;
   uint8_t* a_ring = smem;
@@ -537,7 +559,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
   uint64_t* a_split = a_empty + MAX_A_STAGES;
   uint64_t* b_full = a_split + MAX_A_STAGES;
   uint64_t* b_empty = b_full + MAX_B_STAGES;
-  uint64_t* acc_bar = b_empty + MAX_B_STAGES;
+  uint64_t* ta_full = b_empty + MAX_B_STAGES;     // PRECISE: split A operand of a stage is in TMEM
+  uint64_t* ta_empty = ta_full + MAX_TA_STAGES;   // PRECISE: MMAs reading that TMEM stage have completed
+  uint64_t* acc_bar = ta_empty + MAX_TA_STAGES;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -548,8 +572,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
   if (tid == 0) {
     for (int s = 0; s < SA; ++s) {
       mbar_init(a_full + s, T2_PROD_WARPS * 32);   // cp.async-completion arrivals of the producer threads
-      mbar_init(a_empty + s, 1);
+      mbar_init(a_empty + s, PRECISE ? 128 : 1);   // PRECISE: freed by the 128 splitter threads once they have read it
       mbar_init(a_split + s, 128);
+    }
+    for (int s = 0; s < MAX_TA_STAGES; ++s) {
+      mbar_init(ta_full + s, 128);
+      mbar_init(ta_empty + s, 1);
     }
     for (int s = 0; s < SB; ++s) {
       mbar_init(b_full + s, 1);
@@ -685,40 +713,58 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
       const uint32_t desc_hi = uint32_t(1024 >> 4) | (1u << 14) | (2u << 29);
       const uint32_t a_ring_base = smem_u32(a_ring), b_ring_base = smem_u32(b_ring);
       const int row_bytes = p.row_bytes;
-      int sa = 0, sb = 0;
-      uint32_t pha = 0, phb = 0;
+      int sa = 0, sb = 0, tsa = 0;
+      uint32_t pha = 0, phb = 0, phta = 0;
+      (void)sa; (void)pha; (void)tsa; (void)phta; (void)a_ring_base;
       for (int k = 0; k < K; ++k) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(b_full + sb, phb);
+          if constexpr (PRECISE) fence_proxy_async();
           const uint32_t b_base = b_ring_base + uint32_t(sb) * b_bytes;
           const uint32_t b_lo32 = ((b_base >> 4) & 0x3FFF) | (1u << 16);
           const int valid = min(KBLOCK_BYTES, row_bytes - kb * KBLOCK_BYTES);
           const int ksteps = (valid + 31) >> 5;
           const uint32_t acc_flag = (k | kb) ? 1u : 0u;
           for (int t = 0; t < TM; ++t) {
-            mbar_wait(a_full + sa, pha);
-            if constexpr (PRECISE) mbar_wait(a_split + sa, pha);
-            fence_proxy_async();   // generic-proxy writes (cp.async / splitters) -> visible to the tensor core's reads
-            tc_fence_after();
-            const uint32_t a_base = a_ring_base + uint32_t(sa) * A_BYTES;
-            const uint32_t a_lo32 = ((a_base >> 4) & 0x3FFF) | (1u << 16);
             const uint32_t d_addr = tmem_base + uint32_t(t * p.n_tile);
-            if (elect_one()) {
+            if constexpr (PRECISE) {
+              // A operand (hi | lo) comes from TMEM, written by the splitter warps; only the weights are read from smem
+              mbar_wait(ta_full + tsa, phta);
+              tc_fence_after();
+              const uint32_t a_tm = tmem_base + uint32_t(p.ta_col0 + tsa * 64);
+              if (elect_one()) {
 #pragma unroll 4
-              for (int j = 0; j < ksteps; ++j) {
-                const uint64_t a_hi = desc_from(a_lo32 + 2 * j, desc_hi), b_hi = desc_from(b_lo32 + 2 * j, desc_hi);
-                umma<BF16>(d_addr, a_hi, b_hi, idesc, acc_flag | uint32_t(j));
-                if constexpr (PRECISE) {
-                  umma<BF16>(d_addr, desc_from(a_lo32 + (A_STAGE_BYTES >> 4) + 2 * j, desc_hi), b_hi, idesc, 1u);
-                  umma<BF16>(d_addr, a_hi, desc_from(b_lo32 + (p.b_stage_bytes >> 4) + 2 * j, desc_hi), idesc, 1u);
+                for (int j = 0; j < ksteps; ++j) {
+                  const uint64_t b_hi = desc_from(b_lo32 + 2 * j, desc_hi);
+                  umma_ts_tf32(d_addr, a_tm + 8 * j, b_hi, idesc, acc_flag | uint32_t(j));
+                  umma_ts_tf32(d_addr, a_tm + 32 + 8 * j, b_hi, idesc, 1u);
+                  umma_ts_tf32(d_addr, a_tm + 8 * j, desc_from(b_lo32 + (p.b_stage_bytes >> 4) + 2 * j, desc_hi), idesc, 1u);
                 }
+                umma_commit(ta_empty + tsa);
               }
-              umma_commit(a_empty + sa);
-            }
-            __syncwarp();
-            if (++sa == SA) {
-              sa = 0;
-              pha ^= 1;
+              __syncwarp();
+              if (++tsa == p.ta_stages) {
+                tsa = 0;
+                phta ^= 1;
+              }
+            } else {
+              mbar_wait(a_full + sa, pha);
+              fence_proxy_async();   // generic-proxy writes (cp.async) -> visible to the tensor core's reads
+              tc_fence_after();
+              const uint32_t a_base = a_ring_base + uint32_t(sa) * A_BYTES;
+              const uint32_t a_lo32 = ((a_base >> 4) & 0x3FFF) | (1u << 16);
+              if (elect_one()) {
+#pragma unroll 4
+                for (int j = 0; j < ksteps; ++j)
+                  umma<BF16>(d_addr, desc_from(a_lo32 + 2 * j, desc_hi), desc_from(b_lo32 + 2 * j, desc_hi), idesc,
+                             acc_flag | uint32_t(j));
+                umma_commit(a_empty + sa);
+              }
+              __syncwarp();
+              if (++sa == SA) {
+                sa = 0;
+                pha ^= 1;
+              }
             }
           }
           if (elect_one()) umma_commit(b_empty + sb);
@@ -761,36 +807,45 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
   }
   if constexpr (PRECISE) {
     if (warp >= T2_PROD_WARPS + 2) {
-      // =================================== hi/lo splitters (128 threads) ===================================
-      const int st = tid - T2_THREADS;
+      // =================================== hi/lo splitters (128 threads): smem tile -> TMEM ===================================
+      // thread <-> row of the tile (TMEM lane): read the row's 8 swizzled 16-byte chunks, split, tcgen05.st hi and lo.
+      const int lq = warp & 3;                     // TMEM lane quadrant this warp may access
+      const int r = lq * 32 + lane;
+      const uint32_t lane_addr = uint32_t(lq * 32) << 16;
       const int total = K * num_kb * TM;
-      int s = 0;
-      uint32_t ph = 0;
+      int s = 0, ts = 0;
+      uint32_t ph = 0, pht = 0;
       for (int it = 0; it < total; ++it) {
-        mbar_wait(a_full + s, ph);
-        float4* a_hi = reinterpret_cast<float4*>(a_ring + size_t(s) * A_BYTES) + st;
-        float4* a_lo = reinterpret_cast<float4*>(a_ring + size_t(s) * A_BYTES + A_STAGE_BYTES) + st;
-        float4 v[8];
+        mbar_wait(a_full + s, ph);                 // gathered rows have landed (cp.async completion arrivals)
+        const uint8_t* a_row = a_ring + size_t(s) * A_BYTES + r * KBLOCK_BYTES;
+        uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = a_hi[128 * i];
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(a_row + ((c ^ (r & 7)) << 4));
+          const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u);
-          h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u);
-          h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u);
-          h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u);
-          l.x = v[i].x - h.x;
-          l.y = v[i].y - h.y;
-          l.z = v[i].z - h.z;
-          l.w = v[i].w - h.w;
-          a_lo[128 * i] = l;
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t h = __float_as_uint(f[e]) & 0xFFFFE000u;
+            hi[c * 4 + e] = h;
+            lo[c * 4 + e] = __float_as_uint(f[e] - __uint_as_float(h));
+          }
         }
-        fence_proxy_async();
-        mbar_arrive(a_split + s);
+        mbar_arrive(a_empty + s);                  // the shared-memory stage can be refilled
+        mbar_wait(ta_empty + ts, pht ^ 1);         // MMAs that read this TMEM stage last time are done
+        tc_fence_after();
+        const uint32_t ta = tmem_base + lane_addr + uint32_t(p.ta_col0 + ts * 64);
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(ta_full + ts);
         if (++s == SA) {
           s = 0;
           ph ^= 1;
+        }
+        if (++ts == p.ta_stages) {
+          ts = 0;
+          pht ^= 1;
         }
       }
     }
@@ -942,11 +997,12 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
     const int c_pad2 = ((((c_pad_all + n_slices - 1) / n_slices) + 15) / 16) * 16;     // columns per CTA
     const int64_t tiles = cdiv(n_out, BM);
     int TM = 0;
+    const int ta_min_cols = precise ? 128 : 0;   // PRECISE keeps >= 2 split-A stages (64 columns each) in TMEM
     if (tiles * n_slices >= 148 && n_in > 0 && !getenv("LGS_TC_NO_MULTI")) {
       // pick TM in {4,2,1} minimising waves*TM (ties -> larger TM: less weight traffic)
       int64_t best = -1;
       for (int tm = 1; tm <= 4; tm *= 2) {
-        if (tm * c_pad2 > 512) break;
+        if (tm * c_pad2 + ta_min_cols > 512) break;
         const int64_t cost = cdiv(cdiv(tiles, tm) * n_slices, 148) * tm;
         if (best < 0 || cost <= best) {
           best = cost;
@@ -955,7 +1011,7 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
       }
       if (const char* e = getenv("LGS_TC_TM")) TM = atoi(e);
     }
-    if (TM >= 2) {
+    if (TM >= 2 || (TM == 1 && precise && getenv("LGS_TC_TS1"))) {
       Params2 q;
       q.in = static_cast<const uint8_t*>(in);
       q.row_bytes = row_bytes;
@@ -970,11 +1026,14 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
       q.n_tile = c_pad2;
       q.TM = TM;
       q.b_stage_bytes = c_pad2 * KBLOCK_BYTES;
+      q.ta_col0 = ((TM * c_pad2 + 31) / 32) * 32;
+      q.ta_stages = precise ? (512 - q.ta_col0) / 64 : 0;
+      if (q.ta_stages > MAX_TA_STAGES) q.ta_stages = MAX_TA_STAGES;
       int cols = 32;
-      while (cols < TM * c_pad2) cols <<= 1;
+      while (cols < (precise ? q.ta_col0 + q.ta_stages * 64 : TM * c_pad2)) cols <<= 1;
       q.tmem_cols = cols;
-      const int a_bytes = nsplit * A_STAGE_BYTES, b_bytes = nsplit * q.b_stage_bytes;
-      const int fixed2 = 2 * 4 * BM * 4 + (3 * MAX_A_STAGES + 2 * MAX_B_STAGES + 1) * 8 + 16 + 1024;
+      const int a_bytes = A_STAGE_BYTES, b_bytes = nsplit * q.b_stage_bytes;
+      const int fixed2 = 2 * 4 * BM * 4 + (3 * MAX_A_STAGES + 2 * MAX_B_STAGES + 2 * MAX_TA_STAGES + 1) * 8 + 16 + 1024;
       int sb = 2;
       int sa = (227 * 1024 - fixed2 - sb * b_bytes) / a_bytes;
       if (sa > MAX_A_STAGES) sa = MAX_A_STAGES;
