@@ -515,8 +515,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
 // accumulators in TMEM (TM * n_tile <= 512 columns).  Loop order  offset k -> channel block kb -> tile t :
 // every weight block W[k][kb] is TMA-loaded ONCE per CTA and feeds TM MMAs groups, cutting the L2->SM weight traffic
 // (the dominant stream of the single-tile kernel: 27 * Cin * Cout * 4 B per 128 rows) by TM.  A and B live in separate
-// mbarrier rings.  The neighbour table is staged per offset (double buffered, 2 * TM * 128 indices), prefetched one
-// offset ahead by the producers themselves.
+// mbarrier rings.  Table entries are read straight from global memory by the producers, one offset ahead.
+// PRECISE (3xTF32): the gathered tile only LANDS in shared memory; four splitter warps (thread <-> row = TMEM lane) read
+// their row, split it into hi = trunc_tf32(a) and lo = a - hi and write both with tcgen05.st into a TMEM ring after the
+// accumulators; the MMAs run in TS form (A from TMEM), so shared memory serves only the cp.async landing, one read by the
+// splitters and the weight operand: 74 KB per 16 KB stage instead of 138 KB (SS form with a second `lo` tile).
 // =============================================================================================================
 struct Params2 {
   const uint8_t* in;
@@ -553,11 +556,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
   const int SA = p.a_stages, SB = p.b_stages, TM = p.TM;
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + size_t(SA) * A_BYTES;
-  int32_t* sidx = reinterpret_cast<int32_t*>(b_ring + size_t(SB) * b_bytes);   // [2][TM*128]
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sidx + 2 * 4 * BM);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + size_t(SB) * b_bytes);
   uint64_t* a_empty = a_full + MAX_A_STAGES;
-  uint64_t* a_split = a_empty + MAX_A_STAGES;
-  uint64_t* b_full = a_split + MAX_A_STAGES;
+  uint64_t* b_full = a_empty + MAX_A_STAGES;
   uint64_t* b_empty = b_full + MAX_B_STAGES;
   uint64_t* ta_full = b_empty + MAX_B_STAGES;     // PRECISE: split A operand of a stage is in TMEM
   uint64_t* ta_empty = ta_full + MAX_TA_STAGES;   // PRECISE: MMAs reading that TMEM stage have completed
@@ -573,7 +574,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
     for (int s = 0; s < SA; ++s) {
       mbar_init(a_full + s, T2_PROD_WARPS * 32);   // cp.async-completion arrivals of the producer threads
       mbar_init(a_empty + s, PRECISE ? 128 : 1);   // PRECISE: freed by the 128 splitter threads once they have read it
-      mbar_init(a_split + s, 128);
     }
     for (int s = 0; s < MAX_TA_STAGES; ++s) {
       mbar_init(ta_full + s, 128);
@@ -1033,7 +1033,7 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
       while (cols < (precise ? q.ta_col0 + q.ta_stages * 64 : TM * c_pad2)) cols <<= 1;
       q.tmem_cols = cols;
       const int a_bytes = A_STAGE_BYTES, b_bytes = nsplit * q.b_stage_bytes;
-      const int fixed2 = 2 * 4 * BM * 4 + (3 * MAX_A_STAGES + 2 * MAX_B_STAGES + 2 * MAX_TA_STAGES + 1) * 8 + 16 + 1024;
+      const int fixed2 = (2 * MAX_A_STAGES + 2 * MAX_B_STAGES + 2 * MAX_TA_STAGES + 1) * 8 + 16 + 1024;
       int sb = 2;
       int sa = (227 * 1024 - fixed2 - sb * b_bytes) / a_bytes;
       if (sa > MAX_A_STAGES) sa = MAX_A_STAGES;
