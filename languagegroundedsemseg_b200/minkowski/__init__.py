@@ -176,15 +176,16 @@ class CoordinateMapKey:
     def __init__(self, tensor_stride, tag=""):
         self.tensor_stride = tuple(int(t) for t in tensor_stride)
         self.tag = tag
+        self._hash = hash((self.tensor_stride, tag))
 
     def get_tensor_stride(self):
         return list(self.tensor_stride)
 
     def __eq__(self, o):
-        return isinstance(o, CoordinateMapKey) and (self.tensor_stride, self.tag) == (o.tensor_stride, o.tag)
+        return self is o or (isinstance(o, CoordinateMapKey) and self.tensor_stride == o.tensor_stride and self.tag == o.tag)
 
     def __hash__(self):
-        return hash((self.tensor_stride, self.tag))
+        return self._hash
 
     def __repr__(self):
         return f"CoordinateMapKey(stride={list(self.tensor_stride)}, tag={self.tag!r})"
@@ -246,6 +247,7 @@ class CoordinateManager:
         self.D = D
         self._maps = {}
         self._kmaps = {}
+        self._conv_cache = {}
 
     def _prebuild(self):
         if not CoordinateManager.prebuild:
@@ -336,6 +338,18 @@ class CoordinateManager:
         self._kmaps[ck] = km
         return km
 
+    def conv_maps(self, in_key, ks, stride, dil, transpose):
+        """(output key, kernel map) of one convolution call — one dict lookup on the hot path."""
+        ck = (in_key, ks, stride, dil, transpose)
+        r = self._conv_cache.get(ck)
+        if r is None:
+            if transpose:
+                out_key = self.key_with_stride([t // stride for t in in_key.tensor_stride])
+            else:
+                out_key = self.stride(in_key, [stride] * self.D) if stride > 1 else in_key
+            r = self._conv_cache[ck] = (out_key, self.kernel_map(in_key, out_key, [ks] * self.D, [dil] * self.D, transpose))
+        return r
+
     def kernel_map_pairs(self, km: KernelMap):
         """ME-style pair lists [(in_idx, out_idx)] per offset, derived from the table (for inspection / tests)."""
         res = []
@@ -425,8 +439,15 @@ class SparseTensor:
         if o.coordinate_map_key != self.coordinate_map_key or o.coordinate_manager is not self.coordinate_manager:
             raise RuntimeError("SparseTensor arithmetic needs identical coordinate_map_key")
 
+    @classmethod
+    def _make(cls, F, key, mgr, pending=None):
+        """op-output constructor: no coordinate work, no argument parsing (called ~250 times per step)"""
+        o = object.__new__(cls)
+        o._F, o.coordinate_map_key, o.coordinate_manager, o._pending = F, key, mgr, pending
+        return o
+
     def _like(self, F):
-        return SparseTensor(F, coordinate_map_key=self.coordinate_map_key, coordinate_manager=self.coordinate_manager)
+        return SparseTensor._make(F, self.coordinate_map_key, self.coordinate_manager)
 
     def __add__(self, o):
         self._same(o)
@@ -455,9 +476,10 @@ class _BNActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, res, gamma, beta, bn, relu, update_running):
         lib = _lib.load()
-        x = x.contiguous()
+        if not x.is_contiguous():
+            x = x.contiguous()
         n, c = x.shape
-        if res is not None:
+        if res is not None and not res.is_contiguous():
             res = res.contiguous()
         z = torch.empty_like(x)
         stats = torch.empty((2, c), dtype=torch.float32, device=x.device)       # save_mean, save_invstd
@@ -477,7 +499,8 @@ class _BNActFn(torch.autograd.Function):
     def backward(ctx, dz):
         lib = _lib.load()
         x, z, gamma, stats = ctx.saved_tensors
-        dz = dz.contiguous()
+        if not dz.is_contiguous():
+            dz = dz.contiguous()
         n, c = x.shape
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if (ctx.has_res and ctx.needs_input_grad[1]) else None
@@ -496,8 +519,8 @@ def _bn_act(p: _PendingBN, relu: bool):
 
 
 def _bn_fusable(bn, F):
-    return (_state["fuse_bn"] and type(bn) is nn.BatchNorm1d and bn.training and bn.track_running_stats and bn.affine
-            and bn.momentum is not None and F.is_cuda and F.dtype == torch.float32 and F.dim() == 2
+    return (bn.training and F.dtype is torch.float32 and _state["fuse_bn"] and type(bn) is nn.BatchNorm1d
+            and bn.track_running_stats and bn.affine and bn.momentum is not None and F.is_cuda and F.dim() == 2
             and F.shape[0] >= 1 and F.shape[1] % 4 == 0 and F.shape[1] <= 1024)
 
 
@@ -515,10 +538,11 @@ class _SparseConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feats, weight, bias, km, algo):
         lib = _lib.load()
-        feats = feats.contiguous()
+        if not feats.is_contiguous():
+            feats = feats.contiguous()
         w3 = weight.view(1, *weight.shape) if weight.dim() == 2 else weight
         K, c_in, c_out = w3.shape
-        dt = _dtype_code(feats)
+        dt = _lib.F32 if feats.dtype is torch.float32 else _dtype_code(feats)
         if algo == _lib.ALGO_TC3 and dt == _lib.BF16:
             algo = _lib.ALGO_TC                                   # bf16 features: plain bf16 tensor-core products
         n_in = feats.shape[0]
@@ -526,7 +550,9 @@ class _SparseConvFn(torch.autograd.Function):
         out = torch.empty((n_out, c_out), dtype=feats.dtype, device=feats.device)
         b32 = bias.detach().float().contiguous().view(-1) if bias is not None else None
         need_dgrad = ctx.needs_input_grad[0]
-        w32 = w3.detach().float().contiguous()
+        w32 = w3.detach()
+        if w32.dtype is not torch.float32 or not w32.is_contiguous():
+            w32 = w32.float().contiguous()
         # A tiny channel count (the 3 colour channels of conv0p1s1) is zero-padded to a 16-byte row so that the layer
         # takes the tensor-core kernels; the padded weight rows are zero and the padded gradients are dropped.
         c_in_true = c_in
@@ -570,10 +596,11 @@ class _SparseConvFn(torch.autograd.Function):
         lib = _lib.load()
         feats, w_bwd = ctx.saved_tensors
         km, algo = ctx.km, ctx.algo
-        gout = gout.contiguous()
+        if not gout.is_contiguous():
+            gout = gout.contiguous()
         K, c_in, c_out = ctx.dims
         n_in, n_out = feats.shape[0], gout.shape[0]
-        dt = _dtype_code(feats)
+        dt = _lib.F32 if feats.dtype is torch.float32 else _dtype_code(feats)
         gin = gw = gb = None
         if ctx.needs_input_grad[0]:
             # dgrad = the same kernel on the transposed problem; W[k] ([c_in,c_out]) is its K-major B operand as is
@@ -631,6 +658,10 @@ class _ConvBase(nn.Module):
         self.kernel = nn.Parameter(torch.empty((in_channels, out_channels) if self.use_mm
                                                else (K, in_channels, out_channels)))
         self.bias = nn.Parameter(torch.empty(1, out_channels)) if bias else None
+        # scalars of the (isotropic) kernel, computed once: forward() runs ~125 times per step
+        self._ks = _uniform(list(kernel_generator.kernel_size), "kernel size")
+        self._dil = _uniform(list(kernel_generator.kernel_dilation), "dilation")
+        self._stride = _uniform(list(kernel_generator.kernel_stride), "stride")
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -643,17 +674,12 @@ class _ConvBase(nn.Module):
                 self.bias.uniform_(-stdv, stdv)
 
     def forward(self, x: SparseTensor):
-        mgr, kg = x.coordinate_manager, self.kernel_generator
+        mgr = x.coordinate_manager
         in_key = x.coordinate_map_key
         if self.use_mm:
             return x._like(sparse_conv(x.F, self.kernel, self.bias, None))
-        if self.TRANSPOSE:
-            out_key = mgr.key_with_stride([t // s for t, s in zip(in_key.tensor_stride, kg.kernel_stride)])
-        else:
-            out_key = mgr.stride(in_key, kg.kernel_stride) if any(s > 1 for s in kg.kernel_stride) else in_key
-        km = mgr.kernel_map(in_key, out_key, kg.kernel_size, kg.kernel_dilation, self.TRANSPOSE)
-        out = sparse_conv(x.F, self.kernel, self.bias, km)
-        return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=mgr)
+        out_key, km = mgr.conv_maps(in_key, self._ks, self._stride, self._dil, self.TRANSPOSE)
+        return SparseTensor._make(sparse_conv(x.F, self.kernel, self.bias, km), out_key, mgr)
 
     def extra_repr(self):
         kg = self.kernel_generator
@@ -681,8 +707,7 @@ class MinkowskiBatchNorm(nn.Module):
     def forward(self, x: SparseTensor):
         F = x.F
         if _bn_fusable(self.bn, F):
-            return SparseTensor(None, coordinate_map_key=x.coordinate_map_key, coordinate_manager=x.coordinate_manager,
-                                _pending=_PendingBN(self.bn, F))
+            return SparseTensor._make(None, x.coordinate_map_key, x.coordinate_manager, _PendingBN(self.bn, F))
         return x._like(self.bn(F))
 
 
