@@ -338,6 +338,20 @@ class CoordinateManager:
         self._kmaps[ck] = km
         return km
 
+    def tensors(self):
+        """every device buffer this manager owns (coordinate rows, cuckoo tables, neighbour tables)"""
+        seen = set()
+        for cm in self._maps.values():
+            for t in (cm.coords, cm.tkeys, cm.tvals):
+                if id(t) not in seen:
+                    seen.add(id(t))
+                    yield t
+        for km in self._kmaps.values():
+            for t in (km.fwd_table, km.bwd_table, km.counts):
+                if t is not None and id(t) not in seen:
+                    seen.add(id(t))
+                    yield t
+
     def conv_maps(self, in_key, ks, stride, dil, transpose):
         """(output key, kernel map) of one convolution call — one dict lookup on the hot path."""
         ck = (in_key, ks, stride, dil, transpose)

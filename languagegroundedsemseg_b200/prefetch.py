@@ -1,0 +1,51 @@
+"""Side-stream staging of the next sparse batch: host->device copies plus the whole coordinate manager (cuckoo
+coordinate map, strided maps, kernel maps) are built on a second CUDA stream while the current step runs.
+
+Why: `SparseTensor(features, coordinates)` needs one host sync per coordinate map (the row count sizes the next buffers).
+Issued on the training stream, that sync waits for the previous step's whole backlog and leaves the GPU idle until the
+host has queued new work (~5 ms of a 21 ms step).  On a side stream the sync waits only for the ~1 ms of map kernels and
+the training stream never drains.  This is the device-side analogue of the reference's DataLoader workers
+(lib/dataset.py:337-416) + the batch transfer Lightning does before `model_step` (pl_BaselineTrainer.py:288-300).
+
+    pf = SparseBatchPrefetcher(device)
+    ticket = pf.stage(coords, feats, labels)          # host (pinned) or device tensors
+    for ...:
+        sinput, target = pf.get(ticket)               # training stream waits on the staging event (no host sync)
+        ticket = pf.stage(next_coords, next_feats, next_labels)
+        ... forward / backward / step on sinput ...
+"""
+import torch
+
+from . import minkowski as E
+
+
+class SparseBatchPrefetcher:
+    def __init__(self, device=None, feature_dtype=torch.float32):
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.stream = torch.cuda.Stream(self.device)
+        self.feature_dtype = feature_dtype
+
+    def stage(self, coords, feats, labels=None):
+        """Enqueue copies + map builds on the staging stream; returns a ticket for `get`.  Blocks the host only for the
+        staging stream's own work."""
+        with torch.cuda.stream(self.stream):
+            c = coords.to(self.device, non_blocking=True)
+            f = feats.to(self.device, non_blocking=True).to(self.feature_dtype)
+            lab = labels.to(self.device, non_blocking=True) if labels is not None else None
+            st = E.SparseTensor(f, c)                  # hash + every learned strided / kernel map, on this stream
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return st, lab, ev
+
+    def get(self, ticket):
+        """Hand the staged batch to the current (training) stream."""
+        st, lab, ev = ticket
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        # the tensors were allocated on the staging stream: tell the caching allocator the training stream uses them
+        for t in st.coordinate_manager.tensors():
+            t.record_stream(cur)
+        for t in (st.F, lab, getattr(st, "unique_index", None), getattr(st, "inverse_mapping", None)):
+            if t is not None:
+                t.record_stream(cur)
+        return st, lab
