@@ -154,6 +154,17 @@ int lgs_clip_ce(const float* d_feats, int64_t n, int32_t c, const float* d_ancho
                 const int64_t* d_labels, int64_t ignore_label,
                 float* d_loss, float* d_grad_feats, int32_t* d_pred, float* d_grad_logits, void* stream);
 
+/* The same loss on the tensor cores: S = F @ An^T as a 3xTF32 tcgen05 GEMM (fp32-grade products, fp32 accumulation in TMEM)
+ * with the row norms, softmax cross-entropy, argmax and G = softmax - onehot fused into the TMEM epilogue, and
+ * dF = (G @ An - (G.S) F_hat) / |F| as a second tcgen05 GEMM whose A operand (G) never leaves TMEM.
+ * Shapes: c % 4 == 0, a % 4 == 0, a <= 208 (lgs_clip_ce_tc_supported); other shapes -> lgs_clip_ce (same results).
+ * d_ws: caller-allocated scratch of lgs_clip_ce_tc_ws_elems(c, a) floats (hi/lo-split anchors, both operand forms). */
+int lgs_clip_ce_tc_supported(int32_t c, int32_t a);
+int64_t lgs_clip_ce_tc_ws_elems(int32_t c, int32_t a);
+int lgs_clip_ce_tc(const float* d_feats, int64_t n, int32_t c, const float* d_anchors_n, int32_t a,
+                   const int64_t* d_labels, int64_t ignore_label,
+                   float* d_loss, float* d_grad_feats, int32_t* d_pred, float* d_grad_logits, float* d_ws, void* stream);
+
 /* Hinge variant (ContrastiveLanguageLoss.py:184-192, 'cos' distance :87-93): negatives' anchor ids are an input
  * [n,n_neg] (the reference draws them on the host, :131-138).
  *   pos_i = relu(1 - S[i,y_i] - pos_thresh);  neg_i = relu(neg_thresh - (1 - mean_j S[i,neg_ij]));  0 where ignored. */

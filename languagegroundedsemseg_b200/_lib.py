@@ -32,6 +32,9 @@ SIGNATURES = {
     "lgs_bn_fwd": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _f32, _f32, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "lgs_bn_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
     "lgs_clip_ce": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _i64, _p, _p, _p, _p, _p]),
+    "lgs_clip_ce_tc_supported": (C.c_int, [_i32, _i32]),
+    "lgs_clip_ce_tc_ws_elems": (_i64, [_i32, _i32]),
+    "lgs_clip_ce_tc": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _i64, _p, _p, _p, _p, _p, _p]),
     "lgs_clip_hinge": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _p, _i32, _i64, _f32, _f32, _f32, _p, _p, _p, _p]),
     "lgs_voxelize_affine": (C.c_int, [_p, _i64, C.POINTER(C.c_double), _i32, _p, _p]),
 }

@@ -14,6 +14,17 @@ import torch.nn.functional as F
 from . import _lib
 
 
+# 'tc'  : tcgen05 kernel (3xTF32 GEMM + fused softmax-CE + second GEMM for dF) whenever the shape allows   [default]
+# 'simt': the exact-fp32 FMA kernel (parity anchor; also serves shapes outside the tensor-core envelope)
+_clip = {"algo": "tc"}
+
+
+def set_clip_algo(name: str):
+    if name not in ("tc", "simt"):
+        raise ValueError(name)
+    _clip["algo"] = name
+
+
 def _stream():
     return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
@@ -36,8 +47,15 @@ class _ClipCEFn(torch.autograd.Function):
         need_a = ctx.needs_input_grad[1]
         gf = torch.empty_like(feats) if need_f else None
         gl = torch.empty((n, a), dtype=torch.float32, device=feats.device) if need_a else None
-        _lib.check(lib.lgs_clip_ce(_lib.ptr(feats), n, c, _lib.ptr(anchors_n), a, _lib.ptr(labels), int(ignore_label),
-                                   _lib.ptr(loss), _lib.ptr(gf), _lib.ptr(pred), _lib.ptr(gl), _stream()))
+        if _clip["algo"] == "tc" and lib.lgs_clip_ce_tc_supported(c, a):
+            ws = torch.empty(lib.lgs_clip_ce_tc_ws_elems(c, a), dtype=torch.float32, device=feats.device)
+            _lib.check(lib.lgs_clip_ce_tc(_lib.ptr(feats), n, c, _lib.ptr(anchors_n), a, _lib.ptr(labels),
+                                          int(ignore_label), _lib.ptr(loss), _lib.ptr(gf), _lib.ptr(pred), _lib.ptr(gl),
+                                          _lib.ptr(ws), _stream()))
+        else:
+            _lib.check(lib.lgs_clip_ce(_lib.ptr(feats), n, c, _lib.ptr(anchors_n), a, _lib.ptr(labels),
+                                       int(ignore_label), _lib.ptr(loss), _lib.ptr(gf), _lib.ptr(pred), _lib.ptr(gl),
+                                       _stream()))
         ctx.save_for_backward(gf, gl, feats if need_a else None)
         ctx.mark_non_differentiable(pred)
         return loss, pred

@@ -11,10 +11,13 @@ from tests.helpers import rel_err
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def L(lib):
+@pytest.fixture(params=["tc", "simt"])
+def L(lib, request):
+    """both kernels behind the same facade: the tcgen05 one (default) and the exact-fp32 SIMT one"""
     from languagegroundedsemseg_b200 import losses
-    return losses
+    losses.set_clip_algo(request.param)
+    yield losses
+    losses.set_clip_algo("tc")
 
 
 @pytest.mark.parametrize("tag", ["c96", "c512"])
@@ -88,3 +91,55 @@ def test_clip_hinge_vs_oracle(L):
     assert abs(lg.item() - lo.item()) < 1e-5
     assert rel_err(pg.cpu(), po) < 1e-5 and rel_err(ng.cpu(), no) < 1e-5
     assert rel_err(Fg.grad.cpu(), Fo.grad) < 1e-4
+
+
+@pytest.mark.parametrize("n,c,a", [(1, 96, 200), (127, 96, 200), (129, 16, 20), (1000, 100, 200), (333, 512, 200),
+                                   (4097, 96, 208), (640, 32, 4), (2000, 192, 56)])
+def test_clip_ce_tc_shapes_vs_oracle(lib, n, c, a):
+    """tcgen05 kernel on ragged shapes (partial tiles, 16-column tails, K padding, multi-chunk dF) vs the fp32 oracle:
+    loss / dF / d anchors within 1e-4 relative, argmax identical where the top-2 margin exceeds 1e-5."""
+    from languagegroundedsemseg_b200 import losses
+    from oracle import losses_cpu
+    assert lib.lgs_clip_ce_tc_supported(c, a) == 1
+    losses.set_clip_algo("tc")
+    torch.manual_seed(n + c + a)
+    F_, A = torch.randn(n, c) * 3.0, torch.randn(a, c)
+    y = torch.randint(0, a, (n,))
+    y[1::9] = -1            # row 0 stays labelled (n = 1: an all-ignored batch has no defined mean)
+    Fo, Ao = F_.clone().requires_grad_(True), A.clone().requires_grad_(True)
+    lo = losses_cpu.clip_ce_loss(Fo, y, Ao)
+    lo.backward()
+    Fg, Ag = F_.cuda().requires_grad_(True), A.cuda().requires_grad_(True)
+    l0 = lib.lgs_launch_count()
+    crit = losses.ContrastiveLanguageCELoss(num_labels=a)
+    lg = crit(Fg, y.cuda(), Ag)[0]
+    assert lib.lgs_launch_count() - l0 == 2          # weight_prep (anchor split) + the fused kernel
+    lg.backward()
+    assert abs(lg.item() - lo.item()) < 1e-4 * max(1.0, abs(lo.item()))
+    assert rel_err(Fg.grad.cpu(), Fo.grad) < 1e-4
+    assert rel_err(Ag.grad.cpu(), Ao.grad) < 1e-4
+    assert torch.all(Fg.grad[y.cuda() == -1] == 0)
+    S = losses_cpu.feature_sim(F_, A)
+    top2 = S.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-5
+    assert torch.equal(crit.last_pred.cpu().long()[clear], S.argmax(1)[clear])
+    # per-row losses too
+    lr = losses.ContrastiveLanguageCELoss(num_labels=a, reduction="none")(Fg.detach(), y.cuda(), Ag.detach())[0]
+    Sd = S.double()
+    ref = torch.nn.functional.cross_entropy(Sd, y, ignore_index=-1, reduction="none").float()
+    np.testing.assert_allclose(lr.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=2e-5)
+
+
+def test_clip_ce_tc_rejects_unsupported_shapes(lib):
+    from languagegroundedsemseg_b200 import _lib
+    assert lib.lgs_clip_ce_tc_supported(96, 200) == 1
+    assert lib.lgs_clip_ce_tc_supported(97, 200) == 0 and lib.lgs_clip_ce_tc_supported(96, 256) == 0
+    rc = lib.lgs_clip_ce_tc(None, 10, 97, None, 200, None, -1, None, None, None, None, None, None)
+    assert rc == _lib.E_UNSUPPORTED and b"lgs_clip_ce_tc" in lib.lgs_last_error()
+    # the facade serves such shapes with the SIMT kernel
+    from languagegroundedsemseg_b200 import losses
+    F_, A = torch.randn(50, 97, device="cuda"), torch.randn(30, 97, device="cuda")
+    y = torch.randint(0, 30, (50,), device="cuda")
+    loss, _ = losses.clip_ce(F_, y, A)
+    S = torch.nn.functional.normalize(F_, dim=1) @ torch.nn.functional.normalize(A, dim=1).t()
+    assert rel_err(loss, torch.nn.functional.cross_entropy(S, y, reduction="none")) < 1e-4
