@@ -103,6 +103,13 @@ int lgs_conv_tc_supported(int32_t c_in, int32_t c_out, int32_t dtype);
 int lgs_weight_prep(const float* d_weight, int32_t K, int32_t c_in, int32_t c_out, int32_t nsplit,
                     void* d_fwd, void* d_bwd, int32_t dtype, void* stream);
 
+/* The same for every layer of a network in ONE launch (63 per-layer launches per Res16UNet34C step otherwise).
+ *   d_desc: device int64 [n_layers][8] = { d_weight, d_fwd, d_bwd (0 = skip), K, c_in, c_out, first_tile, 0 } where a
+ *   layer owns K * ceil(c_in/32) * ceil(c_out/32) consecutive tiles from first_tile (ascending); total_tiles = their sum.
+ *   nsplit / dtype as in lgs_weight_prep, common to all layers. */
+int lgs_weight_prep_batch(const int64_t* d_desc, int32_t n_layers, int64_t total_tiles, int32_t nsplit, int32_t dtype,
+                          void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Sparse convolution.   Replaces ME ConvolutionForwardGPU / ConvolutionBackwardGPU (and ...Transpose...)
  *   call sites: models/modules/common.py:195-203, 228-236; autograd backward of the same.

@@ -27,6 +27,7 @@ SIGNATURES = {
     "lgs_kmap_transpose": (C.c_int, [_p, _i32, _i64, _i64, _p, _p]),
     "lgs_conv_tc_supported": (C.c_int, [_i32, _i32, _i32]),
     "lgs_weight_prep": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _i32, _p]),
+    "lgs_weight_prep_batch": (C.c_int, [_p, _i32, _i64, _i32, _i32, _p]),
     "lgs_conv_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i32, _p, _i64, _i32, _p, _p, _i32, _i32, _p]),
     "lgs_conv_wgrad": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _p, _i32, _p, _i32, _i32, _p]),
     "lgs_bn_fwd": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _f32, _f32, _i32, _p, _p, _p, _p, _p, _p, _p]),

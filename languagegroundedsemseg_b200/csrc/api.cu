@@ -13,6 +13,7 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w, int K, in
 int conv_tc_shape_ok(int c_in, int c_out, int dtype);
 int weight_prep(const float* w, int K, int c_in, int c_out, int nsplit, void* fwd, void* bwd, int dtype,
                 cudaStream_t stream);
+int weight_prep_batch(const int64_t* desc, int n_layers, int64_t total_tiles, int nsplit, int dtype, cudaStream_t stream);
 int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int64_t n_out, int c_out,
                   const int32_t* table, int K, float* gw, int dtype, cudaStream_t stream);
 bool tc_built();
@@ -32,6 +33,15 @@ int lgs_weight_prep(const float* d_weight, int32_t K, int32_t c_in, int32_t c_ou
     return fail(LGS_E_INVALID, "lgs_weight_prep: bad arguments");
   if (dtype != LGS_F32 && dtype != LGS_BF16) return fail(LGS_E_INVALID, "lgs_weight_prep: dtype %d", dtype);
   return weight_prep(d_weight, K, c_in, c_out, nsplit, d_fwd, d_bwd, dtype, static_cast<cudaStream_t>(stream_));
+}
+
+int lgs_weight_prep_batch(const int64_t* d_desc, int32_t n_layers, int64_t total_tiles, int32_t nsplit, int32_t dtype,
+                          void* stream_) {
+  if (n_layers < 0 || total_tiles < 0 || total_tiles >= (int64_t(1) << 31) || (nsplit != 1 && nsplit != 2) ||
+      (n_layers > 0 && !d_desc))
+    return fail(LGS_E_INVALID, "lgs_weight_prep_batch: bad arguments");
+  if (dtype != LGS_F32 && dtype != LGS_BF16) return fail(LGS_E_INVALID, "lgs_weight_prep_batch: dtype %d", dtype);
+  return weight_prep_batch(d_desc, n_layers, total_tiles, nsplit, dtype, static_cast<cudaStream_t>(stream_));
 }
 
 int lgs_conv_fwd(const void* d_in, int64_t n_in, int32_t c_in, const void* d_weight, int32_t weight_layout, int32_t K,

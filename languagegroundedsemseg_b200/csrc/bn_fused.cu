@@ -61,6 +61,94 @@ bn_stats_kernel(const float* __restrict__ x, int64_t n, int c, double* __restric
   bn_block_reduce(a, b, ch, c, sums);
 }
 
+// ---- vectorised statistics (default) ---------------------------------------------------------------------------
+// The feature matrix is one flat stream of float4: a block owns BN_VROWS consecutive rows and its T threads
+// (T = the largest multiple of c/4 <= 256) stride over them, so a thread always sees the same 4 channels, every load is
+// 16 bytes and a warp reads 512 contiguous bytes.  U loads are in flight per thread.
+constexpr int BN_VROWS = 128;   // small blocks: 8 resident per SM keep ~128 KB of loads in flight
+constexpr int BN_VTHREADS = 256;
+
+// partial sums of the threads that own the same channel quad -> fp64 atomics (one per channel and block)
+__device__ __forceinline__ void bn_vec_reduce(const float (&a)[4], const float (&b)[4], int c4, int T, int c, double* sums) {
+  __shared__ float sh[BN_VTHREADS][9];
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    sh[t][e] = a[e];
+    sh[t][4 + e] = b[e];
+  }
+  __syncthreads();
+  // c4 * 8 (quad, component) pairs, each summed over the T / c4 threads of that quad
+  for (int j = t; j < c4 * 8; j += BN_VTHREADS) {
+    const int q = j >> 3, e = j & 7;
+    double acc = 0.0;
+    for (int u = q; u < T; u += c4) acc += sh[u][e];
+    double* dst = sums + size_t(blockIdx.x % BN_COPIES) * 2 * c;
+    atomicAdd(dst + (e < 4 ? 0 : c) + q * 4 + (e & 3), acc);
+  }
+}
+
+template <int U>
+__global__ void __launch_bounds__(BN_VTHREADS)
+bn_stats_vec_kernel(const float4* __restrict__ x, int64_t n, int c, int T, double* __restrict__ sums /*[BN_COPIES][2c]*/) {
+  const int c4 = c >> 2;
+  const int64_t i0 = int64_t(blockIdx.x) * BN_VROWS * c4;
+  const int64_t i1 = min(n, int64_t(blockIdx.x + 1) * BN_VROWS) * c4;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (int(threadIdx.x) < T) {
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += int64_t(U) * T) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = (i + int64_t(u) * T < i1) ? __ldg(x + i + int64_t(u) * T) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        a[0] += v[u].x; a[1] += v[u].y; a[2] += v[u].z; a[3] += v[u].w;
+        b[0] = fmaf(v[u].x, v[u].x, b[0]); b[1] = fmaf(v[u].y, v[u].y, b[1]);
+        b[2] = fmaf(v[u].z, v[u].z, b[2]); b[3] = fmaf(v[u].w, v[u].w, b[3]);
+      }
+    }
+  }
+  bn_vec_reduce(a, b, c4, T, c, sums);
+}
+
+template <int U>
+__global__ void __launch_bounds__(BN_VTHREADS)
+bn_bwd_stats_vec_kernel(const float4* __restrict__ x, const float4* __restrict__ z, const float4* __restrict__ dz, int64_t n,
+                        int c, int T, const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                        double* __restrict__ sums /*[BN_COPIES][2c]: sum dy, sum dy*xhat*/) {
+  const int c4 = c >> 2;
+  const int64_t i0 = int64_t(blockIdx.x) * BN_VROWS * c4;
+  const int64_t i1 = min(n, int64_t(blockIdx.x + 1) * BN_VROWS) * c4;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (int(threadIdx.x) < T) {
+    const int q = int(threadIdx.x) % c4;      // T is a multiple of c4 and i0 a multiple of c4: the quad never changes
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + q);
+    const float4 is = __ldg(reinterpret_cast<const float4*>(invstd) + q);
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += int64_t(U) * T) {
+      float4 g[U], zz[U], v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool ok = i + int64_t(u) * T < i1;
+        const int64_t j = i + int64_t(u) * T;
+        g[u] = ok ? __ldg(dz + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        zz[u] = (ok && relu) ? __ldg(z + j) : make_float4(1.f, 1.f, 1.f, 1.f);
+        v[u] = ok ? __ldg(x + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float d0 = zz[u].x > 0.f ? g[u].x : 0.f, d1 = zz[u].y > 0.f ? g[u].y : 0.f;
+        const float d2 = zz[u].z > 0.f ? g[u].z : 0.f, d3 = zz[u].w > 0.f ? g[u].w : 0.f;
+        a[0] += d0; a[1] += d1; a[2] += d2; a[3] += d3;
+        b[0] = fmaf(d0, (v[u].x - m.x) * is.x, b[0]);
+        b[1] = fmaf(d1, (v[u].y - m.y) * is.y, b[1]);
+        b[2] = fmaf(d2, (v[u].z - m.z) * is.z, b[2]);
+        b[3] = fmaf(d3, (v[u].w - m.w) * is.w, b[3]);
+      }
+    }
+  }
+  bn_vec_reduce(a, b, c4, T, c, sums);
+}
+
 // mean / invstd from the sums; block (0,0) also updates the running statistics
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, int64_t n, int c,
@@ -203,6 +291,14 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ z, co
 
 using namespace lgs;
 
+// threads of a vectorised statistics block: the largest multiple of c/4 that fits (c <= 1024 => c/4 <= 256)
+static inline int bn_vec_threads(int c) { return (BN_VTHREADS / (c >> 2)) * (c >> 2); }
+static inline bool bn_use_vec(const void* a, const void* b, const void* d, int c) {
+  static const bool off = getenv("LGS_BN_SCALAR") != nullptr;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(d);
+  return !off && (bits & 15) == 0 && (c & 3) == 0 && c >= 4 && c <= 1024;
+}
+
 extern "C" {
 
 int lgs_bn_fwd(const float* d_x, const float* d_residual, int64_t n, int32_t c, const float* d_gamma, const float* d_beta,
@@ -214,7 +310,10 @@ int lgs_bn_fwd(const float* d_x, const float* d_residual, int64_t n, int32_t c, 
   LGS_CUDA(cudaMemsetAsync(d_scratch, 0, size_t(BN_COPIES) * 2 * c * sizeof(double), stream));
   const dim3 grid{unsigned((c + BN_TX - 1) / BN_TX), unsigned(cdiv(n, BN_ROWS)), 1u}, block{BN_TX, BN_TY, 1u};
   static const int unroll = getenv("LGS_BN_UNROLL") ? atoi(getenv("LGS_BN_UNROLL")) : 4;
-  if (unroll == 1) {
+  if (bn_use_vec(d_x, nullptr, nullptr, c)) {
+    LGS_LAUNCH(bn_stats_vec_kernel<4>, unsigned(cdiv(n, BN_VROWS)), BN_VTHREADS, 0, stream,
+               reinterpret_cast<const float4*>(d_x), n, c, bn_vec_threads(c), d_scratch);
+  } else if (unroll == 1) {
     LGS_LAUNCH(bn_stats_kernel<1>, grid, block, 0, stream, d_x, n, c, d_scratch);
   } else {
     LGS_LAUNCH(bn_stats_kernel<4>, grid, block, 0, stream, d_x, n, c, d_scratch);
@@ -238,7 +337,12 @@ int lgs_bn_bwd(const float* d_x, const float* d_z, const float* d_dz, int64_t n,
   LGS_CUDA(cudaMemsetAsync(d_scratch, 0, size_t(BN_COPIES) * 2 * c * sizeof(double), stream));
   const dim3 grid{unsigned((c + BN_TX - 1) / BN_TX), unsigned(cdiv(n, BN_ROWS)), 1u}, block{BN_TX, BN_TY, 1u};
   static const int unroll = getenv("LGS_BN_UNROLL") ? atoi(getenv("LGS_BN_UNROLL")) : 4;
-  if (unroll == 1) {
+  if (bn_use_vec(d_x, relu ? d_z : nullptr, d_dz, c) && !(reinterpret_cast<uintptr_t>(d_save_mean) & 15) &&
+      !(reinterpret_cast<uintptr_t>(d_save_invstd) & 15)) {
+    LGS_LAUNCH(bn_bwd_stats_vec_kernel<2>, unsigned(cdiv(n, BN_VROWS)), BN_VTHREADS, 0, stream,
+               reinterpret_cast<const float4*>(d_x), reinterpret_cast<const float4*>(d_z),
+               reinterpret_cast<const float4*>(d_dz), n, c, bn_vec_threads(c), d_save_mean, d_save_invstd, relu, d_scratch);
+  } else if (unroll == 1) {
     LGS_LAUNCH(bn_bwd_stats_kernel<1>, grid, block, 0, stream, d_x, d_z, d_dz, n, c, d_save_mean, d_save_invstd, relu, d_scratch);
   } else {
     LGS_LAUNCH(bn_bwd_stats_kernel<4>, grid, block, 0, stream, d_x, d_z, d_dz, n, c, d_save_mean, d_save_invstd, relu, d_scratch);

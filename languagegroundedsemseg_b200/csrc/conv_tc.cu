@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 
@@ -393,6 +394,8 @@ struct Params2 {
   int32_t num_kb;
   int32_t n_tile;        // output channels per CTA: padded c_out, or an equal slice of it when c_out > 256 (blockIdx.y)
   int32_t TM;            // tiles per CTA
+  int32_t rt;            // output rows per tile (<= 128): rows beyond it are empty MMA lanes, so that TM*rt*gridDim.x can
+                         // match n_out on a grid that is a multiple of the SM count (no partial last wave)
   int32_t a_stages, b_stages;
   int32_t tmem_cols;
   int32_t b_stage_bytes;
@@ -425,7 +428,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t m0 = int64_t(blockIdx.x) * (int64_t(TM) * BM);
+  const int64_t m0 = int64_t(blockIdx.x) * (int64_t(TM) * p.rt);
   const int n0 = blockIdx.y * p.n_tile;          // output-channel slice of this CTA (c_out > 256 is sliced)
   const int K = p.K, num_kb = p.num_kb;
 
@@ -479,8 +482,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
         for (int t = 0; t < 4; ++t) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int64_t o = m0 + int64_t(t) * BM + rbase + 32 * i;
-            v[t][i] = (t < TM && o < p.n_out) ? (trow ? __ldg(trow + o) : int32_t(o)) : -1;
+            const int r = rbase + 32 * i;
+            const int64_t o = m0 + int64_t(t) * p.rt + r;
+            v[t][i] = (t < TM && r < p.rt && o < p.n_out) ? (trow ? __ldg(trow + o) : int32_t(o)) : -1;
           }
         }
       };
@@ -526,11 +530,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params2 p) {
     const int ncols = min(p.n_tile, p.c_out - n0);
     const int lq = warp & 3;                       // TMEM lane quadrant this warp may read
     for (int t = warp >> 2; t < TM; t += T2_PROD_WARPS / 4) {
-      const int64_t o = m0 + int64_t(t) * BM + lq * 32 + lane;
+      const int64_t o = m0 + int64_t(t) * p.rt + lq * 32 + lane;
+      const bool row_ok = lq * 32 + lane < p.rt && o < p.n_out;
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + (uint32_t(lq * 32) << 16) + uint32_t(t * p.n_tile + c0), v);
-        if (o < p.n_out) {
+        if (row_ok) {
           if constexpr (BF16) {
             __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out) + size_t(o) * p.c_out + n0 + c0;
 #pragma unroll
@@ -775,6 +780,63 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
   }
 }
 
+// All layers of a network in ONE launch (the per-layer launches are latency-bound: 63 of them per training step).
+// desc [n_layers][8] int64 = {w, fwd, bwd, K, c_in, c_out, first tile of the layer, unused}; a block finds its layer by
+// binary search over the first-tile column, then does the same 32x32 tile as weight_prep_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) weight_prep_batch_kernel(const int64_t* __restrict__ desc, int n_layers, int nsplit) {
+  __shared__ float tile[32][33];
+  const int64_t b = blockIdx.x;
+  int lo = 0, hi = n_layers - 1;
+  while (lo < hi) {                       // last layer whose first tile <= b
+    const int mid = (lo + hi + 1) >> 1;
+    if (desc[mid * 8 + 6] <= b) lo = mid; else hi = mid - 1;
+  }
+  const int64_t* d = desc + lo * 8;
+  const float* w = reinterpret_cast<const float*>(d[0]);
+  T* fwd = reinterpret_cast<T*>(d[1]);
+  T* bwd = reinterpret_cast<T*>(d[2]);
+  const int K = int(d[3]), c_in = int(d[4]), c_out = int(d[5]);
+  (void)K;
+  const int tx = (c_out + 31) / 32, ty = (c_in + 31) / 32;
+  int64_t t = b - d[6];
+  const int co0 = int(t % tx) * 32;
+  t /= tx;
+  const int ci0 = int(t % ty) * 32;
+  const int k = int(t / ty);
+  const int64_t total = int64_t(d[3]) * c_in * c_out;
+  const float* wk = w + int64_t(k) * c_in * c_out;
+#pragma unroll
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    float v = 0.f;
+    if (ci < c_in && co < c_out) {
+      v = wk[int64_t(ci) * c_out + co];
+      if (bwd) wp_store<T>(bwd, int64_t(k) * c_in * c_out + int64_t(ci) * c_out + co, total, v, nsplit);
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (!fwd) return;
+#pragma unroll
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    if (ci < c_in && co < c_out)
+      wp_store<T>(fwd, int64_t(k) * c_in * c_out + int64_t(co) * c_in + ci, total, tile[threadIdx.x][r], nsplit);
+  }
+}
+
+int weight_prep_batch(const int64_t* desc, int n_layers, int64_t total_tiles, int nsplit, int dtype, cudaStream_t stream) {
+  if (n_layers == 0 || total_tiles == 0) return LGS_OK;
+  const dim3 block{32u, 8u, 1u};
+  if (dtype == LGS_BF16) {
+    LGS_LAUNCH(weight_prep_batch_kernel<__nv_bfloat16>, unsigned(total_tiles), block, 0, stream, desc, n_layers, 1);
+  } else {
+    LGS_LAUNCH(weight_prep_batch_kernel<float>, unsigned(total_tiles), block, 0, stream, desc, n_layers, nsplit);
+  }
+  return LGS_OK;
+}
+
 int weight_prep(const float* w, int K, int c_in, int c_out, int nsplit, void* fwd, void* bwd, int dtype,
                 cudaStream_t stream) {
   const int64_t total = int64_t(K) * c_in * c_out;
@@ -839,20 +901,36 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
     const int n_slices = (c_pad_all + 255) / 256;
     const int c_pad2 = ((((c_pad_all + n_slices - 1) / n_slices) + 15) / 16) * 16;     // columns per CTA
     const int64_t tiles = cdiv(n_out, BM);
-    int TM = 0;
+    int TM = 0, RT = BM;
     const int ta_min_cols = precise ? 128 : 0;   // PRECISE keeps >= 2 split-A stages (64 columns each) in TMEM
     if (tiles * n_slices >= 148 && n_in > 0 && !getenv("LGS_TC_NO_MULTI")) {
-      // pick TM in {4,2,1} minimising waves*TM (ties -> larger TM: less weight traffic)
-      int64_t best = -1;
-      for (int tm = 1; tm <= 4; tm *= 2) {
+      // Cost of a decomposition = tile-rows an SM processes in sequence.  (a) full 128-row tiles: waves * TM.
+      // (b) balanced: a grid of w * 148 CTAs (exactly w full waves) with TM tiles of rt = ceil(rows per CTA / TM) <= 128
+      // rows: the gather stream shrinks with rt, the MMAs do not (empty lanes), hence the floor.  A map of 301 tiles
+      // (level 1 of a 150 K-voxel scene) costs 3 as 128-row tiles (148 + 148 + 5 CTAs) but 3 * 87/128 = 2.04 balanced.
+      // Ties go to the larger TM (less weight traffic).
+      static const bool balance = !getenv("LGS_TC_NO_BALANCE");
+      const double mma_floor = precise ? 0.6 : 0.35;
+      double best = -1.0;
+      const bool ts1 = precise && getenv("LGS_TC_TS1");   // TM = 1 otherwise means conv_tc_kernel below
+      for (int tm = 1; tm <= 4; ++tm) {
         if (tm * c_pad2 + ta_min_cols > 512) break;
-        const int64_t cost = cdiv(cdiv(tiles, tm) * n_slices, 148) * tm;
-        if (best < 0 || cost <= best) {
-          best = cost;
-          TM = tm;
+        if (tm != 3) {
+          const double cost = double(cdiv(cdiv(tiles, tm) * n_slices, 148) * tm);
+          if (best < 0 || cost <= best) best = cost, TM = tm, RT = BM;
+        }
+        if (!balance || (tm == 1 && !ts1)) continue;
+        for (int w = 1; w <= 64; ++w) {
+          const int64_t gx = std::max<int64_t>(1, int64_t(148) * w / n_slices);
+          const int64_t rt = cdiv(cdiv(n_out, gx), int64_t(tm));
+          if (rt > BM) continue;
+          const double cost = double(w) * tm * std::max(double(rt) / BM, mma_floor);
+          if (cost <= best * 0.97) best = cost, TM = tm, RT = int(rt);   // must beat full tiles by 3 %
+          break;
         }
       }
-      if (const char* e = getenv("LGS_TC_TM")) TM = atoi(e);
+      if (const char* e = getenv("LGS_TC_TM")) TM = atoi(e), RT = BM;
+      if (const char* e = getenv("LGS_TC_RT")) RT = std::min(BM, std::max(8, atoi(e)));
     }
     if (TM >= 2 || (TM == 1 && precise && getenv("LGS_TC_TS1"))) {
       Params2 q;
@@ -868,6 +946,7 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
       q.num_kb = (row_bytes + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
       q.n_tile = c_pad2;
       q.TM = TM;
+      q.rt = RT;
       q.b_stage_bytes = c_pad2 * KBLOCK_BYTES;
       q.ta_col0 = ((TM * c_pad2 + 31) / 32) * 32;
       q.ta_stages = precise ? (512 - q.ta_col0) / 64 : 0;
@@ -899,7 +978,7 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr2 != CUDA_SUCCESS) return fail(LGS_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(cr2));
-        const dim3 grid2{unsigned(cdiv(tiles, TM)), unsigned(n_slices), 1u};
+        const dim3 grid2{unsigned(cdiv(n_out, int64_t(TM) * RT)), unsigned(n_slices), 1u};
         if (dtype == LGS_BF16) {
           LGS_LAUNCH((conv_tc2_kernel<true, false>), grid2, T2_THREADS, smem2, stream, tmap2, q);
         } else if (precise) {

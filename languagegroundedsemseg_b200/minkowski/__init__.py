@@ -21,8 +21,10 @@ from __future__ import annotations
 import collections
 import collections.abc
 import ctypes
+import os
 import sys
 import types
+import weakref
 from enum import Enum
 
 import numpy as np
@@ -43,7 +45,13 @@ for _n in ("Sequence", "Iterable"):
 # 'tc'    tcgen05 tensor cores, parity-grade: 3xTF32 products for fp32 features (bf16 MMA for bf16 features)  [default]
 # 'tf32'  tcgen05 single-pass TF32 (fast, ~7e-4 relative error per layer)
 _ALGO = {"simt": _lib.ALGO_SIMT, "tc": _lib.ALGO_TC3, "tf32": _lib.ALGO_TC}
-_state = {"algo": _lib.ALGO_TC3, "profile": None, "fuse_bn": True}
+_state = {"algo": _lib.ALGO_TC3, "profile": None, "fuse_bn": True,
+          # conv -> BatchNorm (+ residual) (+ ReLU) as ONE autograd node (the conv is evaluated lazily); kernels unchanged
+          "fuse_conv_bn": os.environ.get("LGS_FUSE_CONV_BN", "1") != "0",
+          # backward: wgrad on a side stream while dgrad runs on the training stream (joined before the node returns)
+          "overlap_wgrad": os.environ.get("LGS_OVERLAP_WGRAD", "1") != "0",
+          # tensor-core operand forms of ALL layers' weights in one launch per parameter update
+          "batch_prep": os.environ.get("LGS_BATCH_PREP", "1") != "0"}
 
 
 def profile_begin():
@@ -107,6 +115,45 @@ def get_conv_algo() -> str:
 def _stream():
     # torch.cuda.current_stream() costs ~16 us per call (device-index plumbing); the raw getter is ~0.3 us
     return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+
+
+def set_conv_bn_fusion(flag: bool):
+    """conv -> BatchNorm (+ residual) (+ ReLU) recorded as one autograd node (default on); same kernels either way."""
+    _state["fuse_conv_bn"] = bool(flag)
+
+
+def set_wgrad_overlap(flag: bool):
+    """Backward: launch wgrad on a side stream next to dgrad (default on); joined before the backward node returns."""
+    _state["overlap_wgrad"] = bool(flag)
+
+
+def set_batched_weight_prep(flag: bool):
+    """One lgs_weight_prep_batch launch per parameter update instead of one lgs_weight_prep per layer call."""
+    _state["batch_prep"] = bool(flag)
+
+
+_bn_scratch = {}
+
+
+def _scratch64(dev_index):
+    """fp64 accumulator scratch of the BatchNorm kernels: one persistent buffer per (device, stream) — launches on one
+    stream are ordered, so consecutive layers can share it."""
+    key = (dev_index, torch._C._cuda_getCurrentRawStream(dev_index))
+    t = _bn_scratch.get(key)
+    if t is None:
+        t = _bn_scratch[key] = torch.empty(16 * 1024, dtype=torch.float64, device=torch.device("cuda", dev_index))
+    return t
+
+
+_side = {}
+
+
+def _side_stream(dev_index):
+    r = _side.get(dev_index)
+    if r is None:
+        with torch.cuda.device(dev_index):
+            r = _side[dev_index] = (torch.cuda.Stream(), torch.cuda.Event(), torch.cuda.Event())
+    return r
 
 
 _tc_ok_cache = {}
@@ -376,14 +423,28 @@ class CoordinateManager:
 # ----------------------------------------------------------------------------------------------------------
 # SparseTensor
 # ----------------------------------------------------------------------------------------------------------
+class _PendingConv:
+    """A convolution whose launch is deferred until its output is needed: if the consumer is a fusable BatchNorm, conv,
+    BatchNorm (+ residual) (+ ReLU) run inside ONE autograd node (_ConvBNActFn) — same kernels, half the autograd /
+    Python dispatch work.  `.F` on the output materialises the plain convolution."""
+    __slots__ = ("conv", "x", "km", "plain")
+
+    def __init__(self, conv, x, km):
+        self.conv, self.x, self.km, self.plain = conv, x, km, None
+
+    def out_rows(self):
+        return self.km.n_out if self.km is not None else self.x.shape[0]
+
+
 class _PendingBN:
     """A BatchNorm whose application is deferred so that a following `+= residual` and ReLU fuse into one kernel pair
     (lgs_bn_fwd / lgs_bn_bwd).  The reference calls bn -> (+= residual) -> relu as separate modules
-    (models/modules/resnet_block.py:41-57, models/res16unet.py:196-270); nothing in the model code changes."""
-    __slots__ = ("bn", "x", "res", "plain", "consumed")
+    (models/modules/resnet_block.py:41-57, models/res16unet.py:196-270); nothing in the model code changes.
+    `conv` is the still-pending convolution that feeds it (then `x` is that convolution's INPUT features)."""
+    __slots__ = ("bn", "x", "res", "plain", "consumed", "conv")
 
-    def __init__(self, bn, x):
-        self.bn, self.x, self.res, self.plain, self.consumed = bn, x, None, None, False
+    def __init__(self, bn, x, conv=None):
+        self.bn, self.x, self.res, self.plain, self.consumed, self.conv = bn, x, None, None, False, conv
 
 
 class SparseTensor:
@@ -416,9 +477,12 @@ class SparseTensor:
     @property
     def F(self):
         p = self._pending
-        if p is not None:            # materialise the deferred BatchNorm (+ residual), no ReLU
+        if p is not None:
             if p.plain is None:
-                p.plain = _bn_act(p, relu=False)
+                if type(p) is _PendingConv:      # materialise the deferred convolution
+                    p.plain = sparse_conv(p.x, p.conv.kernel, p.conv.bias, p.km, module=p.conv)
+                else:                            # materialise the deferred BatchNorm (+ residual), no ReLU
+                    p.plain = _bn_act(p, relu=False)
             self._F, self._pending = p.plain, None
         return self._F
 
@@ -470,7 +534,7 @@ class SparseTensor:
     def __iadd__(self, o):  # models/modules/resnet_block.py:54  `out += residual`
         self._same(o)
         p = self._pending
-        if p is not None and p.res is None and p.plain is None:
+        if type(p) is _PendingBN and p.res is None and p.plain is None:
             p.res = o.F              # fused into the deferred BatchNorm's epilogue
             return self
         self._F = self.F + o.F
@@ -486,56 +550,72 @@ def cat(*sts):
 # ----------------------------------------------------------------------------------------------------------
 # fused BatchNorm (+ residual) (+ ReLU)
 # ----------------------------------------------------------------------------------------------------------
+def _bn_fwd_impl(x, res, gamma, beta, bn, relu, update_running):
+    lib = _lib.load()
+    if not x.is_contiguous():
+        x = x.contiguous()
+    n, c = x.shape
+    if res is not None and not res.is_contiguous():
+        res = res.contiguous()
+    z = torch.empty_like(x)
+    stats = torch.empty((2, c), dtype=torch.float32, device=x.device)       # save_mean, save_invstd
+    rm = bn.running_mean if update_running else None
+    rv = bn.running_var if update_running else None
+    _lib.check(lib.lgs_bn_fwd(_lib.ptr(x), _lib.ptr(res), n, c, _lib.ptr(gamma), _lib.ptr(beta), float(bn.eps),
+                              float(bn.momentum), 1 if relu else 0, _lib.ptr(rm), _lib.ptr(rv), _lib.ptr(z),
+                              _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(_scratch64(x.device.index)), _stream()))
+    if update_running:
+        bn.num_batches_tracked.add_(1)
+    return x, z, stats
+
+
+def _bn_bwd_impl(x, z, gamma, stats, dz, relu, need_dres):
+    lib = _lib.load()
+    if not dz.is_contiguous():
+        dz = dz.contiguous()
+    n, c = x.shape
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if need_dres else None
+    dgb = torch.empty((2, c), dtype=torch.float32, device=x.device)
+    _lib.check(lib.lgs_bn_bwd(_lib.ptr(x), _lib.ptr(z), _lib.ptr(dz), n, c, _lib.ptr(gamma), _lib.ptr(stats[0]),
+                              _lib.ptr(stats[1]), 1 if relu else 0, _lib.ptr(dx), _lib.ptr(dres), _lib.ptr(dgb[0]),
+                              _lib.ptr(dgb[1]), _lib.ptr(_scratch64(x.device.index)), _stream()))
+    return dx, dres, dgb[0], dgb[1]
+
+
 class _BNActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, res, gamma, beta, bn, relu, update_running):
-        lib = _lib.load()
-        if not x.is_contiguous():
-            x = x.contiguous()
-        n, c = x.shape
-        if res is not None and not res.is_contiguous():
-            res = res.contiguous()
-        z = torch.empty_like(x)
-        stats = torch.empty((2, c), dtype=torch.float32, device=x.device)       # save_mean, save_invstd
-        scratch = torch.empty(16 * c, dtype=torch.float64, device=x.device)
-        rm = bn.running_mean if update_running else None
-        rv = bn.running_var if update_running else None
-        _lib.check(lib.lgs_bn_fwd(_lib.ptr(x), _lib.ptr(res), n, c, _lib.ptr(gamma), _lib.ptr(beta), float(bn.eps),
-                                  float(bn.momentum), 1 if relu else 0, _lib.ptr(rm), _lib.ptr(rv), _lib.ptr(z),
-                                  _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(scratch), _stream()))
-        if update_running:
-            bn.num_batches_tracked.add_(1)
+        x, z, stats = _bn_fwd_impl(x, res, gamma, beta, bn, relu, update_running)
         ctx.save_for_backward(x, z if relu else None, gamma, stats)
         ctx.relu, ctx.has_res = relu, res is not None
         return z
 
     @staticmethod
     def backward(ctx, dz):
-        lib = _lib.load()
         x, z, gamma, stats = ctx.saved_tensors
-        if not dz.is_contiguous():
-            dz = dz.contiguous()
-        n, c = x.shape
-        dx = torch.empty_like(x)
-        dres = torch.empty_like(x) if (ctx.has_res and ctx.needs_input_grad[1]) else None
-        dgb = torch.empty((2, c), dtype=torch.float32, device=x.device)
-        scratch = torch.empty(16 * c, dtype=torch.float64, device=x.device)
-        _lib.check(lib.lgs_bn_bwd(_lib.ptr(x), _lib.ptr(z), _lib.ptr(dz), n, c, _lib.ptr(gamma), _lib.ptr(stats[0]),
-                                  _lib.ptr(stats[1]), 1 if ctx.relu else 0, _lib.ptr(dx), _lib.ptr(dres), _lib.ptr(dgb[0]),
-                                  _lib.ptr(dgb[1]), _lib.ptr(scratch), _stream()))
-        return dx, dres, dgb[0], dgb[1], None, None, None
+        dx, dres, dg, db = _bn_bwd_impl(x, z, gamma, stats, dz, ctx.relu, ctx.has_res and ctx.needs_input_grad[1])
+        return dx, dres, dg, db, None, None, None
 
 
 def _bn_act(p: _PendingBN, relu: bool):
-    out = _BNActFn.apply(p.x, p.res, p.bn.weight, p.bn.bias, p.bn, relu, not p.consumed)
+    if p.conv is not None:
+        c = p.conv
+        out = _ConvBNActFn.apply(c.x, c.conv.kernel, p.bn.weight, p.bn.bias, p.res, c.km, _state["algo"], p.bn, relu,
+                                 not p.consumed, c.conv)
+    else:
+        out = _BNActFn.apply(p.x, p.res, p.bn.weight, p.bn.bias, p.bn, relu, not p.consumed)
     p.consumed = True          # running statistics are updated once per BatchNorm call
     return out
 
 
+def _bn_fusable_meta(bn, dtype, n, c):
+    return (bn.training and dtype is torch.float32 and _state["fuse_bn"] and type(bn) is nn.BatchNorm1d
+            and bn.track_running_stats and bn.affine and bn.momentum is not None and n >= 1 and c % 4 == 0 and c <= 1024)
+
+
 def _bn_fusable(bn, F):
-    return (bn.training and F.dtype is torch.float32 and _state["fuse_bn"] and type(bn) is nn.BatchNorm1d
-            and bn.track_running_stats and bn.affine and bn.momentum is not None and F.is_cuda and F.dim() == 2
-            and F.shape[0] >= 1 and F.shape[1] % 4 == 0 and F.shape[1] <= 1024)
+    return F.is_cuda and F.dim() == 2 and _bn_fusable_meta(bn, F.dtype, F.shape[0], F.shape[1])
 
 
 def set_bn_fusion(flag: bool):
@@ -546,103 +626,239 @@ def set_bn_fusion(flag: bool):
 # ----------------------------------------------------------------------------------------------------------
 # convolution
 # ----------------------------------------------------------------------------------------------------------
-class _SparseConvFn(torch.autograd.Function):
-    """out = conv(feats, W) through the C ABI; backward = dgrad (same kernel, W^T, mirrored/transposed table) + wgrad."""
+class _WeightPrep:
+    """Tensor-core operand forms (lgs_weight_prep) of every registered convolution's weights, refreshed by ONE
+    lgs_weight_prep_batch launch when a layer finds its parameter changed (version counter / storage) — i.e. once per
+    optimiser step instead of once per layer call.  Buffers are persistent per module.
+    Parameters updated through `.data` (which has its own version counter) need `invalidate_weight_cache()`."""
 
-    @staticmethod
-    def forward(ctx, feats, weight, bias, km, algo):
+    def __init__(self):
+        self.mods = weakref.WeakSet()
+        self.desc = {}          # (device, dt, nsplit) -> (key, device descriptor table, n_layers, total tiles, entries)
+
+    def register(self, mod):
+        self.mods.add(mod)
+
+    def invalidate(self):
+        for m in list(self.mods):
+            m._prep = None
+
+    def lookup(self, mod, w3, dt, nsplit, tdtype):
+        """(w_fwd, w_bwd) for `mod` (either may be None if the tensor-core kernels do not take that direction), or None
+        when this module is not handled here."""
+        st = mod._prep
+        sig = (w3._version, w3.data_ptr(), dt, nsplit)
+        if st is None or st[0] != sig:
+            self.refresh(w3.device, dt, nsplit, tdtype)
+            st = mod._prep
+            if st is None or st[0] != (w3._version, w3.data_ptr(), dt, nsplit):
+                return None
+        return st[1], st[2]
+
+    def refresh(self, device, dt, nsplit, tdtype):
         lib = _lib.load()
-        if not feats.is_contiguous():
-            feats = feats.contiguous()
-        w3 = weight.view(1, *weight.shape) if weight.dim() == 2 else weight
-        K, c_in, c_out = w3.shape
-        dt = _lib.F32 if feats.dtype is torch.float32 else _dtype_code(feats)
-        if algo == _lib.ALGO_TC3 and dt == _lib.BF16:
-            algo = _lib.ALGO_TC                                   # bf16 features: plain bf16 tensor-core products
-        n_in = feats.shape[0]
-        n_out = km.n_out if km is not None else n_in
-        out = torch.empty((n_out, c_out), dtype=feats.dtype, device=feats.device)
-        b32 = bias.detach().float().contiguous().view(-1) if bias is not None else None
-        need_dgrad = ctx.needs_input_grad[0]
-        w32 = w3.detach()
-        if w32.dtype is not torch.float32 or not w32.is_contiguous():
-            w32 = w32.float().contiguous()
-        # A tiny channel count (the 3 colour channels of conv0p1s1) is zero-padded to a 16-byte row so that the layer
-        # takes the tensor-core kernels; the padded weight rows are zero and the padded gradients are dropped.
-        c_in_true = c_in
-        row_bytes = c_in * feats.element_size()
-        if algo != _lib.ALGO_SIMT and c_in < 16 and row_bytes % 16 != 0:
-            c_in = -(-row_bytes // 16) * 16 // feats.element_size()
-            feats = torch.nn.functional.pad(feats, (0, c_in - c_in_true))
-            w32 = torch.nn.functional.pad(w32, (0, 0, 0, c_in - c_in_true))
-        # tensor-core operand forms of the weights (one launch); a direction the TC kernels do not take (e.g. c_in = 3)
-        # runs on the exact SIMT kernel with the parameter itself
-        fwd_tc = algo != _lib.ALGO_SIMT and _tc_supported(lib, c_in, c_out, dt)
-        bwd_tc = algo != _lib.ALGO_SIMT and need_dgrad and _tc_supported(lib, c_out, c_in, dt)
-        nsplit = 2 if algo == _lib.ALGO_TC3 else 1
-        w_fwd = w_bwd = None
-        if fwd_tc or bwd_tc:
+        es = 2 if dt == _lib.BF16 else 4
+        entries = []
+        for m in list(self.mods):
+            w = m.kernel
+            if w.device != device or w.dtype is not torch.float32 or not w.is_contiguous():
+                continue
+            K, c_in, c_out = (1,) + tuple(w.shape) if w.dim() == 2 else tuple(w.shape)
+            if (c_in * es) % 16 != 0:
+                continue                                   # padded per call (conv0p1s1)
+            f_ok, b_ok = _tc_supported(lib, c_in, c_out, dt), _tc_supported(lib, c_out, c_in, dt)
+            if not (f_ok or b_ok):
+                continue
+            bufs = m._prep_bufs.get((dt, nsplit))
+            if bufs is None or bufs[2] != w.data_ptr():
+                fb = torch.empty((nsplit, K, c_out, c_in), dtype=tdtype, device=device) if f_ok else None
+                bb = torch.empty((nsplit, K, c_in, c_out), dtype=tdtype, device=device) if b_ok else None
+                bufs = m._prep_bufs[(dt, nsplit)] = (fb, bb, w.data_ptr())
+            entries.append((m, w, K, c_in, c_out, bufs[0], bufs[1]))
+        if not entries:
+            return
+        key = tuple((e[1].data_ptr(), e[5].data_ptr() if e[5] is not None else 0,
+                     e[6].data_ptr() if e[6] is not None else 0) for e in entries)
+        cached = self.desc.get((device, dt, nsplit))
+        if cached is None or cached[0] != key:
+            rows, tile0 = [], 0
+            for (_, w, K, c_in, c_out, fb, bb), k3 in zip(entries, key):
+                rows.append([k3[0], k3[1], k3[2], K, c_in, c_out, tile0, 0])
+                tile0 += K * ((c_in + 31) // 32) * ((c_out + 31) // 32)
+            table = torch.tensor(rows, dtype=torch.int64).to(device)
+            cached = self.desc[(device, dt, nsplit)] = (key, table, len(rows), tile0)
+        _lib.check(lib.lgs_weight_prep_batch(_lib.ptr(cached[1]), cached[2], cached[3], nsplit, dt, _stream()))
+        for m, w, _, _, _, fb, bb in entries:
+            m._prep = ((w._version, w.data_ptr(), dt, nsplit), fb, bb)
+
+
+_weight_prep = _WeightPrep()
+
+
+def invalidate_weight_cache():
+    """Force the next convolution call to re-derive the tensor-core weight operands (needed only after in-place
+    parameter updates that bypass the version counter, e.g. through `.data`)."""
+    _weight_prep.invalidate()
+
+
+class _ConvMeta:
+    __slots__ = ("km", "algo", "bwd_tc", "tc_layout", "dims", "w_shape", "w_dtype", "has_bias", "c_in_true")
+
+
+def _conv_fwd_impl(feats, weight, bias, km, algo, need_dgrad, module=None):
+    """one convolution launch (+ weight operand prep); returns (out, feats as saved for wgrad, dgrad weights, meta)"""
+    lib = _lib.load()
+    if not feats.is_contiguous():
+        feats = feats.contiguous()
+    w3 = weight.view(1, *weight.shape) if weight.dim() == 2 else weight
+    K, c_in, c_out = w3.shape
+    dt = _lib.F32 if feats.dtype is torch.float32 else _dtype_code(feats)
+    if algo == _lib.ALGO_TC3 and dt == _lib.BF16:
+        algo = _lib.ALGO_TC                                   # bf16 features: plain bf16 tensor-core products
+    n_in = feats.shape[0]
+    n_out = km.n_out if km is not None else n_in
+    out = torch.empty((n_out, c_out), dtype=feats.dtype, device=feats.device)
+    b32 = bias.detach().float().contiguous().view(-1) if bias is not None else None
+    w32 = w3.detach()
+    if w32.dtype is not torch.float32 or not w32.is_contiguous():
+        w32 = w32.float().contiguous()
+    # A tiny channel count (the 3 colour channels of conv0p1s1) is zero-padded to a 16-byte row so that the layer
+    # takes the tensor-core kernels; the padded weight rows are zero and the padded gradients are dropped.
+    c_in_true = c_in
+    row_bytes = c_in * feats.element_size()
+    padded = algo != _lib.ALGO_SIMT and c_in < 16 and row_bytes % 16 != 0
+    if padded:
+        c_in = -(-row_bytes // 16) * 16 // feats.element_size()
+        feats = torch.nn.functional.pad(feats, (0, c_in - c_in_true))
+        w32 = torch.nn.functional.pad(w32, (0, 0, 0, c_in - c_in_true))
+    # tensor-core operand forms of the weights; a direction the TC kernels do not take (e.g. c_in = 3) runs on the
+    # exact SIMT kernel with the parameter itself
+    fwd_tc = algo != _lib.ALGO_SIMT and _tc_supported(lib, c_in, c_out, dt)
+    bwd_tc = algo != _lib.ALGO_SIMT and need_dgrad and _tc_supported(lib, c_out, c_in, dt)
+    nsplit = 2 if algo == _lib.ALGO_TC3 else 1
+    w_fwd = w_bwd = None
+    if fwd_tc or bwd_tc:
+        pre = None
+        if (module is not None and not padded and _state["batch_prep"] and weight.dtype is torch.float32
+                and weight.is_contiguous()):
+            pre = _weight_prep.lookup(module, w3, dt, nsplit, feats.dtype)     # one launch for all layers, per update
+        if pre is not None and (pre[0] is not None or not fwd_tc) and (pre[1] is not None or not bwd_tc):
+            w_fwd, w_bwd = pre[0], (pre[1] if bwd_tc else None)
+        else:
             if fwd_tc:
                 w_fwd = torch.empty((nsplit, K, c_out, c_in), dtype=feats.dtype, device=feats.device)
             if bwd_tc:
                 w_bwd = torch.empty((nsplit, K, c_in, c_out), dtype=feats.dtype, device=feats.device)
             _lib.check(lib.lgs_weight_prep(_lib.ptr(w32), K, c_in, c_out, nsplit, _lib.ptr(w_fwd), _lib.ptr(w_bwd), dt,
                                            _stream()))
-        tc_layout = _lib.W_KNC_SPLIT if nsplit == 2 else _lib.W_KNC
-        if fwd_tc:
-            wf, layout, a = w_fwd, tc_layout, algo
+    tc_layout = _lib.W_KNC_SPLIT if nsplit == 2 else _lib.W_KNC
+    if fwd_tc:
+        wf, layout, a = w_fwd, tc_layout, algo
+    else:
+        wf, layout, a = w32.to(feats.dtype), _lib.W_KCN, _lib.ALGO_SIMT
+    with _Timed("fwd", K, c_in, c_out, n_in, n_out, km, feats.dtype):
+        _lib.check(lib.lgs_conv_fwd(_lib.ptr(feats), n_in, c_in, _lib.ptr(wf), layout, K, c_out,
+                                    _lib.ptr(km.fwd_table) if km is not None else None, n_out, 0, _lib.ptr(b32),
+                                    _lib.ptr(out), dt, a, _stream()))
+    if need_dgrad and not bwd_tc:
+        w_bwd = w32.to(feats.dtype)                           # [K, c_in, c_out] read as LGS_W_KNC by the SIMT dgrad
+    m = _ConvMeta()
+    m.km, m.algo, m.bwd_tc, m.tc_layout = km, algo, bwd_tc, tc_layout
+    m.dims, m.w_shape, m.w_dtype, m.has_bias = (K, c_in, c_out), weight.shape, weight.dtype, bias is not None
+    m.c_in_true = c_in_true
+    return out, feats, w_bwd, m
+
+
+def _conv_bwd_impl(m, feats, w_bwd, gout, need_gin, need_gw, need_gb):
+    """dgrad (the forward kernel on the transposed problem) + wgrad (+ bias gradient) of one convolution"""
+    lib = _lib.load()
+    km, algo = m.km, m.algo
+    if not gout.is_contiguous():
+        gout = gout.contiguous()
+    K, c_in, c_out = m.dims
+    n_in, n_out = feats.shape[0], gout.shape[0]
+    dt = _lib.F32 if feats.dtype is torch.float32 else _dtype_code(feats)
+    gin = gw = gb = None
+    table = _lib.ptr(km.fwd_table) if km is not None else None
+    joined = None
+    if need_gw:
+        gw = torch.empty((K, c_in, c_out), dtype=torch.float32, device=feats.device)
+        if need_gin and _state["overlap_wgrad"] and _state["profile"] is None:
+            # fork: wgrad on the side stream (it reads feats / gout, ready on this stream now), dgrad on this stream;
+            # joined below, before anything can consume gw — every buffer stays owned by the training stream
+            side, ev_fork, ev_join = _side_stream(feats.device.index)
+            ev_fork.record()
+            side.wait_event(ev_fork)
+            _lib.check(lib.lgs_conv_wgrad(_lib.ptr(feats), n_in, c_in, _lib.ptr(gout), n_out, c_out, table, K,
+                                          _lib.ptr(gw), dt, algo, ctypes.c_void_p(side.cuda_stream)))
+            ev_join.record(side)
+            joined = ev_join
+    if need_gin:
+        # dgrad = the same kernel on the transposed problem; W[k] ([c_in,c_out]) is its K-major B operand as is
+        gin = torch.empty((n_in, c_in), dtype=feats.dtype, device=feats.device)
+        layout, a = (m.tc_layout, algo) if m.bwd_tc else (_lib.W_KNC, _lib.ALGO_SIMT)
+        with _Timed("dgrad", K, c_out, c_in, n_out, n_in, km, feats.dtype):
+            _lib.check(lib.lgs_conv_fwd(_lib.ptr(gout), n_out, c_out, _lib.ptr(w_bwd), layout, K, c_in,
+                                        _lib.ptr(km.bwd_table) if km is not None else None, n_in,
+                                        1 if (km is not None and km.bwd_reverse) else 0, None, _lib.ptr(gin), dt,
+                                        a, _stream()))
+    if need_gw:
+        if joined is not None:
+            joined.wait()                                     # training stream waits for the side-stream wgrad
         else:
-            wf, layout, a = w32.to(feats.dtype), _lib.W_KCN, _lib.ALGO_SIMT
-        with _Timed("fwd", K, c_in, c_out, n_in, n_out, km, feats.dtype):
-            _lib.check(lib.lgs_conv_fwd(_lib.ptr(feats), n_in, c_in, _lib.ptr(wf), layout, K, c_out,
-                                        _lib.ptr(km.fwd_table) if km is not None else None, n_out, 0, _lib.ptr(b32),
-                                        _lib.ptr(out), dt, a, _stream()))
-        if need_dgrad and not bwd_tc:
-            w_bwd = w32.to(feats.dtype)                           # [K, c_in, c_out] read as LGS_W_KNC by the SIMT dgrad
+            with _Timed("wgrad", K, c_in, c_out, n_in, n_out, km, feats.dtype):
+                _lib.check(lib.lgs_conv_wgrad(_lib.ptr(feats), n_in, c_in, _lib.ptr(gout), n_out, c_out, table, K,
+                                              _lib.ptr(gw), dt, algo, _stream()))
+        if m.c_in_true != c_in:
+            gw = gw[:, :m.c_in_true, :].contiguous()
+        gw = gw.view(m.w_shape).to(m.w_dtype)
+    if need_gb:
+        gb = gout.float().sum(0, keepdim=True)
+    if gin is not None and m.c_in_true != c_in:
+        gin = gin[:, :m.c_in_true].contiguous()
+    return gin, gw, gb
+
+
+class _SparseConvFn(torch.autograd.Function):
+    """out = conv(feats, W) through the C ABI; backward = dgrad (same kernel, W^T, mirrored/transposed table) + wgrad."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, bias, km, algo, module):
+        out, feats, w_bwd, ctx.meta = _conv_fwd_impl(feats, weight, bias, km, algo, ctx.needs_input_grad[0], module)
         ctx.save_for_backward(feats, w_bwd)
-        ctx.km, ctx.algo, ctx.bwd_tc, ctx.tc_layout = km, algo, bwd_tc, tc_layout
-        ctx.dims, ctx.w_shape, ctx.w_dtype, ctx.has_bias = (K, c_in, c_out), weight.shape, weight.dtype, bias is not None
-        ctx.c_in_true = c_in_true
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        lib = _lib.load()
         feats, w_bwd = ctx.saved_tensors
-        km, algo = ctx.km, ctx.algo
-        if not gout.is_contiguous():
-            gout = gout.contiguous()
-        K, c_in, c_out = ctx.dims
-        n_in, n_out = feats.shape[0], gout.shape[0]
-        dt = _lib.F32 if feats.dtype is torch.float32 else _dtype_code(feats)
-        gin = gw = gb = None
-        if ctx.needs_input_grad[0]:
-            # dgrad = the same kernel on the transposed problem; W[k] ([c_in,c_out]) is its K-major B operand as is
-            gin = torch.empty((n_in, c_in), dtype=feats.dtype, device=feats.device)
-            layout, a = (ctx.tc_layout, algo) if ctx.bwd_tc else (_lib.W_KNC, _lib.ALGO_SIMT)
-            with _Timed("dgrad", K, c_out, c_in, n_out, n_in, km, feats.dtype):
-                _lib.check(lib.lgs_conv_fwd(_lib.ptr(gout), n_out, c_out, _lib.ptr(w_bwd), layout, K, c_in,
-                                            _lib.ptr(km.bwd_table) if km is not None else None, n_in,
-                                            1 if (km is not None and km.bwd_reverse) else 0, None, _lib.ptr(gin), dt,
-                                            a, _stream()))
-        if ctx.needs_input_grad[1]:
-            gw = torch.empty((K, c_in, c_out), dtype=torch.float32, device=feats.device)
-            with _Timed("wgrad", K, c_in, c_out, n_in, n_out, km, feats.dtype):
-                _lib.check(lib.lgs_conv_wgrad(_lib.ptr(feats), n_in, c_in, _lib.ptr(gout), n_out, c_out,
-                                              _lib.ptr(km.fwd_table) if km is not None else None, K, _lib.ptr(gw), dt,
-                                              algo, _stream()))
-            if ctx.c_in_true != c_in:
-                gw = gw[:, :ctx.c_in_true, :].contiguous()
-            gw = gw.view(ctx.w_shape).to(ctx.w_dtype)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gout.float().sum(0, keepdim=True)
-        if gin is not None and ctx.c_in_true != c_in:
-            gin = gin[:, :ctx.c_in_true].contiguous()
-        return gin, gw, gb, None, None
+        m = ctx.meta
+        gin, gw, gb = _conv_bwd_impl(m, feats, w_bwd, gout, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                     m.has_bias and ctx.needs_input_grad[2])
+        return gin, gw, gb, None, None, None
 
 
-def sparse_conv(feats, weight, bias, km, algo=None):
-    return _SparseConvFn.apply(feats, weight, bias, km, _state["algo"] if algo is None else algo)
+class _ConvBNActFn(torch.autograd.Function):
+    """z = relu?( BatchNorm(conv(feats, W)) [+ residual] ) as ONE autograd node: lgs_conv_fwd + lgs_bn_fwd forward,
+    lgs_bn_bwd + dgrad + wgrad backward.  (models/modules/resnet_block.py:41-57: conv -> norm -> (+=) -> relu)"""
+
+    @staticmethod
+    def forward(ctx, feats, weight, gamma, beta, res, km, algo, bn, relu, update_running, module):
+        y, feats, w_bwd, ctx.meta = _conv_fwd_impl(feats, weight, None, km, algo, ctx.needs_input_grad[0], module)
+        y, z, stats = _bn_fwd_impl(y, res, gamma, beta, bn, relu, update_running)
+        ctx.save_for_backward(feats, w_bwd, y, z if relu else None, gamma, stats)
+        ctx.relu, ctx.has_res = relu, res is not None
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        feats, w_bwd, y, z, gamma, stats = ctx.saved_tensors
+        dy, dres, dg, db = _bn_bwd_impl(y, z, gamma, stats, dz, ctx.relu, ctx.has_res and ctx.needs_input_grad[4])
+        gin, gw, _ = _conv_bwd_impl(ctx.meta, feats, w_bwd, dy, ctx.needs_input_grad[0], ctx.needs_input_grad[1], False)
+        return gin, gw, dg, db, dres, None, None, None, None, None, None
+
+
+def sparse_conv(feats, weight, bias, km, algo=None, module=None):
+    return _SparseConvFn.apply(feats, weight, bias, km, _state["algo"] if algo is None else algo, module)
 
 
 class MinkowskiNetwork(nn.Module):
@@ -676,6 +892,8 @@ class _ConvBase(nn.Module):
         self._ks = _uniform(list(kernel_generator.kernel_size), "kernel size")
         self._dil = _uniform(list(kernel_generator.kernel_dilation), "dilation")
         self._stride = _uniform(list(kernel_generator.kernel_stride), "stride")
+        self._prep, self._prep_bufs = None, {}      # cached tensor-core weight operands (_WeightPrep)
+        _weight_prep.register(self)
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -691,9 +909,14 @@ class _ConvBase(nn.Module):
         mgr = x.coordinate_manager
         in_key = x.coordinate_map_key
         if self.use_mm:
-            return x._like(sparse_conv(x.F, self.kernel, self.bias, None))
-        out_key, km = mgr.conv_maps(in_key, self._ks, self._stride, self._dil, self.TRANSPOSE)
-        return SparseTensor._make(sparse_conv(x.F, self.kernel, self.bias, km), out_key, mgr)
+            out_key, km = in_key, None
+        else:
+            out_key, km = mgr.conv_maps(in_key, self._ks, self._stride, self._dil, self.TRANSPOSE)
+        F = x.F
+        if self.bias is None and _state["fuse_conv_bn"] and F.dtype is torch.float32:
+            # deferred: a following fusable BatchNorm turns conv + BN (+ residual) (+ ReLU) into one autograd node
+            return SparseTensor._make(None, out_key, mgr, _PendingConv(self, F, km))
+        return SparseTensor._make(sparse_conv(F, self.kernel, self.bias, km, module=self), out_key, mgr)
 
     def extra_repr(self):
         kg = self.kernel_generator
@@ -719,6 +942,10 @@ class MinkowskiBatchNorm(nn.Module):
                                  track_running_stats=track_running_stats)
 
     def forward(self, x: SparseTensor):
+        p = x._pending
+        if (type(p) is _PendingConv and p.plain is None
+                and _bn_fusable_meta(self.bn, p.x.dtype, p.out_rows(), p.conv.out_channels)):
+            return SparseTensor._make(None, x.coordinate_map_key, x.coordinate_manager, _PendingBN(self.bn, p.x, p))
         F = x.F
         if _bn_fusable(self.bn, F):
             return SparseTensor._make(None, x.coordinate_map_key, x.coordinate_manager, _PendingBN(self.bn, F))
@@ -743,7 +970,7 @@ class MinkowskiReLU(nn.Module):
 
     def forward(self, x: SparseTensor):
         p = x._pending
-        if p is not None and p.plain is None:
+        if type(p) is _PendingBN and p.plain is None:
             return x._like(_bn_act(p, relu=True))      # BatchNorm (+ residual) + ReLU in one kernel pair
         return x._like(torch.relu(x.F))
 

@@ -162,3 +162,31 @@ def test_bf16_features(E):
         out = E.sparse_conv(g.F, w.cuda(), None, gk)
         assert out.dtype == torch.bfloat16
         assert rel_err(out.float().cpu(), ref) < 1e-2     # one bf16 rounding of the output
+
+
+@pytest.mark.parametrize("tm,rt", [(None, None), (2, 128), (3, 87), (4, 66), (2, 40), (3, 128), (4, 8)])
+@pytest.mark.parametrize("cin,cout", [(96, 96), (128, 96), (32, 32)])
+def test_balanced_row_tiles(E, monkeypatch, tm, rt, cin, cout):
+    """multi-tile tcgen05 kernel with TM tiles of rt <= 128 rows per CTA (grid = a whole number of waves; rows >= rt are
+    empty MMA lanes): forward and dgrad equal the exact SIMT kernels on a level-1-sized map (~40 K voxels = 313 tiles,
+    the case that costs 3 waves as full tiles), for the heuristic's own choice and for forced (TM, rt) pairs."""
+    from languagegroundedsemseg_b200 import scenes
+    c, _, _ = scenes.synthetic_voxel_scene(1, 40000)
+    torch.manual_seed(cin + cout)
+    f = torch.randn(c.shape[0], cin).cuda()
+    gy = torch.randn(c.shape[0], cout).cuda()
+    conv = E.MinkowskiConvolution(cin, cout, kernel_size=3, dimension=3).cuda()
+    cc = torch.from_numpy(c).cuda()
+    res = {}
+    for algo in ("simt", "tc"):
+        E.set_conv_algo(algo)
+        if algo == "tc" and tm is not None:
+            monkeypatch.setenv("LGS_TC_TM", str(tm))
+            monkeypatch.setenv("LGS_TC_RT", str(rt))
+        x = f.clone().requires_grad_(True)
+        y = conv(E.SparseTensor(x, cc)).F
+        y.backward(gy)
+        res[algo] = (y.detach(), x.grad.clone())
+        conv.kernel.grad = None
+    assert rel_err(res["tc"][0], res["simt"][0]) < TOL["tc"]
+    assert rel_err(res["tc"][1], res["simt"][1]) < TOL["tc"]
