@@ -1442,6 +1442,27 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
   if (chunks < 1) chunks = 1;
   p.rows_per_chunk = cdiv(cdiv(n_out, chunks), R) * R;
   chunks = cdiv(n_out, p.rows_per_chunk);
+  if (!getenv("LGS_WGRAD_NO_BALANCE")) {
+    // One CTA per SM is resident (TMEM): a grid a few CTAs over a multiple of 148 pays a whole extra wave (76 x 2 = 152
+    // CTAs for the 32 -> 32 layers of a 38 K-row map).  Search the chunk count for the cheapest waves x (tiles + 2 for the
+    // red.add epilogue) and keep the choice above unless another one is clearly better.
+    const int64_t per = int64_t(groups) * n_splits * m_slices;
+    auto cost_of = [&](int64_t c, int64_t& rows, int64_t& act) {
+      rows = cdiv(cdiv(n_out, c), R) * R;
+      act = cdiv(n_out, rows);
+      return double(cdiv(act * per, 148)) * double(rows / R + 2);
+    };
+    int64_t rows = 0, act = 0;
+    double best = cost_of(chunks, rows, act);
+    int64_t best_rows = p.rows_per_chunk, best_chunks = chunks;
+    const int64_t c_hi = std::min<int64_t>(max_chunks, cdiv(148 * 4, per));   // chunks stay >= 4 tiles tall
+    for (int64_t c = 1; c <= c_hi; ++c) {
+      const double cost = cost_of(c, rows, act);
+      if (cost < best * 0.97) best = cost, best_rows = rows, best_chunks = act;
+    }
+    p.rows_per_chunk = best_rows;
+    chunks = best_chunks;
+  }
 
   // kernel-side sizes use nb_in (gathered) for the producer loop but the stage stride must cover what the MMA reads
   WParams q = p;
