@@ -294,7 +294,7 @@ using namespace lgs;
 // threads of a vectorised statistics block: the largest multiple of c/4 that fits (c <= 1024 => c/4 <= 256)
 static inline int bn_vec_threads(int c) { return (BN_VTHREADS / (c >> 2)) * (c >> 2); }
 static inline bool bn_use_vec(const void* a, const void* b, const void* d, int c) {
-  static const bool off = getenv("LGS_BN_SCALAR") != nullptr;
+  const bool off = getenv("LGS_BN_SCALAR") != nullptr;
   const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(d);
   return !off && (bits & 15) == 0 && (c & 3) == 0 && c >= 4 && c <= 1024;
 }

@@ -909,7 +909,7 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
       // rows: the gather stream shrinks with rt, the MMAs do not (empty lanes), hence the floor.  A map of 301 tiles
       // (level 1 of a 150 K-voxel scene) costs 3 as 128-row tiles (148 + 148 + 5 CTAs) but 3 * 87/128 = 2.04 balanced.
       // Ties go to the larger TM (less weight traffic).
-      static const bool balance = !getenv("LGS_TC_NO_BALANCE");
+      const bool balance = !getenv("LGS_TC_NO_BALANCE");
       const double mma_floor = precise ? 0.6 : 0.35;
       double best = -1.0;
       const bool ts1 = precise && getenv("LGS_TC_TS1");   // TM = 1 otherwise means conv_tc_kernel below

@@ -63,6 +63,7 @@ def main():
     E._stream = lambda: None
     E._scratch64 = lambda idx: torch.empty(16 * 1024, dtype=torch.float64)
     E._side_stream = lambda idx: (FakeStream(), FakeEvent(), FakeEvent())
+    E._cur_stream_obj = lambda idx: FakeStream()
     sizes = {1: 1000, 2: 300, 4: 100, 8: 30, 16: 10}
     for flags in ((True, True, True), (False, False, False), (True, False, True), (False, True, False)):
         E.set_conv_bn_fusion(flags[0]), E.set_wgrad_overlap(flags[1]), E.set_batched_weight_prep(flags[2])
