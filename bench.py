@@ -35,6 +35,11 @@ MODEL = "Res16UNet34C"
 TARGET_VOXELS = 150_000
 
 
+def workload_string(model, n_vox, voxel_size, voxels_target):
+    return (f"{model} fwd+bwd+SGD, 1 synthetic ScanNet-shaped scene/GPU, {n_vox} voxels @{voxel_size * 100:g}cm, 200 classes"
+            + (" (BASELINE configs[1])" if (model == MODEL and voxels_target == TARGET_VOXELS) else ""))
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -50,6 +55,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.window = None          # (t0, t1) host times of the timed region: only samples inside it are reported
 
     def __enter__(self):
         try:
@@ -65,7 +71,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.time()] + [x.strip() for x in line.split(",")])
 
     def __exit__(self, *a):
         if self.proc:
@@ -74,14 +80,17 @@ class ClockSampler:
             self.t.join(timeout=2)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        rows = [r[1:] for r in self.rows if self.window is None or self.window[0] <= r[0] <= self.window[1] + 0.25]
+        if not rows:                # region shorter than one polling period: the nearest samples
+            rows = [r[1:] for r in self.rows[-2:]]
+        rows = [r for r in rows if len(r) >= 7]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 7:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -218,20 +227,25 @@ def run_engine(args, rank, world, local_rank):
             loss_evt[(i - 1) & 1].synchronize()
             e2e_state["last"] = float(loss_host[(i - 1) & 1])
 
-    for _ in range(args.warmup):
-        resident_step()
-    barrier()
+    # The nvidia-smi poller starts BEFORE the warm-up (its NVML start-up stalls the driver for tens of ms, which used to
+    # land inside the timed region); it keeps polling every 200 ms through the timed region and only those samples are
+    # reported.  One poller (rank 0): concurrent nvidia-smi loops slow the driver.
+    with ClockSampler(local_rank if rank == 0 else -1) as clk:
+        for _ in range(args.warmup):
+            resident_step()
+        barrier()
 
-    # ---- timed region: `value` --------------------------------------------------------------------------
-    l0 = _lib.launch_count()
-    with ClockSampler(local_rank if rank == 0 else -1) as clk:   # one poller: concurrent nvidia-smi loops slow the driver
+        # ---- timed region: `value` ----------------------------------------------------------------------
+        l0 = _lib.launch_count()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_w0 = time.time()
         ev0.record()
         for _ in range(args.steps):
             loss = resident_step()
         ev1.record()
         barrier()
+        clk.window = (t_w0, time.time())
     ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - l0
     loss_val = float(loss.item())
@@ -351,8 +365,7 @@ def run_engine(args, rank, world, local_rank):
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.dtype == "f32" else "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.model} fwd+bwd+SGD, 1 synthetic ScanNet-shaped scene/GPU, {n_vox} voxels @{args.voxel_size * 100:g}cm, "
-                               f"200 classes{' (BASELINE configs[1])' if (args.model == MODEL and args.voxels == TARGET_VOXELS) else ''}", "voxels_per_gpu": n_vox, "algo": args.algo,
+        "config": {"workload": workload_string(args.model, n_vox, args.voxel_size, args.voxels), "voxels_per_gpu": n_vox, "algo": args.algo,
                    "math": {"tc": "tcgen05 3xTF32 products (fp32-grade) fwd/dgrad, TF32 wgrad, fp32 accumulate in TMEM",
                             "tf32": "tcgen05 single-pass TF32, fp32 accumulate", "simt": "fp32 FMA"}[args.algo]
                    if args.dtype == "f32" else "tcgen05 bf16 products, fp32 accumulate in TMEM",
@@ -439,8 +452,11 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt / steps * 1e3, 1),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{MODEL} fwd+bwd+SGD; CPU restatement of MinkowskiEngine 0.5.4's CPU algorithm "
-                                       f"(the reference's own ME is not installable here) on a bounded {n}-voxel sample",
+                # same workload as the engine arm; each step runs on a bounded sample of it (cpu_baseline.sample)
+                "config": {"workload": workload_string(MODEL, make_scene(0, TARGET_VOXELS)[0].shape[0], 0.02, TARGET_VOXELS),
+                           "sample_voxels": n,
+                           "implementation": "CPU restatement of MinkowskiEngine 0.5.4's CPU algorithm (oracle/me_cpu.py; the "
+                                             "reference's own ME is not installable here), all host threads",
                            "cpu": cpu_model_name()},
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

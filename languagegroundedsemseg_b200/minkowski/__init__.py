@@ -640,30 +640,48 @@ def set_bn_fusion(flag: bool):
 # ----------------------------------------------------------------------------------------------------------
 class _WeightPrep:
     """Tensor-core operand forms (lgs_weight_prep) of every registered convolution's weights, refreshed by ONE
-    lgs_weight_prep_batch launch when a layer finds its parameter changed (version counter / storage) — i.e. once per
-    optimiser step instead of once per layer call.  Buffers are persistent per module.
-    Parameters updated through `.data` (which has its own version counter) need `invalidate_weight_cache()`."""
+    lgs_weight_prep_batch launch instead of one launch per layer call.  Buffers are persistent per module.
+    A cached operand is trusted only while (a) no convolution weight gradient has been computed since it was derived
+    (every training step therefore re-derives all of them, once, at its first convolution), (b) no torch optimiser has
+    stepped (global post-step hook) and (c) the parameter's version counter and storage are unchanged.  Version
+    counters alone are not enough: torch's fused optimisers update parameters without bumping them.
+    Parameters changed behind all three (e.g. `p.data.add_()` in inference code) need `invalidate_weight_cache()`."""
 
     def __init__(self):
         self.mods = weakref.WeakSet()
         self.desc = {}          # (device, dt, nsplit) -> (key, device descriptor table, n_layers, total tiles, entries)
+        self.epoch = 0          # bumped whenever the parameters may have changed
+        self.dirty = False      # a weight gradient was computed / an optimiser stepped since the last refresh
+        self.hooked = False
 
     def register(self, mod):
+        self.hook_optimizers()
         self.mods.add(mod)
 
     def invalidate(self):
-        for m in list(self.mods):
-            m._prep = None
+        self.dirty = True
+
+    def hook_optimizers(self):
+        if not self.hooked:
+            self.hooked = True
+            try:
+                from torch.optim.optimizer import register_optimizer_step_post_hook
+                register_optimizer_step_post_hook(lambda *a, **k: self.invalidate())
+            except ImportError:      # older torch: the gradient rule (a) still covers training loops
+                pass
 
     def lookup(self, mod, w3, dt, nsplit, tdtype):
         """(w_fwd, w_bwd) for `mod` (either may be None if the tensor-core kernels do not take that direction), or None
         when this module is not handled here."""
+        if self.dirty:
+            self.dirty = False
+            self.epoch += 1
         st = mod._prep
-        sig = (w3._version, w3.data_ptr(), dt, nsplit)
+        sig = (self.epoch, w3._version, w3.data_ptr(), dt, nsplit)
         if st is None or st[0] != sig:
             self.refresh(w3.device, dt, nsplit, tdtype)
             st = mod._prep
-            if st is None or st[0] != (w3._version, w3.data_ptr(), dt, nsplit):
+            if st is None or st[0] != sig:
                 return None
         return st[1], st[2]
 
@@ -701,7 +719,7 @@ class _WeightPrep:
             cached = self.desc[(device, dt, nsplit)] = (key, table, len(rows), tile0)
         _lib.check(lib.lgs_weight_prep_batch(_lib.ptr(cached[1]), cached[2], cached[3], nsplit, dt, _stream()))
         for m, w, _, _, _, fb, bb in entries:
-            m._prep = ((w._version, w.data_ptr(), dt, nsplit), fb, bb)
+            m._prep = ((self.epoch, w._version, w.data_ptr(), dt, nsplit), fb, bb)
 
 
 _weight_prep = _WeightPrep()
@@ -794,6 +812,7 @@ def _conv_bwd_impl(m, feats, w_bwd, gout, need_gin, need_gw, need_gb):
     table = _lib.ptr(km.fwd_table) if km is not None else None
     joined = None
     if need_gw:
+        _weight_prep.dirty = True       # a weight gradient exists: cached tensor-core weight operands expire
         gw = torch.empty((K, c_in, c_out), dtype=torch.float32, device=feats.device)
         if need_gin and _state["overlap_wgrad"] and _state["profile"] is None:
             # fork: wgrad on the side stream (it reads feats / gout, ready on this stream now), dgrad on this stream;
