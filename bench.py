@@ -188,7 +188,8 @@ def run_engine(args, rank, world, local_rank):
     # Every step stages the NEXT step's batch (copies + coordinate/kernel maps) on a side stream while it runs
     # (languagegroundedsemseg_b200/prefetch.py); the map build is still done once per step, inside the timed region.
     from languagegroundedsemseg_b200.prefetch import SparseBatchPrefetcher
-    pf = SparseBatchPrefetcher(dev, fdtype) if not args.no_prefetch else None
+    pf = (SparseBatchPrefetcher(dev, fdtype, threaded=os.environ.get("LGS_STAGE_THREAD", "1") != "0")
+          if not args.no_prefetch else None)
     tickets = {}
 
     def staged_step(key, src):

@@ -929,7 +929,10 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
           break;
         }
       }
-      if (const char* e = getenv("LGS_TC_TM")) TM = atoi(e), RT = BM;
+      if (const char* e = getenv("LGS_TC_TM")) {      // tuning / test override, clamped to what TMEM holds
+        TM = std::min(4, std::max(1, atoi(e))), RT = BM;
+        while (TM > 1 && TM * c_pad2 + ta_min_cols > 512) --TM;
+      }
       if (const char* e = getenv("LGS_TC_RT")) RT = std::min(BM, std::max(8, atoi(e)));
     }
     if (TM >= 2 || (TM == 1 && precise && getenv("LGS_TC_TS1"))) {

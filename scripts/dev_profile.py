@@ -23,6 +23,6 @@ for e in ev:
     if getattr(e, "device_type", None) is not None and e.device_type.name == "CUDA":
         seen[e.key] = (e.device_time_total / 3e3, e.count // 3)
 tot = sum(v[0] for v in seen.values())
-print(f"GPU kernel time per step: {tot:.2f} ms")
+print(f"GPU kernel time per step: {tot:.2f} ms (sum of kernel durations; equals GPU-busy time only with LGS_OVERLAP_WGRAD=0)")
 for k, (t, n) in sorted(seen.items(), key=lambda kv: -kv[1][0])[:28]:
     print(f"{t:8.3f} ms {100*t/tot:5.1f}% x{n:4d}  {k[:110]}")
