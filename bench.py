@@ -111,11 +111,15 @@ def build_net(engine, device, dtype, model=None):
     return net, opt
 
 
-def train_step(ST, net, opt, coords, feats, labels, reducer=None, st=None):
+def _aten_criterion(logits, labels):
+    return torch.nn.functional.cross_entropy(logits.float(), labels, ignore_index=-1)
+
+
+def train_step(ST, net, opt, coords, feats, labels, reducer=None, st=None, criterion=_aten_criterion):
     if st is None:
         st = ST(feats, coords)                               # pl_BaselineTrainer.py:300
     out, _ = net(st)                                         # res16unet.py:196
-    loss = torch.nn.functional.cross_entropy(out.F.float(), labels, ignore_index=-1)   # :350
+    loss = criterion(out.F, labels)                          # :350  CrossEntropyLoss(ignore_index)
     opt.zero_grad(set_to_none=True)
     loss.backward()
     if reducer is not None:
@@ -188,20 +192,25 @@ def run_engine(args, rank, world, local_rank):
     # Every step stages the NEXT step's batch (copies + coordinate/kernel maps) on a side stream while it runs
     # (languagegroundedsemseg_b200/prefetch.py); the map build is still done once per step, inside the timed region.
     from languagegroundedsemseg_b200.prefetch import SparseBatchPrefetcher
-    pf = (SparseBatchPrefetcher(dev, fdtype, threaded=os.environ.get("LGS_STAGE_THREAD", "1") != "0")
+    pf = (SparseBatchPrefetcher(dev, fdtype, threaded=os.environ.get("LGS_STAGE_THREAD", "0") != "0",
+                                high_priority=os.environ.get("LGS_STAGE_PRIORITY", "1") != "0")
           if not args.no_prefetch else None)
     tickets = {}
+
+    from languagegroundedsemseg_b200 import losses as lgs_losses
+    # the engine's fused softmax cross-entropy (lgs_seg_ce: one pass over the logits) unless LGS_ATEN_CE=1
+    crit = _aten_criterion if os.environ.get("LGS_ATEN_CE") else (lambda x, y: lgs_losses.cross_entropy(x, y, ignore_index=-1))
 
     def staged_step(key, src):
         flush.fill_(0.0)
         if pf is None:
             c, f, lab = (t.to(dev, non_blocking=True) for t in src)
-            return train_step(E.SparseTensor, model, opt, c, f.to(fdtype), lab, reducer)
+            return train_step(E.SparseTensor, model, opt, c, f.to(fdtype), lab, reducer, criterion=crit)
         if key not in tickets:
             tickets[key] = pf.stage(*src)
         st, lab = pf.get(tickets[key])
         tickets[key] = pf.stage(*src)                        # next step's batch, overlapped with this step
-        return train_step(None, model, opt, None, None, lab, reducer, st=st)
+        return train_step(None, model, opt, None, None, lab, reducer, st=st, criterion=crit)
 
     def resident_step():
         return staged_step("resident", (d_coords, d_feats, d_labels))
@@ -373,7 +382,7 @@ def run_engine(args, rank, world, local_rank):
                    "l2": "256 MB buffer written between steps (L2 flush); per-step activations >> 126 MB L2",
                    "parallelism": f"dp{world}" + (" (one scene per rank, one flat NCCL gradient all-reduce per step)" if world > 1 else ""),
                    "step": "coordinate+kernel maps" + ("" if args.no_prefetch else " (staged on a side stream during the previous step)")
-                           + ", fwd, CE loss, bwd, SGD"},
+                           + ", fwd, CE loss (fused lgs_seg_ce), bwd, SGD"},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": e2e_state["last"],
                 "how": "pinned host coords/feats/labels -> H2D every step (staged on a side stream one step ahead), "

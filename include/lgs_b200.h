@@ -142,13 +142,28 @@ int lgs_conv_wgrad(const void* d_in, int64_t n_in, int32_t c_in,
  *        updated in place with `momentum` (biased variance normalises, unbiased variance feeds the running estimate).
  *   bwd: dy = dz * (z > 0)?;  dx (BatchNorm backward through the batch statistics), d_residual = dy (may be NULL),
  *        dgamma, dbeta.   d_scratch: 16c doubles (8 interleaved copies of the 2c column sums).
+ *   d_scratch_next == NULL: the call clears d_scratch itself (one memset node).  d_scratch_next != NULL (16384 doubles):
+ *   the caller guarantees d_scratch is all zero on entry and the call leaves d_scratch_next all zero on exit — callers
+ *   alternate two scratch halves per stream, so a chain of BatchNorm calls needs no memset nodes at all.
+ *   d_num_batches_tracked (int64, may be NULL) is incremented by the forward kernel (nn.BatchNorm1d bookkeeping).
  * --------------------------------------------------------------------------------------------------------- */
 int lgs_bn_fwd(const float* d_x, const float* d_residual, int64_t n, int32_t c, const float* d_gamma, const float* d_beta,
                float eps, float momentum, int32_t relu, float* d_running_mean, float* d_running_var, float* d_z,
-               float* d_save_mean, float* d_save_invstd, double* d_scratch, void* stream);
+               float* d_save_mean, float* d_save_invstd, double* d_scratch, double* d_scratch_next,
+               int64_t* d_num_batches_tracked, void* stream);
 int lgs_bn_bwd(const float* d_x, const float* d_z, const float* d_dz, int64_t n, int32_t c, const float* d_gamma,
                const float* d_save_mean, const float* d_save_invstd, int32_t relu, float* d_dx, float* d_dresidual,
-               float* d_dgamma, float* d_dbeta, double* d_scratch, void* stream);
+               float* d_dgamma, float* d_dbeta, double* d_scratch, double* d_scratch_next, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused softmax cross-entropy over per-point class logits [n,c] fp32 (c % 4 == 0, c <= 1024), mean over the points
+ * whose label != ignore_label; forward and d loss / d logits in one pass (two launches, no memset).
+ *   Replaces nn.CrossEntropyLoss(ignore_index=...) at lib/train_test/pl_BaselineTrainer.py:343,350 (five ATen passes over
+ *   the logit matrix).  d_ws: 4 doubles of workspace; d_loss: one float; d_grad_logits [n,c] may be NULL (evaluation).
+ * --------------------------------------------------------------------------------------------------------- */
+int lgs_seg_ce_supported(int32_t c);
+int lgs_seg_ce(const float* d_logits, int64_t n, int32_t c, const int64_t* d_labels, int64_t ignore_label,
+               double* d_ws, float* d_loss, float* d_grad_logits, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * CLIP text-anchor loss.   Replaces lib/losses/ContrastiveLanguageLoss.py:224-237 (+ feat_dist :206-222) and

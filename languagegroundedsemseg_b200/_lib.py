@@ -30,8 +30,10 @@ SIGNATURES = {
     "lgs_weight_prep_batch": (C.c_int, [_p, _i32, _i64, _i32, _i32, _p]),
     "lgs_conv_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i32, _p, _i64, _i32, _p, _p, _i32, _i32, _p]),
     "lgs_conv_wgrad": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _p, _i32, _p, _i32, _i32, _p]),
-    "lgs_bn_fwd": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _f32, _f32, _i32, _p, _p, _p, _p, _p, _p, _p]),
-    "lgs_bn_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p]),
+    "lgs_bn_fwd": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _f32, _f32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "lgs_bn_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "lgs_seg_ce_supported": (C.c_int, [_i32]),
+    "lgs_seg_ce": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _p, _p]),
     "lgs_clip_ce": (C.c_int, [_p, _i64, _i32, _p, _i32, _p, _i64, _p, _p, _p, _p, _p]),
     "lgs_clip_ce_tc_supported": (C.c_int, [_i32, _i32]),
     "lgs_clip_ce_tc_ws_elems": (_i64, [_i32, _i32]),

@@ -18,6 +18,7 @@ constexpr int BN_TX = 32;     // channels per block (x): one warp reads 128 cont
 constexpr int BN_TY = 8;      // row lanes per block (y)
 constexpr int BN_ROWS = 256;  // rows per block
 constexpr int BN_COPIES = 8;  // interleaved copies of the fp64 accumulators (block b adds into copy b % 8): less contention
+constexpr int BN_SCRATCH_DOUBLES = 2 * BN_COPIES * 1024;   // one accumulator scratch: [BN_COPIES][2 * c], c <= 1024
 
 __device__ __forceinline__ void bn_block_reduce(float a, float b, int ch, int c, double* sums) {
   __shared__ float s1[BN_TY][BN_TX + 1], s2[BN_TY][BN_TX + 1];
@@ -154,7 +155,8 @@ __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, int64_t n, int c,
                 const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
                 float eps, int relu, float* __restrict__ z, float* __restrict__ save_mean, float* __restrict__ save_invstd,
-                float* running_mean, float* running_var, float momentum) {
+                float* running_mean, float* running_var, float momentum, long long* num_batches_tracked,
+                double* __restrict__ zero_next) {
   extern __shared__ float sh[];   // scale[c], shift[c]
   float* scale = sh;
   float* shift = sh + c;
@@ -182,6 +184,11 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, int6
       }
     }
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  // the other half of the caller's accumulator scratch is cleared here for the NEXT BatchNorm launch on this stream
+  // (its previous readers finished before this kernel started), so no memset node is needed per call
+  if (zero_next)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < BN_SCRATCH_DOUBLES; i += gridDim.x * blockDim.x) zero_next[i] = 0.0;
   __syncthreads();
   const int64_t total4 = (n * int64_t(c)) >> 2;   // c % 4 == 0 (checked by the caller)
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total4; i += int64_t(gridDim.x) * blockDim.x) {
@@ -239,7 +246,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ z, const float* __restrict__ dz, int64_t n, int c,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const double* __restrict__ sums, int relu, float* __restrict__ dx, float* __restrict__ dres,
-                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, double* __restrict__ zero_next) {
   extern __shared__ float sh[];   // k1[c] = gamma*invstd, k2[c] = mean(dy), k3[c] = mean(dy*xhat), m[c], is[c]
   float* k1 = sh;
   float* k2 = sh + c;
@@ -264,6 +271,8 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ z, co
       if (dbeta) dbeta[ch] = float(s1);
     }
   }
+  if (zero_next)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < BN_SCRATCH_DOUBLES; i += gridDim.x * blockDim.x) zero_next[i] = 0.0;
   __syncthreads();
   const int64_t total4 = (n * int64_t(c)) >> 2;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total4; i += int64_t(gridDim.x) * blockDim.x) {
@@ -303,11 +312,13 @@ extern "C" {
 
 int lgs_bn_fwd(const float* d_x, const float* d_residual, int64_t n, int32_t c, const float* d_gamma, const float* d_beta,
                float eps, float momentum, int32_t relu, float* d_running_mean, float* d_running_var, float* d_z,
-               float* d_save_mean, float* d_save_invstd, double* d_scratch /*[16c]*/, void* stream_) {
+               float* d_save_mean, float* d_save_invstd, double* d_scratch /*[16c]*/, double* d_scratch_next /*[16384] or NULL*/,
+               int64_t* d_num_batches_tracked, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n < 1 || c < 4 || (c & 3) || c > 1024) return fail(LGS_E_UNSUPPORTED, "lgs_bn_fwd: n=%lld c=%d (need c %% 4 == 0, c <= 1024)", (long long)n, c);
   if (!d_x || !d_z || !d_save_mean || !d_save_invstd || !d_scratch) return fail(LGS_E_INVALID, "lgs_bn_fwd: null pointer");
-  LGS_CUDA(cudaMemsetAsync(d_scratch, 0, size_t(BN_COPIES) * 2 * c * sizeof(double), stream));
+  // with d_scratch_next the caller guarantees d_scratch is already zero (cleared by the previous call's apply kernel)
+  if (!d_scratch_next) LGS_CUDA(cudaMemsetAsync(d_scratch, 0, size_t(BN_COPIES) * 2 * c * sizeof(double), stream));
   const dim3 grid{unsigned((c + BN_TX - 1) / BN_TX), unsigned(cdiv(n, BN_ROWS)), 1u}, block{BN_TX, BN_TY, 1u};
   static const int unroll = getenv("LGS_BN_UNROLL") ? atoi(getenv("LGS_BN_UNROLL")) : 4;
   if (bn_use_vec(d_x, nullptr, nullptr, c)) {
@@ -323,18 +334,20 @@ int lgs_bn_fwd(const float* d_x, const float* d_residual, int64_t n, int32_t c, 
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   LGS_LAUNCH(bn_apply_kernel, blocks, 256, size_t(2 * c) * sizeof(float), stream, d_x, d_residual, n, c, d_scratch, d_gamma, d_beta,
-             eps, relu, d_z, d_save_mean, d_save_invstd, d_running_mean, d_running_var, momentum);
+             eps, relu, d_z, d_save_mean, d_save_invstd, d_running_mean, d_running_var, momentum,
+             reinterpret_cast<long long*>(d_num_batches_tracked), d_scratch_next);
   return LGS_OK;
 }
 
 int lgs_bn_bwd(const float* d_x, const float* d_z, const float* d_dz, int64_t n, int32_t c, const float* d_gamma,
                const float* d_save_mean, const float* d_save_invstd, int32_t relu, float* d_dx, float* d_dresidual,
-               float* d_dgamma, float* d_dbeta, double* d_scratch /*[16c]*/, void* stream_) {
+               float* d_dgamma, float* d_dbeta, double* d_scratch /*[16c]*/, double* d_scratch_next /*[16384] or NULL*/,
+               void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n < 1 || c < 4 || (c & 3) || c > 1024) return fail(LGS_E_UNSUPPORTED, "lgs_bn_bwd: n=%lld c=%d", (long long)n, c);
   if (!d_x || !d_dz || !d_dx || !d_save_mean || !d_save_invstd || !d_scratch || (relu && !d_z))
     return fail(LGS_E_INVALID, "lgs_bn_bwd: null pointer");
-  LGS_CUDA(cudaMemsetAsync(d_scratch, 0, size_t(BN_COPIES) * 2 * c * sizeof(double), stream));
+  if (!d_scratch_next) LGS_CUDA(cudaMemsetAsync(d_scratch, 0, size_t(BN_COPIES) * 2 * c * sizeof(double), stream));
   const dim3 grid{unsigned((c + BN_TX - 1) / BN_TX), unsigned(cdiv(n, BN_ROWS)), 1u}, block{BN_TX, BN_TY, 1u};
   static const int unroll = getenv("LGS_BN_UNROLL") ? atoi(getenv("LGS_BN_UNROLL")) : 4;
   if (bn_use_vec(d_x, relu ? d_z : nullptr, d_dz, c) && !(reinterpret_cast<uintptr_t>(d_save_mean) & 15) &&
@@ -352,7 +365,7 @@ int lgs_bn_bwd(const float* d_x, const float* d_z, const float* d_dz, int64_t n,
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   LGS_LAUNCH(bn_bwd_apply_kernel, blocks, 256, size_t(5 * c) * sizeof(float), stream, d_x, d_z, d_dz, n, c, d_save_mean,
-             d_save_invstd, d_gamma, d_scratch, relu, d_dx, d_dresidual, d_dgamma, d_dbeta);
+             d_save_invstd, d_gamma, d_scratch, relu, d_dx, d_dresidual, d_dgamma, d_dbeta, d_scratch_next);
   return LGS_OK;
 }
 

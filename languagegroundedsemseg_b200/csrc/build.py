@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["coords.cu", "conv_simt.cu", "conv_tc.cu", "clip_loss.cu", "clip_loss_tc.cu", "bn_fused.cu", "api.cu"]
+SOURCES = ["coords.cu", "conv_simt.cu", "conv_tc.cu", "clip_loss.cu", "clip_loss_tc.cu", "bn_fused.cu", "seg_ce.cu", "api.cu"]
 LIB = os.path.join(HERE, "liblgs_b200.so")
 HEADERS = ["common.cuh", "tcgen05.cuh", os.path.join("..", "..", "include", "lgs_b200.h")]
 

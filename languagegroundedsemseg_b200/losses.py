@@ -93,6 +93,48 @@ class ContrastiveLanguageCELoss(nn.Module):
         return loss, torch.zeros(1), loss   # same 3-tuple as the reference (:239)
 
 
+class _SegCEFn(torch.autograd.Function):
+    """mean softmax cross-entropy over the non-ignored points + its gradient in one pass (lgs_seg_ce)"""
+
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index):
+        lib = _lib.load()
+        n, c = logits.shape
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        ws = torch.empty(4, dtype=torch.float64, device=logits.device)
+        g = torch.empty_like(logits) if ctx.needs_input_grad[0] else None
+        _lib.check(lib.lgs_seg_ce(_lib.ptr(logits), n, c, _lib.ptr(labels), int(ignore_index), _lib.ptr(ws),
+                                  _lib.ptr(loss), _lib.ptr(g), _stream()))
+        ctx.save_for_backward(g)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        (g,) = ctx.saved_tensors
+        return (g.mul_(gloss) if g is not None else None), None, None     # g is this node's own buffer
+
+
+def cross_entropy(input, target, ignore_index=-100):
+    """`nn.CrossEntropyLoss(ignore_index=...)(soutput.F, target)` of lib/train_test/pl_BaselineTrainer.py:343,350
+    (criterion from loss_by_name, :96; reduction 'mean') as one fused pass over the logits.  Shapes the kernel does not
+    take (class count not a multiple of 4 or above 1024, non-fp32 logits) use ATen's cross_entropy on the same device."""
+    if (input.is_cuda and input.dim() == 2 and input.dtype is torch.float32 and input.shape[0] > 0
+            and _lib.load().lgs_seg_ce_supported(input.shape[1])):
+        return _SegCEFn.apply(input.contiguous(), target.long().contiguous(), ignore_index)
+    return F.cross_entropy(input.float(), target.long(), ignore_index=ignore_index)
+
+
+class CrossEntropyLoss(nn.Module):
+    """drop-in for the `nn.CrossEntropyLoss(ignore_index=config.ignore_label)` the reference trains with"""
+
+    def __init__(self, ignore_index=-100):
+        super().__init__()
+        self.ignore_index = ignore_index
+
+    def forward(self, input, target):
+        return cross_entropy(input, target, self.ignore_index)
+
+
 class _ClipHingeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feats, anchors_n, labels, neg_ids, ignore_label, pos_thresh, neg_thresh, neg_weight):

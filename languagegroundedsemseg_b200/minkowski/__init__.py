@@ -133,15 +133,36 @@ def set_batched_weight_prep(flag: bool):
 
 
 _bn_scratch = {}
+_BN_SCRATCH_DOUBLES = 16 * 1024
+
+
+class _Scratch:
+    """fp64 accumulator scratch of the BatchNorm kernels, one per (device, stream): two zero-initialised halves used
+    alternately — every lgs_bn_fwd / lgs_bn_bwd call accumulates into the current half and clears the other one for the
+    next call on that stream (launches on one stream are ordered), so no memset node is issued per BatchNorm."""
+    __slots__ = ("buf", "cur")
+
+    def __init__(self, device):
+        self.buf = torch.zeros((2, _BN_SCRATCH_DOUBLES), dtype=torch.float64, device=device)
+        self.cur = 0
+
+    def pair(self):
+        """(accumulators, half to clear) as c_void_p"""
+        a, b = self.buf[self.cur], self.buf[1 - self.cur]
+        return ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr())
+
+    def done(self, ok):
+        if ok:
+            self.cur = 1 - self.cur
+        else:                    # a failed call may have left partial sums behind
+            self.buf.zero_()
 
 
 def _scratch64(dev_index):
-    """fp64 accumulator scratch of the BatchNorm kernels: one persistent buffer per (device, stream) — launches on one
-    stream are ordered, so consecutive layers can share it."""
     key = (dev_index, torch._C._cuda_getCurrentRawStream(dev_index))
     t = _bn_scratch.get(key)
     if t is None:
-        t = _bn_scratch[key] = torch.empty(16 * 1024, dtype=torch.float64, device=torch.device("cuda", dev_index))
+        t = _bn_scratch[key] = _Scratch(torch.device("cuda", dev_index))
     return t
 
 
@@ -573,11 +594,14 @@ def _bn_fwd_impl(x, res, gamma, beta, bn, relu, update_running):
     stats = torch.empty((2, c), dtype=torch.float32, device=x.device)       # save_mean, save_invstd
     rm = bn.running_mean if update_running else None
     rv = bn.running_var if update_running else None
-    _lib.check(lib.lgs_bn_fwd(_lib.ptr(x), _lib.ptr(res), n, c, _lib.ptr(gamma), _lib.ptr(beta), float(bn.eps),
-                              float(bn.momentum), 1 if relu else 0, _lib.ptr(rm), _lib.ptr(rv), _lib.ptr(z),
-                              _lib.ptr(stats[0]), _lib.ptr(stats[1]), _lib.ptr(_scratch64(x.device.index)), _stream()))
-    if update_running:
-        bn.num_batches_tracked.add_(1)
+    sc = _scratch64(x.device.index)
+    acc, nxt = sc.pair()
+    rc = lib.lgs_bn_fwd(_lib.ptr(x), _lib.ptr(res), n, c, _lib.ptr(gamma), _lib.ptr(beta), float(bn.eps),
+                        float(bn.momentum), 1 if relu else 0, _lib.ptr(rm), _lib.ptr(rv), _lib.ptr(z),
+                        ctypes.c_void_p(stats.data_ptr()), ctypes.c_void_p(stats.data_ptr() + 4 * c), acc, nxt,
+                        _lib.ptr(bn.num_batches_tracked) if update_running else None, _stream())
+    sc.done(rc == _lib.OK)
+    _lib.check(rc)
     return x, z, stats
 
 
@@ -589,9 +613,14 @@ def _bn_bwd_impl(x, z, gamma, stats, dz, relu, need_dres):
     dx = torch.empty_like(x)
     dres = torch.empty_like(x) if need_dres else None
     dgb = torch.empty((2, c), dtype=torch.float32, device=x.device)
-    _lib.check(lib.lgs_bn_bwd(_lib.ptr(x), _lib.ptr(z), _lib.ptr(dz), n, c, _lib.ptr(gamma), _lib.ptr(stats[0]),
-                              _lib.ptr(stats[1]), 1 if relu else 0, _lib.ptr(dx), _lib.ptr(dres), _lib.ptr(dgb[0]),
-                              _lib.ptr(dgb[1]), _lib.ptr(_scratch64(x.device.index)), _stream()))
+    sc = _scratch64(x.device.index)
+    acc, nxt = sc.pair()
+    sp, gp = stats.data_ptr(), dgb.data_ptr()
+    rc = lib.lgs_bn_bwd(_lib.ptr(x), _lib.ptr(z), _lib.ptr(dz), n, c, _lib.ptr(gamma), ctypes.c_void_p(sp),
+                        ctypes.c_void_p(sp + 4 * c), 1 if relu else 0, _lib.ptr(dx), _lib.ptr(dres), ctypes.c_void_p(gp),
+                        ctypes.c_void_p(gp + 4 * c), acc, nxt, _stream())
+    sc.done(rc == _lib.OK)
+    _lib.check(rc)
     return dx, dres, dgb[0], dgb[1]
 
 
@@ -707,8 +736,9 @@ class _WeightPrep:
             entries.append((m, w, K, c_in, c_out, bufs[0], bufs[1]))
         if not entries:
             return
+        # shapes belong in the key: a new layer's tensors can land on a dead layer's addresses
         key = tuple((e[1].data_ptr(), e[5].data_ptr() if e[5] is not None else 0,
-                     e[6].data_ptr() if e[6] is not None else 0) for e in entries)
+                     e[6].data_ptr() if e[6] is not None else 0, e[2], e[3], e[4]) for e in entries)
         cached = self.desc.get((device, dt, nsplit))
         if cached is None or cached[0] != key:
             rows, tile0 = [], 0
@@ -749,9 +779,15 @@ def _conv_fwd_impl(feats, weight, bias, km, algo, need_dgrad, module=None):
     n_out = km.n_out if km is not None else n_in
     out = torch.empty((n_out, c_out), dtype=feats.dtype, device=feats.device)
     b32 = bias.detach().float().contiguous().view(-1) if bias is not None else None
-    w32 = w3.detach()
-    if w32.dtype is not torch.float32 or not w32.is_contiguous():
-        w32 = w32.float().contiguous()
+    w32 = None
+
+    def weights32():
+        w = w3.detach()
+        if w.dtype is not torch.float32 or not w.is_contiguous():
+            w = w.float().contiguous()
+        if padded:
+            w = torch.nn.functional.pad(w, (0, 0, 0, c_in - c_in_true))
+        return w
     # A tiny channel count (the 3 colour channels of conv0p1s1) is zero-padded to a 16-byte row so that the layer
     # takes the tensor-core kernels; the padded weight rows are zero and the padded gradients are dropped.
     c_in_true = c_in
@@ -760,7 +796,6 @@ def _conv_fwd_impl(feats, weight, bias, km, algo, need_dgrad, module=None):
     if padded:
         c_in = -(-row_bytes // 16) * 16 // feats.element_size()
         feats = torch.nn.functional.pad(feats, (0, c_in - c_in_true))
-        w32 = torch.nn.functional.pad(w32, (0, 0, 0, c_in - c_in_true))
     # tensor-core operand forms of the weights; a direction the TC kernels do not take (e.g. c_in = 3) runs on the
     # exact SIMT kernel with the parameter itself
     fwd_tc = algo != _lib.ALGO_SIMT and _tc_supported(lib, c_in, c_out, dt)
@@ -779,19 +814,21 @@ def _conv_fwd_impl(feats, weight, bias, km, algo, need_dgrad, module=None):
                 w_fwd = torch.empty((nsplit, K, c_out, c_in), dtype=feats.dtype, device=feats.device)
             if bwd_tc:
                 w_bwd = torch.empty((nsplit, K, c_in, c_out), dtype=feats.dtype, device=feats.device)
+            w32 = weights32()
             _lib.check(lib.lgs_weight_prep(_lib.ptr(w32), K, c_in, c_out, nsplit, _lib.ptr(w_fwd), _lib.ptr(w_bwd), dt,
                                            _stream()))
     tc_layout = _lib.W_KNC_SPLIT if nsplit == 2 else _lib.W_KNC
     if fwd_tc:
         wf, layout, a = w_fwd, tc_layout, algo
     else:
+        w32 = weights32() if w32 is None else w32
         wf, layout, a = w32.to(feats.dtype), _lib.W_KCN, _lib.ALGO_SIMT
     with _Timed("fwd", K, c_in, c_out, n_in, n_out, km, feats.dtype):
         _lib.check(lib.lgs_conv_fwd(_lib.ptr(feats), n_in, c_in, _lib.ptr(wf), layout, K, c_out,
                                     _lib.ptr(km.fwd_table) if km is not None else None, n_out, 0, _lib.ptr(b32),
                                     _lib.ptr(out), dt, a, _stream()))
     if need_dgrad and not bwd_tc:
-        w_bwd = w32.to(feats.dtype)                           # [K, c_in, c_out] read as LGS_W_KNC by the SIMT dgrad
+        w_bwd = (weights32() if w32 is None else w32).to(feats.dtype)                           # [K, c_in, c_out] read as LGS_W_KNC by the SIMT dgrad
     m = _ConvMeta()
     m.km, m.algo, m.bwd_tc, m.tc_layout = km, algo, bwd_tc, tc_layout
     m.dims, m.w_shape, m.w_dtype, m.has_bias = (K, c_in, c_out), weight.shape, weight.dtype, bias is not None

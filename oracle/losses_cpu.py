@@ -26,6 +26,12 @@ def clip_ce_loss(feats, labels, anchors, ignore_label=-1, reduction="mean"):
                            reduction=reduction)
 
 
+def seg_ce_loss(logits, labels, ignore_label=-1):
+    """nn.CrossEntropyLoss(ignore_index=...) on the class logits (lib/train_test/pl_BaselineTrainer.py:343,350), evaluated
+    in float64 so that it can referee fp32 implementations; the formula IS torch's, so this one is pinned by construction."""
+    return F.cross_entropy(logits.double(), labels.long(), ignore_index=ignore_label)
+
+
 def clip_hinge_loss(feats, labels, anchors, neg_ids, pos_thresh=0.0, neg_thresh=0.6, neg_weight=1.0,
                     ignore_label=-1, reduction="mean"):
     """neg_ids: [N, k] anchor ids of the sampled negatives (ignored rows may hold anything valid)."""

@@ -59,7 +59,8 @@ def install(setattr_fn):
     stub = StubLib()
     setattr_fn(_lib, "load", lambda: stub)
     setattr_fn(E, "_stream", lambda: None)
-    setattr_fn(E, "_scratch64", lambda idx: torch.empty(16 * 1024, dtype=torch.float64))
+    scratch = E._Scratch(torch.device("cpu"))
+    setattr_fn(E, "_scratch64", lambda idx: scratch)
     setattr_fn(E, "_side_stream", lambda idx: (FakeStream(), FakeEvent(), FakeEvent()))
     setattr_fn(E, "_cur_stream_obj", lambda idx: FakeStream())
     return stub

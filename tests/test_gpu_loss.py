@@ -143,3 +143,47 @@ def test_clip_ce_tc_rejects_unsupported_shapes(lib):
     loss, _ = losses.clip_ce(F_, y, A)
     S = torch.nn.functional.normalize(F_, dim=1) @ torch.nn.functional.normalize(A, dim=1).t()
     assert rel_err(loss, torch.nn.functional.cross_entropy(S, y, reduction="none")) < 1e-4
+
+
+@pytest.mark.parametrize("n,c,ignored", [(1, 200, 0.0), (7, 20, 0.3), (5000, 200, 0.1), (4097, 1024, 0.5), (300, 4, 0.0),
+                                          (64, 200, 1.0)])
+def test_seg_cross_entropy_vs_oracle(lib, n, c, ignored):
+    """fused softmax cross-entropy (lgs_seg_ce) = nn.CrossEntropyLoss(ignore_index=-1): loss and d loss / d logits
+    against the float64 oracle, including rows with large logits, all-ignored input and a scaled upstream gradient"""
+    from languagegroundedsemseg_b200 import losses
+    from oracle import losses_cpu
+    torch.manual_seed(n + c)
+    x = (torch.randn(n, c) * 4).requires_grad_(True)
+    x.data[0, : min(c, 3)] += 60.0                       # needs the max-subtraction
+    y = torch.randint(0, c, (n,))
+    y[torch.rand(n) < ignored] = -1
+    ref = losses_cpu.seg_ce_loss(x, y, -1)
+    if ignored < 1.0:
+        (ref * 0.5).backward()
+    xg = x.detach().cuda().requires_grad_(True)
+    out = losses.cross_entropy(xg, y.cuda(), ignore_index=-1)
+    if ignored == 1.0:
+        assert torch.isnan(out).item() == torch.isnan(ref).item()
+        return
+    (out * 0.5).backward()
+    assert abs(out.item() - ref.item()) < 5e-6 * max(1.0, abs(ref.item()))
+    assert rel_err(xg.grad.cpu(), x.grad.float()) < 2e-5
+    assert torch.equal(xg.grad[y.cuda() == -1], torch.zeros_like(xg.grad[y.cuda() == -1]))
+
+
+def test_seg_cross_entropy_full_size_and_fallback(lib):
+    """BASELINE config-2 size (150 K points x 200 classes) vs ATen on the same device; class counts outside the kernel's
+    envelope take ATen's path"""
+    from languagegroundedsemseg_b200 import losses
+    torch.manual_seed(0)
+    x = torch.randn(150000, 200, device="cuda")
+    y = torch.randint(-1, 200, (150000,), device="cuda")
+    a = x.clone().requires_grad_(True)
+    b = x.clone().requires_grad_(True)
+    la = losses.CrossEntropyLoss(ignore_index=-1)(a, y)
+    lb = torch.nn.functional.cross_entropy(b, y, ignore_index=-1)
+    la.backward(), lb.backward()
+    assert abs(la.item() - lb.item()) < 1e-5 * lb.item() and rel_err(a.grad, b.grad) < 1e-4
+    z = torch.randn(50, 7, device="cuda", requires_grad=True)            # 7 classes: not a multiple of 4
+    t = torch.randint(0, 7, (50,), device="cuda")
+    assert torch.allclose(losses.cross_entropy(z, t), torch.nn.functional.cross_entropy(z, t))
