@@ -193,7 +193,7 @@ def run_engine(args, rank, world, local_rank):
     # (languagegroundedsemseg_b200/prefetch.py); the map build is still done once per step, inside the timed region.
     from languagegroundedsemseg_b200.prefetch import SparseBatchPrefetcher
     pf = (SparseBatchPrefetcher(dev, fdtype, threaded=os.environ.get("LGS_STAGE_THREAD", "0") != "0",
-                                high_priority=os.environ.get("LGS_STAGE_PRIORITY", "1") != "0")
+                                high_priority=os.environ.get("LGS_STAGE_PRIORITY", "0") != "0")
           if not args.no_prefetch else None)
     tickets = {}
 

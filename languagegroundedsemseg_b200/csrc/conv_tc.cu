@@ -1015,8 +1015,10 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
   int n_tiles = (c_pad + 255) / 256;
   p.n_tile = ((((c_pad + n_tiles - 1) / n_tiles) + 15) / 16) * 16;   // <= 256; the last slice may be narrower (544 = 192+192+160)
   int k_splits = 1;
-  if (m_tiles * n_tiles <= 74) {
-    int want = int(cdiv(148, m_tiles * n_tiles));
+  int split_target = 148;                          // CTAs to aim for when a map has fewer tiles than SMs
+  if (const char* e = getenv("LGS_TC_SPLIT_TARGET")) split_target = std::max(1, atoi(e));
+  if (m_tiles * n_tiles <= split_target / 2) {
+    int want = int(cdiv(split_target, m_tiles * n_tiles));
     if (dtype == LGS_F32 && K > 1) {
       k_splits = want < K ? want : K;
       want = int(cdiv(want, k_splits));

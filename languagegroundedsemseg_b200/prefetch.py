@@ -24,12 +24,13 @@ from . import minkowski as E
 
 class SparseBatchPrefetcher:
     """Building a coordinate manager blocks the host five times (each coordinate map's row count sizes the next buffers).
-    The staging stream has HIGH priority so that its tiny kernels are scheduled ahead of the training stream's queued
-    CTAs and those waits stay short.  `threaded=True` moves `stage` to a worker thread (the waits happen inside the C
+    `high_priority=True` gives the staging stream CUDA's high priority so that its tiny kernels are scheduled ahead of the
+    training stream's queued CTAs (staging call 2-4 ms -> 1.2 ms of host time), but the end-to-end step became erratic with
+    it (16.1-19.4 ms vs a steady 16.1 ms), hence off by default.  `threaded=True` moves `stage` to a worker thread (the waits happen inside the C
     library with the GIL released); measured neutral on a host-bound step (the worker's Python work contends for the
     GIL: forward issue 6.3 -> 9.3 ms), hence off by default."""
 
-    def __init__(self, device=None, feature_dtype=torch.float32, threaded=False, high_priority=True):
+    def __init__(self, device=None, feature_dtype=torch.float32, threaded=False, high_priority=False):
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.stream = torch.cuda.Stream(self.device, priority=-1 if high_priority else 0)
         self.feature_dtype = feature_dtype

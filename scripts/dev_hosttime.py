@@ -16,7 +16,7 @@ dev = torch.device("cuda", 0)
 dc, df, dl = torch.from_numpy(c).to(dev), torch.from_numpy(f).to(dev), torch.from_numpy(l).to(dev)
 net, opt = bench.build_net(None, dev, torch.float32)
 pf = SparseBatchPrefetcher(dev, torch.float32, threaded=os.environ.get("LGS_STAGE_THREAD", "0") != "0",
-                           high_priority=os.environ.get("LGS_STAGE_PRIORITY", "1") != "0")
+                           high_priority=os.environ.get("LGS_STAGE_PRIORITY", "0") != "0")
 ticket = pf.stage(dc, df, dl)
 acc = {}
 
