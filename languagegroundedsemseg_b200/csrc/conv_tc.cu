@@ -1015,7 +1015,9 @@ int conv_fwd_tc(const void* in, int64_t n_in, int c_in, const void* w_nk, int K,
   int n_tiles = (c_pad + 255) / 256;
   p.n_tile = ((((c_pad + n_tiles - 1) / n_tiles) + 15) / 16) * 16;   // <= 256; the last slice may be narrower (544 = 192+192+160)
   int k_splits = 1;
-  int split_target = 148;                          // CTAs to aim for when a map has fewer tiles than SMs
+  // CTAs to aim for when a map has fewer tiles than SMs: two of these CTAs fit on an SM (<= 100 KB of shared memory each),
+  // and 296 measured 5-15 % faster than 148 on the 8.5 K-row level (scripts/dev_small_layers.py), equal elsewhere
+  int split_target = 296;
   if (const char* e = getenv("LGS_TC_SPLIT_TARGET")) split_target = std::max(1, atoi(e));
   if (m_tiles * n_tiles <= split_target / 2) {
     int want = int(cdiv(split_target, m_tiles * n_tiles));

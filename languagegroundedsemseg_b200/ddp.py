@@ -55,6 +55,8 @@ class GradAllReducer:
         if self.world > 1:
             for p in self.params:
                 dist.broadcast(p.data, src)
+            from . import minkowski
+            minkowski.invalidate_weight_cache()     # `.data` writes do not bump the parameters' version counters
 
     def __call__(self):
         if self.world == 1:
