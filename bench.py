@@ -264,6 +264,24 @@ def run_engine(args, rank, world, local_rank):
             print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches)}))
         return None
 
+    # ---- e2e leg (right after the value leg, GPU warm; its own >= 3 warm-up steps; clocks sampled too) -------------
+    with ClockSampler(local_rank if rank == 0 else -1) as clk_e2e:
+        for _ in range(max(3, args.warmup)):
+            e2e_step()
+        e2e_drain()
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t_e0 = time.time()
+        t0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e2e_drain()                     # the last step's loss is read inside the timed region too
+        t1.record()
+        barrier()
+        clk_e2e.window = (t_e0, time.time())
+    ms_e2e = t0.elapsed_time(t1)
+
     # ---- per-launch CUDA-event timing of the engine's conv kernels (same process, same data, right after the timed
     # region; kept out of it because ~380 event records per step starve the launch queue and double the step time)
     PROF_STEPS = 2
@@ -272,20 +290,6 @@ def run_engine(args, rank, world, local_rank):
         resident_step()
     torch.cuda.synchronize()
     prof = E.profile_end() or []
-
-    # ---- e2e leg -----------------------------------------------------------------------------------------
-    e2e_step()
-    e2e_drain()
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e2e_drain()                     # the last step's loss is read inside the timed region too
-    t1.record()
-    barrier()
-    ms_e2e = t0.elapsed_time(t1)
 
     # ---- kernel-map build time (coordinate map + 4 strided maps + 9 kernel maps of one scene) -------------
     def build_maps():
@@ -384,7 +388,7 @@ def run_engine(args, rank, world, local_rank):
                    "step": "coordinate+kernel maps" + ("" if args.no_prefetch else " (staged on a side stream during the previous step)")
                            + ", fwd, CE loss (fused lgs_seg_ce), bwd, SGD"},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": e2e_state["last"],
+                "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": e2e_state["last"], "clocks": clk_e2e.summary(),
                 "how": "pinned host coords/feats/labels -> H2D every step (staged on a side stream one step ahead), "
                        "SparseTensor + fwd + loss + bwd + SGD through the facade, loss -> pinned host every step "
                        "(value consumed one step later)"},
