@@ -65,6 +65,8 @@ class ClockSampler:
                                           "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            import atexit
+            atexit.register(self._kill)          # never leave the poller behind, whatever happens to the run
         except Exception:
             self.proc = None
         return self
@@ -73,14 +75,19 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([time.time()] + [x.strip() for x in line.split(",")])
 
+    def _kill(self):
+        if self.proc and self.proc.poll() is None:
+            self.proc.terminate()
+
     def __exit__(self, *a):
-        if self.proc:
+        if self.proc and self.proc.poll() is None:
             time.sleep(0.25)
             self.proc.terminate()
             self.t.join(timeout=2)
 
-    def summary(self):
-        rows = [r[1:] for r in self.rows if self.window is None or self.window[0] <= r[0] <= self.window[1] + 0.25]
+    def summary(self, window=None):
+        window = window or self.window
+        rows = [r[1:] for r in self.rows if window is None or window[0] <= r[0] <= window[1] + 0.25]
         if not rows:                # region shorter than one polling period: the nearest samples
             rows = [r[1:] for r in self.rows[-2:]]
         rows = [r for r in rows if len(r) >= 7]
@@ -161,6 +168,11 @@ def run_engine(args, rank, world, local_rank):
     _lib.load()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # ONE nvidia-smi poller (rank 0 only: concurrent pollers slow the driver), started now — seconds before the first timed
+    # region — because its NVML start-up stalls CUDA calls for a few hundred ms; it then polls every 200 ms through both
+    # timed regions and each region reports the samples that fall inside it.
+    clk = ClockSampler(local_rank if rank == 0 else -1)
+    clk.__enter__()
     E.set_conv_algo(args.algo)
     fdtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
 
@@ -237,49 +249,46 @@ def run_engine(args, rank, world, local_rank):
             loss_evt[(i - 1) & 1].synchronize()
             e2e_state["last"] = float(loss_host[(i - 1) & 1])
 
-    # The nvidia-smi poller starts BEFORE the warm-up (its NVML start-up stalls the driver for tens of ms, which used to
-    # land inside the timed region); it keeps polling every 200 ms through the timed region and only those samples are
-    # reported.  One poller (rank 0): concurrent nvidia-smi loops slow the driver.
-    with ClockSampler(local_rank if rank == 0 else -1) as clk:
-        for _ in range(args.warmup):
-            resident_step()
-        barrier()
+    for _ in range(args.warmup):
+        resident_step()
+    barrier()
 
-        # ---- timed region: `value` ----------------------------------------------------------------------
-        l0 = _lib.launch_count()
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_w0 = time.time()
-        ev0.record()
-        for _ in range(args.steps):
-            loss = resident_step()
-        ev1.record()
-        barrier()
-        clk.window = (t_w0, time.time())
+    # ---- timed region: `value` --------------------------------------------------------------------------
+    l0 = _lib.launch_count()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_w0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        loss = resident_step()
+    ev1.record()
+    barrier()
+    clocks_value = clk.summary((t_w0, time.time()))
     ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - l0
     loss_val = float(loss.item())
     if args.profile_run:
+        clk.__exit__()
         if rank == 0:
             print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches)}))
         return None
 
-    # ---- e2e leg (right after the value leg, GPU warm; its own >= 3 warm-up steps; clocks sampled too) -------------
-    with ClockSampler(local_rank if rank == 0 else -1) as clk_e2e:
-        for _ in range(max(3, args.warmup)):
-            e2e_step()
-        e2e_drain()
-        barrier()
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        t_e0 = time.time()
-        t0.record()
-        for _ in range(args.steps):
-            e2e_step()
-        e2e_drain()                     # the last step's loss is read inside the timed region too
-        t1.record()
-        barrier()
-        clk_e2e.window = (t_e0, time.time())
+    # ---- e2e leg (right after the value leg, GPU warm; its own >= 3 warm-up steps; clocks sampled too) -----------
+    for _ in range(max(3, args.warmup)):
+        e2e_step()
+    e2e_drain()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t_e0 = time.time()
+    t0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e2e_drain()                     # the last step's loss is read inside the timed region too
+    t1.record()
+    barrier()
+    clocks_e2e = clk.summary((t_e0, time.time()))
+    clk.__exit__()
     ms_e2e = t0.elapsed_time(t1)
 
     # ---- per-launch CUDA-event timing of the engine's conv kernels (same process, same data, right after the timed
@@ -388,14 +397,14 @@ def run_engine(args, rank, world, local_rank):
                    "step": "coordinate+kernel maps" + ("" if args.no_prefetch else " (staged on a side stream during the previous step)")
                            + ", fwd, CE loss (fused lgs_seg_ce), bwd, SGD"},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": e2e_state["last"], "clocks": clk_e2e.summary(),
+                "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": e2e_state["last"], "clocks": clocks_e2e,
                 "how": "pinned host coords/feats/labels -> H2D every step (staged on a side stream one step ahead), "
                        "SparseTensor + fwd + loss + bwd + SGD through the facade, loss -> pinned host every step "
                        "(value consumed one step later)"},
         "gpu_launches": int(launches),
         "kernel_map_build_ms": round(kmap_ms, 3),
         "roofline": roofline,
-        "clocks": clk.summary(),
+        "clocks": clocks_value,
         "loss": round(loss_val, 5),
     }
     return res
