@@ -492,6 +492,8 @@ def main():
         return 0
 
     if world > 1:
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION/WARN/INFO) to stdout by default; stdout carries the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         from languagegroundedsemseg_b200 import ddp
         ddp.init_process_group("nccl")
     res = run_engine(args, rank, world, local_rank)
