@@ -274,7 +274,7 @@ def run_engine(args, rank, world, local_rank):
     if args.profile_run:
         clk.__exit__()
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches)}))
+            emit({"profile_run": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches)})
         return None
 
     # ---- e2e leg (right after the value leg, GPU warm; its own >= 3 warm-up steps; clocks sampled too) -----------
@@ -448,6 +448,28 @@ def cpu_model_name():
     return "unknown"
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result: keep a private duplicate of fd 1 for it and point fd 1 at stderr,
+    so that nothing else in the process (NCCL's version banner, library warnings written with printf) lands on stdout"""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -470,6 +492,7 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    claim_stdout()
 
     if args.impl == "reference":
         if rank != 0:
@@ -488,12 +511,10 @@ def main():
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     if world > 1:
-        # NCCL writes its version banner (NCCL_DEBUG=VERSION/WARN/INFO) to stdout by default; stdout carries the JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         from languagegroundedsemseg_b200 import ddp
         ddp.init_process_group("nccl")
     res = run_engine(args, rank, world, local_rank)
@@ -502,7 +523,7 @@ def main():
             cb, _, _ = cpu_arm(1, 0, args.cpu_sample_voxels)
             cb["cpu"] = cpu_model_name()
             res["cpu_baseline"] = cb
-        print(json.dumps(res), flush=True)
+        emit(res)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
