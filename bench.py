@@ -75,6 +75,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([time.time()] + [x.strip() for x in line.split(",")])
 
+    def wait_first_sample(self, timeout=15.0):
+        """block until the poller has printed its first row, i.e. its NVML start-up (1-3 s on an 8-GPU box) is over"""
+        t0 = time.time()
+        while self.proc is not None and self.proc.poll() is None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
     def _kill(self):
         if self.proc and self.proc.poll() is None:
             self.proc.terminate()
@@ -253,6 +259,7 @@ def run_engine(args, rank, world, local_rank):
     # stream, blocks handed over with record_stream) take several steps to stop growing, and a cudaMalloc inside the
     # timed region costs milliseconds (seen as a 19 ms outlier in one of four runs with 5 warm-up steps)
     warm_done = max(args.warmup, 10)
+    clk.wait_first_sample()             # the poller's start-up must not overlap a timed region
     for _ in range(warm_done):
         resident_step()
     barrier()
