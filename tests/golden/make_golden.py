@@ -9,6 +9,9 @@
                      sample, a few gradient norms.
   clip_ce.npz        reference lib/losses/ContrastiveLanguageLoss.py::ContrastiveLanguageCELoss outputs (a genuine
                      reference implementation: pins oracle/losses_cpu.py and the CUDA loss kernel).
+  clip_nets.npz      reference models/clip_models.py::Res16UNet34CR_Proj and ::Res16UNet34D (representation_only) driven
+                     through the oracle ME shim, with the reference's own ContrastiveLanguageCELoss on top (BASELINE
+                     configs 3 / 5 in small): per-point features, projected anchors, loss, two gradient norms.
   voxelize.npz       reference lib/voxelizer.py::Voxelizer.voxelize (affine + floor by the reference's numpy code;
                      de-duplication by the oracle's sparse_quantize).
 
@@ -108,6 +111,37 @@ def clip_ce():
     np.savez_compressed(os.path.join(HERE, "clip_ce.npz"), **out)
 
 
+def clip_nets():
+    sys.modules.setdefault("joblib", __import__("joblib"))
+    from lib.losses.ContrastiveLanguageLoss import ContrastiveLanguageCELoss
+    lcfg = types.SimpleNamespace(ignore_label=-1, num_negative_samples=3, contrast_neg_thresh=0.6,
+                                 contrast_pos_thresh=0.0, contrast_neg_weight=1.0,
+                                 instance_augmentation_color_aug_prob=0.0, scannet_path="/nonexistent",
+                                 projection_model_path="none", representation_distance_type="cos")
+    coords, feats, labels = scenes.synthetic_voxel_scene(seed=9, target_voxels=1500)
+    torch.manual_seed(1)
+    anchors = torch.nn.functional.normalize(torch.randn(200, 512), dim=1)
+    out = {"n": np.int64(coords.shape[0])}
+    for name in ("Res16UNet34CR_Proj", "Res16UNet34D"):
+        torch.manual_seed(42)
+        net = models.load_model(name)(3, 200, cfg)
+        net.train()
+        net.representation_only(True)
+        st = ME.SparseTensor(torch.from_numpy(feats), torch.from_numpy(coords))
+        if name.endswith("Proj"):
+            feat, anc = net(st, anchors)
+        else:
+            feat, anc = net(st), anchors
+        loss = ContrastiveLanguageCELoss(lcfg, 200, reduction="mean")(feat.F, torch.from_numpy(labels).long(), anc)[0]
+        loss.backward()
+        out.update({f"{name}_feat_rows": feat.F.detach()[::25].numpy(), f"{name}_loss": np.float64(loss.item()),
+                    f"{name}_anchor_rows": anc.detach()[::20].numpy(),
+                    f"{name}_g_conv0": np.float64(net.conv0p1s1.kernel.grad.norm().item()),
+                    f"{name}_g_block8": np.float64(net.block8[0].conv1.kernel.grad.norm().item())})
+        print("clip_nets", name, coords.shape[0], tuple(feat.F.shape), loss.item())
+    np.savez_compressed(os.path.join(HERE, "clip_nets.npz"), **out)
+
+
 def voxelize():
     from lib.voxelizer import Voxelizer
     rng = np.random.default_rng(5)
@@ -127,7 +161,7 @@ def voxelize():
 
 
 if __name__ == "__main__":
-    unet14a()
-    unet34c()
-    clip_ce()
-    voxelize()
+    only = sys.argv[1:]            # e.g. `make_golden.py clip_nets` regenerates one fixture
+    for fn in (unet14a, unet34c, clip_ce, clip_nets, voxelize):
+        if not only or fn.__name__ in only:
+            fn()

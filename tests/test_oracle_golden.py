@@ -62,6 +62,29 @@ def test_clip_ce_oracle_matches_reference_class(golden_dir):
         assert torch.all(loss[y == -1] == 0)
 
 
+def test_clip_pretraining_nets_match_reference_models(golden_dir):
+    """nets.py's CLIP pre-training topologies + the oracle loss vs the reference's own clip_models.py classes and its own
+    ContrastiveLanguageCELoss (BASELINE configs 3 / 5 in small)"""
+    g = np.load(os.path.join(golden_dir, "clip_nets.npz"))
+    coords, feats, labels = scenes.synthetic_voxel_scene(seed=9, target_voxels=1500)
+    assert coords.shape[0] == int(g["n"])
+    torch.manual_seed(1)
+    anchors = torch.nn.functional.normalize(torch.randn(200, 512), dim=1)
+    for name in ("Res16UNet34CR_Proj", "Res16UNet34D"):
+        torch.manual_seed(42)
+        net = nets.build_model(name, 3, 200, nets.DefaultConfig(), engine=me_cpu).train()
+        net.representation_only(True)
+        st = me_cpu.SparseTensor(torch.from_numpy(feats), torch.from_numpy(coords))
+        feat, anc = net(st, anchors) if name.endswith("Proj") else (net(st), anchors)
+        loss = losses_cpu.clip_ce_loss(feat.F, torch.from_numpy(labels), anc, ignore_label=-1, reduction="mean")
+        loss.backward()
+        assert abs(loss.item() - float(g[f"{name}_loss"])) < 1e-5
+        np.testing.assert_allclose(feat.F.detach()[::25].numpy(), g[f"{name}_feat_rows"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(anc.detach()[::20].numpy(), g[f"{name}_anchor_rows"], rtol=1e-5, atol=1e-6)
+        assert abs(net.conv0p1s1.kernel.grad.norm().item() - float(g[f"{name}_g_conv0"])) < 1e-3 * float(g[f"{name}_g_conv0"])
+        assert abs(net.block8[0].conv1.kernel.grad.norm().item() - float(g[f"{name}_g_block8"])) < 1e-3 * float(g[f"{name}_g_block8"])
+
+
 def test_voxelize_oracle_matches_reference_voxelizer(golden_dir):
     g = np.load(os.path.join(golden_dir, "voxelize.npz"))
     q, uidx, _ = voxelize_cpu.voxelize(g["pts"], g["M"])
