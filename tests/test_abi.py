@@ -47,3 +47,49 @@ def test_library_is_sm100a(lib):
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+_BINDING_PROBE = r'''
+import sys, ctypes
+sys.path.insert(0, ROOT)
+import torch
+from languagegroundedsemseg_b200 import _lib
+lib = _lib.load()
+x = torch.zeros(8)
+out = [_lib.binding()]
+calls = [
+    ("lgs_conv_fwd", (None, 10, 0, None, 0, 27, 8, None, 10, 0, None, None, 0, 0, None)),
+    ("lgs_conv_fwd", (_lib.ptr(x), 123456789012, 7, _lib.ptr(x), 0, 99, 8, None, -5, 0, None, None, 0, 0, None)),
+    ("lgs_conv_wgrad", (_lib.ptr(x), 5, 0, _lib.ptr(x), 5, 8, None, 27, _lib.ptr(x), 0, 1, None)),
+    ("lgs_bn_fwd", (_lib.ptr(x), None, 1000, 6, None, None, 1e-5, 0.1, 1, None, None, _lib.ptr(x), _lib.ptr(x), _lib.ptr(x),
+                    _lib.ptr(x), None, None, None)),
+    ("lgs_bn_bwd", (_lib.ptr(x), None, _lib.ptr(x), 10, 2048, None, _lib.ptr(x), _lib.ptr(x), 0, _lib.ptr(x), None, None, None,
+                    _lib.ptr(x), None, None)),
+    ("lgs_seg_ce", (_lib.ptr(x), 5, 7, _lib.ptr(x), -1, _lib.ptr(x), _lib.ptr(x), None, ctypes.c_void_p(0))),
+    ("lgs_weight_prep", (_lib.ptr(x), 27, 0, 8, 2, _lib.ptr(x), None, 0, None)),
+    ("lgs_weight_prep_batch", (None, 3, 10, 2, 0, None)),
+    ("lgs_kmap_build", (None, 10, None, None, 1024, 5, 1, 1, None, None, None)),
+    ("lgs_clip_ce", (None, 10, 96, None, 1000, None, -1, None, None, None, None, None)),
+]
+for name, args in calls:
+    rc = getattr(lib, name)(*args)
+    out.append((name, rc, lib.lgs_last_error().decode()))
+print(repr(out))
+'''
+
+
+def test_native_binding_matches_ctypes(lib):
+    """the generated CPython binding (csrc/_lgs_fast*.so, LGS_FAST_BIND=1) hands the C library the same argument values
+    as ctypes: identical return codes and identical error strings (which echo the integer arguments) on calls that stop
+    at argument validation — nothing here needs a GPU"""
+    import subprocess
+    import sys
+    res = {}
+    for mode in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", f"ROOT={ROOT!r}\n" + _BINDING_PROBE], capture_output=True, text=True,
+                           env=dict(os.environ, LGS_FAST_BIND=mode), timeout=300)
+        assert r.returncode == 0, r.stderr
+        res[mode] = eval(r.stdout.strip().splitlines()[-1])
+    assert res["0"][0] == "ctypes" and res["1"][0] == "native"
+    assert res["0"][1:] == res["1"][1:]
+    assert all(rc != 0 for _, rc, _ in res["0"][1:])
