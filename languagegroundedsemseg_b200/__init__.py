@@ -9,4 +9,10 @@ def install_as_minkowski(name="MinkowskiEngine"):
     return minkowski.install(name)
 
 
-__all__ = ["minkowski", "install_as_minkowski"]
+def load_reference_checkpoint(model, checkpoint, lenient=True, map_location="cpu"):
+    """Load a checkpoint written by the reference (lib/utils.py:48-70 / Lightning) into an engine network."""
+    from .checkpoint import load_reference_checkpoint as _load
+    return _load(model, checkpoint, lenient=lenient, map_location=map_location)
+
+
+__all__ = ["minkowski", "install_as_minkowski", "load_reference_checkpoint"]
