@@ -140,16 +140,17 @@ class _Scratch:
     """fp64 accumulator scratch of the BatchNorm kernels, one per (device, stream): two zero-initialised halves used
     alternately — every lgs_bn_fwd / lgs_bn_bwd call accumulates into the current half and clears the other one for the
     next call on that stream (launches on one stream are ordered), so no memset node is issued per BatchNorm."""
-    __slots__ = ("buf", "cur")
+    __slots__ = ("buf", "cur", "halves")
 
     def __init__(self, device):
         self.buf = torch.zeros((2, _BN_SCRATCH_DOUBLES), dtype=torch.float64, device=device)
+        base = self.buf.data_ptr()
+        self.halves = (ctypes.c_void_p(base), ctypes.c_void_p(base + 8 * _BN_SCRATCH_DOUBLES))
         self.cur = 0
 
     def pair(self):
         """(accumulators, half to clear) as c_void_p"""
-        a, b = self.buf[self.cur], self.buf[1 - self.cur]
-        return ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr())
+        return self.halves[self.cur], self.halves[1 - self.cur]
 
     def done(self, ok):
         if ok:
