@@ -12,6 +12,9 @@
   clip_nets.npz      reference models/clip_models.py::Res16UNet34CR_Proj and ::Res16UNet34D (representation_only) driven
                      through the oracle ME shim, with the reference's own ContrastiveLanguageCELoss on top (BASELINE
                      configs 3 / 5 in small): per-point features, projected anchors, loss, two gradient norms.
+  augment.npz        reference lib/transforms.py classes (ElasticDistortion, RandomDropout, RandomHorizontalFlip,
+                     ChromaticAutoContrast / Translation / Jitter composed as in lib/datasets/scannet.py) on seeded
+                     inputs with seeded python/numpy RNGs: pins languagegroundedsemseg_b200/augment.py.
   voxelize.npz       reference lib/voxelizer.py::Voxelizer.voxelize (affine + floor by the reference's numpy code;
                      de-duplication by the oracle's sparse_quantize).
 
@@ -142,6 +145,37 @@ def clip_nets():
     np.savez_compressed(os.path.join(HERE, "clip_nets.npz"), **out)
 
 
+AUG_SEEDS = (0, 4, 7)      # seed 4 and 7 exercise RandomDropout (5000 -> 4000 points at full size)
+
+
+def augment_pipeline(mod):
+    return mod.Compose([mod.ElasticDistortion([(4.0, 1.6), (16.0, 6.4)]), mod.RandomDropout(0.2),
+                        mod.RandomHorizontalFlip("z", False), mod.ChromaticAutoContrast(), mod.ChromaticTranslation(0.1),
+                        mod.ChromaticJitter(0.05)])
+
+
+def augment_inputs(n=1500):
+    rng = np.random.default_rng(0)
+    return ((rng.random((n, 3)) * np.array([300, 250, 120])).astype(np.float32),
+            (rng.random((n, 3)) * 255).astype(np.float32), rng.integers(0, 20, n).astype(np.int32))
+
+
+def augment():
+    import random
+    for m in ("matplotlib", "open3d"):          # imported at module level by lib/transforms.py, unused by these classes
+        sys.modules.setdefault(m, types.ModuleType(m))
+    import lib.transforms as RT
+    c0, f0, l0 = augment_inputs()
+    out = {}
+    for seed in AUG_SEEDS:
+        random.seed(seed)
+        np.random.seed(seed)
+        c, f, l = augment_pipeline(RT)(c0.copy(), f0.copy(), l0.copy())
+        out.update({f"s{seed}_coords": c, f"s{seed}_feats": f, f"s{seed}_labels": l})
+        print("augment", seed, c.shape)
+    np.savez_compressed(os.path.join(HERE, "augment.npz"), **out)
+
+
 def voxelize():
     from lib.voxelizer import Voxelizer
     rng = np.random.default_rng(5)
@@ -162,6 +196,6 @@ def voxelize():
 
 if __name__ == "__main__":
     only = sys.argv[1:]            # e.g. `make_golden.py clip_nets` regenerates one fixture
-    for fn in (unet14a, unet34c, clip_ce, clip_nets, voxelize):
+    for fn in (unet14a, unet34c, clip_ce, clip_nets, augment, voxelize):
         if not only or fn.__name__ in only:
             fn()
