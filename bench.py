@@ -374,11 +374,15 @@ def run_engine(args, rank, world, local_rank):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     shape_tag = f"conv K={dom_key[1]} {dom_key[2]}->{dom_key[3]} n_out={dom_key[5]} {args.algo} {args.dtype}"
+    traffic_src = None
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"K={dom_key[1]} {dom_key[2]}->{dom_key[3]} {args.algo} {args.dtype}")
+        t = json.load(open(tpath)).get(f"K={dom_key[1]} {dom_key[2]}->{dom_key[3]} {args.algo} {args.dtype}")
+        if t:
+            traffic, traffic_src = t["bytes"], t["source"]      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch
     roofline = {"bound": "hbm", "kernel": "conv_tc2_kernel (output-stationary gather -> tcgen05 GEMM, fwd and dgrad): " + shape_tag,
                 "achieved": round(achieved, 1), "peak": hbm_gbs, "unit": "GB/s", "frac": round(achieved / hbm_gbs, 4),
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(dom[1]), "avg_launch_ms": round(dom_ms, 4), "launches_per_step": dom[3] // PROF_STEPS,
                 "share_of_step": round((dom[0] / PROF_STEPS) / (ms / args.steps), 3),
                 "tflops": round(dom[2] / (dom_ms * 1e-3) / 1e12, 2),
