@@ -47,6 +47,13 @@ int lgs_version(void);
 const char* lgs_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t lgs_launch_count(void);
+
+/* Call recorder (host-side testing without a GPU).  Between lgs_trace_begin() and lgs_trace_end() the compute entry points
+ * (weight prep, conv fwd / wgrad, bn fwd / bwd, seg_ce, kmap build / transpose, clip losses) append one text line
+ * "name arg arg ..." each (pointers as %p) and return LGS_OK WITHOUT launching anything.  lgs_trace_end stops recording,
+ * copies the NUL-terminated text into buf if capacity allows, and returns the number of bytes needed.  Process-wide. */
+int lgs_trace_begin(void);
+int64_t lgs_trace_end(char* buf, int64_t capacity);
 /* 1 if the library was built with the tcgen05 path */
 int lgs_has_tc(void);
 

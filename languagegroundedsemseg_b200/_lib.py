@@ -18,6 +18,8 @@ SIGNATURES = {
     "lgs_version": (C.c_int, []),
     "lgs_last_error": (C.c_char_p, []),
     "lgs_launch_count": (C.c_uint64, []),
+    "lgs_trace_begin": (C.c_int, []),
+    "lgs_trace_end": (_i64, [C.c_char_p, _i64]),
     "lgs_has_tc": (C.c_int, []),
     "lgs_coord_limit": (_i32, []),
     "lgs_hash_capacity": (_i64, [_i64]),
@@ -116,3 +118,22 @@ def ptr(t):
 
 def launch_count():
     return int(load().lgs_launch_count())
+
+
+class trace:
+    """`with _lib.trace() as t: ...; t.lines` — record the compute entry points' calls instead of executing them
+    (include/lgs_b200.h: lgs_trace_begin / lgs_trace_end).  Needs no GPU."""
+
+    def __enter__(self):
+        load().lgs_trace_begin()
+        self.lines = []
+        return self
+
+    def __exit__(self, *a):
+        lib = load()
+        need = lib.lgs_trace_end(None, 0)
+        buf = C.create_string_buffer(int(need))
+        # recording is already off; the text stays until the next lgs_trace_begin
+        lib.lgs_trace_end(buf, need)
+        self.lines = buf.value.decode().splitlines()
+        return False

@@ -29,6 +29,7 @@ int lgs_conv_tc_supported(int32_t c_in, int32_t c_out, int32_t dtype) { return c
 
 int lgs_weight_prep(const float* d_weight, int32_t K, int32_t c_in, int32_t c_out, int32_t nsplit, void* d_fwd,
                     void* d_bwd, int32_t dtype, void* stream_) {
+  LGS_TRACE("lgs_weight_prep %p %d %d %d %d %p %p %d %p", (const void*)d_weight, (int)K, (int)c_in, (int)c_out, (int)nsplit, (const void*)d_fwd, (const void*)d_bwd, (int)dtype, (const void*)stream_);
   if (K < 1 || c_in < 1 || c_out < 1 || (nsplit != 1 && nsplit != 2) || !d_weight || (!d_fwd && !d_bwd))
     return fail(LGS_E_INVALID, "lgs_weight_prep: bad arguments");
   if (dtype != LGS_F32 && dtype != LGS_BF16) return fail(LGS_E_INVALID, "lgs_weight_prep: dtype %d", dtype);
@@ -37,6 +38,7 @@ int lgs_weight_prep(const float* d_weight, int32_t K, int32_t c_in, int32_t c_ou
 
 int lgs_weight_prep_batch(const int64_t* d_desc, int32_t n_layers, int64_t total_tiles, int32_t nsplit, int32_t dtype,
                           void* stream_) {
+  LGS_TRACE("lgs_weight_prep_batch %p %d %lld %d %d %p", (const void*)d_desc, (int)n_layers, (long long)total_tiles, (int)nsplit, (int)dtype, (const void*)stream_);
   if (n_layers < 0 || total_tiles < 0 || total_tiles >= (int64_t(1) << 31) || (nsplit != 1 && nsplit != 2) ||
       (n_layers > 0 && !d_desc))
     return fail(LGS_E_INVALID, "lgs_weight_prep_batch: bad arguments");
@@ -48,6 +50,7 @@ int lgs_conv_fwd(const void* d_in, int64_t n_in, int32_t c_in, const void* d_wei
                  int32_t c_out,
                  const int32_t* d_table, int64_t n_out, int32_t reverse_k, const float* d_bias, void* d_out,
                  int32_t dtype, int32_t algo, void* stream_) {
+  LGS_TRACE("lgs_conv_fwd %p %lld %d %p %d %d %d %p %lld %d %p %p %d %d %p", (const void*)d_in, (long long)n_in, (int)c_in, (const void*)d_weight, (int)weight_layout, (int)K, (int)c_out, (const void*)d_table, (long long)n_out, (int)reverse_k, (const void*)d_bias, (const void*)d_out, (int)dtype, (int)algo, (const void*)stream_);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_in < 0 || n_out < 0 || c_in < 1 || c_out < 1 || K < 1 || K > 27)
     return fail(LGS_E_INVALID, "lgs_conv_fwd: bad sizes n_in=%lld n_out=%lld c_in=%d c_out=%d K=%d", (long long)n_in,
@@ -84,6 +87,7 @@ int lgs_conv_fwd(const void* d_in, int64_t n_in, int32_t c_in, const void* d_wei
 
 int lgs_conv_wgrad(const void* d_in, int64_t n_in, int32_t c_in, const void* d_grad_out, int64_t n_out, int32_t c_out,
                    const int32_t* d_table, int32_t K, float* d_grad_w, int32_t dtype, int32_t algo, void* stream_) {
+  LGS_TRACE("lgs_conv_wgrad %p %lld %d %p %lld %d %p %d %p %d %d %p", (const void*)d_in, (long long)n_in, (int)c_in, (const void*)d_grad_out, (long long)n_out, (int)c_out, (const void*)d_table, (int)K, (const void*)d_grad_w, (int)dtype, (int)algo, (const void*)stream_);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_in < 0 || n_out < 0 || c_in < 1 || c_out < 1 || K < 1 || K > 27)
     return fail(LGS_E_INVALID, "lgs_conv_wgrad: bad sizes");

@@ -314,6 +314,7 @@ int lgs_bn_fwd(const float* d_x, const float* d_residual, int64_t n, int32_t c, 
                float eps, float momentum, int32_t relu, float* d_running_mean, float* d_running_var, float* d_z,
                float* d_save_mean, float* d_save_invstd, double* d_scratch /*[16c]*/, double* d_scratch_next /*[16384] or NULL*/,
                int64_t* d_num_batches_tracked, void* stream_) {
+  LGS_TRACE("lgs_bn_fwd %p %p %lld %d %p %p %.9g %.9g %d %p %p %p %p %p %p %p %p %p", (const void*)d_x, (const void*)d_residual, (long long)n, (int)c, (const void*)d_gamma, (const void*)d_beta, (double)eps, (double)momentum, (int)relu, (const void*)d_running_mean, (const void*)d_running_var, (const void*)d_z, (const void*)d_save_mean, (const void*)d_save_invstd, (const void*)d_scratch, (const void*)d_scratch_next, (const void*)d_num_batches_tracked, (const void*)stream_);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n < 1 || c < 4 || (c & 3) || c > 1024) return fail(LGS_E_UNSUPPORTED, "lgs_bn_fwd: n=%lld c=%d (need c %% 4 == 0, c <= 1024)", (long long)n, c);
   if (!d_x || !d_z || !d_save_mean || !d_save_invstd || !d_scratch) return fail(LGS_E_INVALID, "lgs_bn_fwd: null pointer");
@@ -343,6 +344,7 @@ int lgs_bn_bwd(const float* d_x, const float* d_z, const float* d_dz, int64_t n,
                const float* d_save_mean, const float* d_save_invstd, int32_t relu, float* d_dx, float* d_dresidual,
                float* d_dgamma, float* d_dbeta, double* d_scratch /*[16c]*/, double* d_scratch_next /*[16384] or NULL*/,
                void* stream_) {
+  LGS_TRACE("lgs_bn_bwd %p %p %p %lld %d %p %p %p %d %p %p %p %p %p %p %p", (const void*)d_x, (const void*)d_z, (const void*)d_dz, (long long)n, (int)c, (const void*)d_gamma, (const void*)d_save_mean, (const void*)d_save_invstd, (int)relu, (const void*)d_dx, (const void*)d_dresidual, (const void*)d_dgamma, (const void*)d_dbeta, (const void*)d_scratch, (const void*)d_scratch_next, (const void*)stream_);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n < 1 || c < 4 || (c & 3) || c > 1024) return fail(LGS_E_UNSUPPORTED, "lgs_bn_bwd: n=%lld c=%d", (long long)n, c);
   if (!d_x || !d_dz || !d_dx || !d_save_mean || !d_save_invstd || !d_scratch || (relu && !d_z))

@@ -245,6 +245,7 @@ extern "C" {
 int lgs_clip_ce(const float* d_feats, int64_t n, int32_t c, const float* d_anchors_n, int32_t a,
                 const int64_t* d_labels, int64_t ignore_label, float* d_loss, float* d_grad_feats, int32_t* d_pred,
                 float* d_grad_logits, void* stream_) {
+  LGS_TRACE("lgs_clip_ce %p %lld %d %p %d %p %lld %p %p %p %p %p", (const void*)d_feats, (long long)n, (int)c, (const void*)d_anchors_n, (int)a, (const void*)d_labels, (long long)ignore_label, (const void*)d_loss, (const void*)d_grad_feats, (const void*)d_pred, (const void*)d_grad_logits, (const void*)stream_);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n < 0 || c < 1 || a < 1) return fail(LGS_E_INVALID, "lgs_clip_ce: bad sizes n=%lld c=%d a=%d", (long long)n, c, a);
   if (a > CE_AMAX) return fail(LGS_E_UNSUPPORTED, "lgs_clip_ce: at most %d anchors per call (got %d)", CE_AMAX, a);
@@ -263,6 +264,7 @@ int lgs_clip_hinge(const float* d_feats, int64_t n, int32_t c, const float* d_an
                    const int64_t* d_labels, const int32_t* d_neg_ids, int32_t n_neg, int64_t ignore_label,
                    float pos_thresh, float neg_thresh, float neg_weight, float* d_pos_loss, float* d_neg_loss,
                    float* d_grad_feats, void* stream_) {
+  LGS_TRACE("lgs_clip_hinge %p %lld %d %p %d %p %p %d %lld %.9g %.9g %.9g %p %p %p %p", (const void*)d_feats, (long long)n, (int)c, (const void*)d_anchors_n, (int)a, (const void*)d_labels, (const void*)d_neg_ids, (int)n_neg, (long long)ignore_label, (double)pos_thresh, (double)neg_thresh, (double)neg_weight, (const void*)d_pos_loss, (const void*)d_neg_loss, (const void*)d_grad_feats, (const void*)stream_);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n < 0 || c < 1 || a < 1 || n_neg < 1) return fail(LGS_E_INVALID, "lgs_clip_hinge: bad sizes");
   if (n == 0) return LGS_OK;

@@ -535,6 +535,7 @@ int64_t lgs_clip_ce_tc_ws_elems(int32_t c, int32_t a) { return clip_ce_tc_ws_ele
 int lgs_clip_ce_tc(const float* d_feats, int64_t n, int32_t c, const float* d_anchors_n, int32_t a,
                    const int64_t* d_labels, int64_t ignore_label, float* d_loss, float* d_grad_feats, int32_t* d_pred,
                    float* d_grad_logits, float* d_ws, void* stream_) {
+  LGS_TRACE("lgs_clip_ce_tc %p %lld %d %p %d %p %lld %p %p %p %p %p %p", (const void*)d_feats, (long long)n, (int)c, (const void*)d_anchors_n, (int)a, (const void*)d_labels, (long long)ignore_label, (const void*)d_loss, (const void*)d_grad_feats, (const void*)d_pred, (const void*)d_grad_logits, (const void*)d_ws, (const void*)stream_);
   if (n < 0 || c < 1 || a < 1) return fail(LGS_E_INVALID, "lgs_clip_ce_tc: bad sizes n=%lld c=%d a=%d", (long long)n, c, a);
   if (!clip_ce_tc_shape_ok(c, a))
     return fail(LGS_E_UNSUPPORTED, "lgs_clip_ce_tc: needs c %% 4 == 0, a %% 4 == 0, a <= %d (got c=%d a=%d); use lgs_clip_ce",

@@ -37,6 +37,20 @@ inline int fail(int code, const char* fmt, ...) {
     LGS_CUDA(cudaGetLastError());                                                                   \
   } while (0)
 
+// ---- call recorder (lgs_trace_begin / lgs_trace_end) --------------------------------------------------
+// While recording, a traced entry point appends one line "name arg arg ..." and returns LGS_OK WITHOUT touching the
+// GPU, so the host side of the engine (bindings, the facade's call sequence and arguments) can be exercised and
+// compared on a machine with no GPU.  Off (one relaxed atomic load per call) unless lgs_trace_begin() was called.
+extern std::atomic<int> g_trace_on;
+void trace_record(const char* fmt, ...);
+#define LGS_TRACE(...)                                              \
+  do {                                                              \
+    if (::lgs::g_trace_on.load(std::memory_order_relaxed)) {        \
+      ::lgs::trace_record(__VA_ARGS__);                             \
+      return LGS_OK;                                                \
+    }                                                               \
+  } while (0)
+
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- coordinate keys ---------------------------------------------------------------------------------

@@ -4,12 +4,30 @@
 //
 // Replaces: ME insert_and_map_kernel + concurrent_unordered_map, stride_map kernels,
 // count_kernel + preallocated_kernel_map_iteration + thrust sort; lib/voxelizer.py:138-142.
+#include <cstring>
+#include <mutex>
+#include <string>
+
 #include "common.cuh"
 
 namespace lgs {
 
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_trace_on{0};
+static std::mutex g_trace_mu;
+static std::string g_trace_buf;
+
+void trace_record(const char* fmt, ...) {
+  char line[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(line, sizeof(line), fmt, ap);
+  va_end(ap);
+  std::lock_guard<std::mutex> lock(g_trace_mu);
+  g_trace_buf.append(line);
+  g_trace_buf.push_back('\n');
+}
 
 constexpr int kScanBlock = 256;
 constexpr int kScanItems = 8;
@@ -284,6 +302,21 @@ extern "C" {
 int lgs_version(void) { return 100; }
 const char* lgs_last_error(void) { return g_err; }
 uint64_t lgs_launch_count(void) { return g_launches.load(); }
+
+int lgs_trace_begin(void) {
+  std::lock_guard<std::mutex> lock(g_trace_mu);
+  g_trace_buf.clear();
+  g_trace_on.store(1);
+  return LGS_OK;
+}
+
+int64_t lgs_trace_end(char* buf, int64_t capacity) {
+  g_trace_on.store(0);
+  std::lock_guard<std::mutex> lock(g_trace_mu);
+  const int64_t need = int64_t(g_trace_buf.size()) + 1;
+  if (buf && capacity >= need) memcpy(buf, g_trace_buf.c_str(), size_t(need));
+  return need;
+}
 int32_t lgs_coord_limit(void) { return kCoordLimit; }
 
 int64_t lgs_hash_capacity(int64_t n) {
@@ -346,6 +379,7 @@ int lgs_coordmap_build(const int32_t* d_coords, int64_t n, int32_t quant, uint64
 int lgs_kmap_build(const int32_t* d_out_coords, int64_t n_out, const uint64_t* d_in_table_keys,
                    const int32_t* d_in_table_vals, int64_t in_capacity, int32_t ksize, int32_t in_tensor_stride,
                    int32_t dilation, int32_t* d_table, int32_t* d_counts, void* stream_) {
+  LGS_TRACE("lgs_kmap_build %p %lld %p %p %lld %d %d %d %p %p %p", (const void*)d_out_coords, (long long)n_out, (const void*)d_in_table_keys, (const void*)d_in_table_vals, (long long)in_capacity, (int)ksize, (int)in_tensor_stride, (int)dilation, (const void*)d_table, (const void*)d_counts, (const void*)stream_);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (ksize < 1 || ksize > 3 || in_tensor_stride < 1 || dilation < 1 || n_out < 0 ||
       (in_capacity & (in_capacity - 1)) || in_capacity < 1)
@@ -362,6 +396,7 @@ int lgs_kmap_build(const int32_t* d_out_coords, int64_t n_out, const uint64_t* d
 
 int lgs_kmap_transpose(const int32_t* d_table, int32_t K, int64_t n_out, int64_t n_in, int32_t* d_table_t,
                        void* stream_) {
+  LGS_TRACE("lgs_kmap_transpose %p %d %lld %lld %p %p", (const void*)d_table, (int)K, (long long)n_out, (long long)n_in, (const void*)d_table_t, (const void*)stream_);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (K < 1 || n_out < 0 || n_in < 0) return fail(LGS_E_INVALID, "lgs_kmap_transpose: bad sizes");
   LGS_CUDA(cudaMemsetAsync(d_table_t, 0xFF, size_t(K) * n_in * 4, stream));

@@ -124,6 +124,7 @@ int lgs_seg_ce_supported(int32_t c) { return (c >= 4 && (c & 3) == 0 && c <= 32 
 
 int lgs_seg_ce(const float* d_logits, int64_t n, int32_t c, const int64_t* d_labels, int64_t ignore_label,
                double* d_ws /*[4]*/, float* d_loss, float* d_grad_logits, void* stream_) {
+  LGS_TRACE("lgs_seg_ce %p %lld %d %p %lld %p %p %p %p", (const void*)d_logits, (long long)n, (int)c, (const void*)d_labels, (long long)ignore_label, (const void*)d_ws, (const void*)d_loss, (const void*)d_grad_logits, (const void*)stream_);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n < 1 || c < 1) return fail(LGS_E_INVALID, "lgs_seg_ce: bad sizes n=%lld c=%d", (long long)n, c);
   if (!lgs_seg_ce_supported(c)) return fail(LGS_E_UNSUPPORTED, "lgs_seg_ce: c=%d (need c %% 4 == 0, 4 <= c <= %d)", c, 128 * SCE_MAXV);

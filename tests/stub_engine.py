@@ -53,11 +53,16 @@ class FakeManager:
         return self.cache[ck]
 
 
-def install(setattr_fn):
-    """patch the facade through `setattr_fn(obj, name, value)` (pytest's monkeypatch.setattr or plain setattr)"""
+def install(setattr_fn, real_library=False):
+    """patch the facade through `setattr_fn(obj, name, value)` (pytest's monkeypatch.setattr or plain setattr).
+    real_library=True keeps the real C library behind the facade (to be used inside `_lib.trace()`, where the compute
+    entry points record their arguments and return without touching a GPU); only the CUDA stream / scratch plumbing of
+    the facade is replaced."""
     from languagegroundedsemseg_b200 import _lib
-    stub = StubLib()
-    setattr_fn(_lib, "load", lambda: stub)
+    stub = None
+    if not real_library:
+        stub = StubLib()
+        setattr_fn(_lib, "load", lambda: stub)
     setattr_fn(E, "_stream", lambda: None)
     scratch = E._Scratch(torch.device("cpu"))
     setattr_fn(E, "_scratch64", lambda idx: scratch)

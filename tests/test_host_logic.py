@@ -84,3 +84,116 @@ def test_weight_operand_cache_invalidation(stub):
     E.invalidate_weight_cache()
     fwd()
     assert n() == a + 4
+
+
+_TRACE_PROBE = r'''
+import sys, re
+sys.path.insert(0, ROOT)
+import torch
+from tests import stub_engine
+from languagegroundedsemseg_b200 import _lib, minkowski as E, nets
+stub_engine.install(setattr, real_library=True)
+SIZES = {1: 600, 2: 200, 4: 70, 8: 25, 16: 9}
+torch.manual_seed(0)
+net = nets.build_model("Res16UNet34C", 3, 200, nets.DefaultConfig()).train()
+opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9)
+mgr = stub_engine.FakeManager(SIZES)
+with _lib.trace() as t:
+    for _ in range(2):
+        out, _ = net(stub_engine.sparse_input(SIZES[1], 3, mgr))
+        opt.zero_grad(set_to_none=True)
+        out.F.float().mean().backward()
+        opt.step()
+# canonical form (addresses differ from process to process and the allocator re-uses them): a pointer that is the address
+# of a persistent tensor — parameter, buffer, cached weight operand, neighbour table, BatchNorm scratch half — becomes that
+# tensor's NAME (an exact-address match, so this also proves the pointer value arrived intact); any other non-null pointer
+# (activations, gradients, temporaries) becomes "A"; NULL becomes "0"
+names = {}
+for k, v in list(net.named_parameters()) + list(net.named_buffers()):
+    names[v.data_ptr()] = k
+for mn, m in net.named_modules():
+    for key, bufs in getattr(m, "_prep_bufs", {}).items():
+        for tag, b in zip(("w_fwd", "w_bwd"), bufs[:2]):
+            if b is not None:
+                names[b.data_ptr()] = f"{mn}.{tag}"
+for (ts, out_ts, ks), (_, km) in mgr.cache.items():
+    names[km.fwd_table.data_ptr()] = f"table{ks}:{ts}->{out_ts}:fwd"
+    names[km.bwd_table.data_ptr()] = f"table{ks}:{ts}->{out_ts}:bwd"
+sc = E._scratch64(None)
+for i, h in enumerate(sc.halves):
+    names[h.value] = f"bn_scratch{i}"
+def canon(m):
+    if m.group(0) == "(nil)":
+        return "0"
+    return names.get(int(m.group(0), 16), "A")
+lines = [re.sub(r"0x[0-9a-f]+|\(nil\)", canon, l) for l in t.lines]
+print(_lib.binding())
+print("\n".join(lines))
+'''
+
+
+def test_both_bindings_issue_identical_calls(lib):
+    """two SGD steps of Res16UNet34C through the facade with the REAL library recording its calls (lgs_trace_begin: the
+    compute entry points log their arguments and return; no GPU needed): the ctypes binding and the generated native
+    binding (LGS_FAST_BIND=1) must produce the same call sequence with the same integer / float arguments and the same
+    pointer structure — i.e. the native binding marshals every argument of every hot entry point like ctypes does"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", f"ROOT={root!r}\n" + _TRACE_PROBE], capture_output=True, text=True,
+                           env=dict(os.environ, LGS_FAST_BIND=mode), timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out = r.stdout.strip().splitlines()
+        res[mode] = (out[0], out[1:])
+    assert res["0"][0] == "ctypes" and res["1"][0] == "native"
+    a, b = res["0"][1], res["1"][1]
+    assert len(a) == len(b) == 2 * (125 + 63 + 62 + 62 + 1 + 1)
+    for x, y in zip(a, b):
+        assert x == y
+    names = [l.split()[0] for l in a]
+    assert names.count("lgs_conv_fwd") == 2 * (63 + 62) and names.count("lgs_conv_wgrad") == 2 * 63
+    assert names.count("lgs_bn_fwd") == names.count("lgs_bn_bwd") == 2 * 62 and names.count("lgs_weight_prep_batch") == 2
+    named = sum(tok not in ("A", "0") and not tok[0].isdigit() and not tok.startswith("lgs_") and not tok.startswith("-")
+                for l in a for tok in l.split())
+    assert named > 1500                  # parameters, buffers, weight operands, tables and scratch halves were all recognised
+    # BatchNorm scratch halves alternate: the half a call clears is the half the next call accumulates into
+    bn = [l.split() for l in a if l.startswith("lgs_bn_")]
+    for prev, nxt in zip(bn, bn[1:]):
+        p_next = prev[-3] if prev[0] == "lgs_bn_fwd" else prev[-2]       # d_scratch_next of the earlier call
+        n_acc = nxt[-4] if nxt[0] == "lgs_bn_fwd" else nxt[-3]           # d_scratch of the later call
+        assert p_next == n_acc and p_next.startswith("bn_scratch")
+
+
+def _one_step_trace(mode="0"):
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", f"ROOT={root!r}\n" + _TRACE_PROBE], capture_output=True, text=True,
+                       env=dict(os.environ, LGS_FAST_BIND=mode), timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout.strip().splitlines()[1:][314:]          # the second (steady-state) step
+
+
+def test_facade_call_sequence_is_the_committed_one(lib, golden_dir):
+    """the exact sequence of C-ABI calls (entry, sizes, flags, which table / weight operand / BatchNorm tensor) of one
+    Res16UNet34C training step — the contract a native step driver has to reproduce — against the committed trace"""
+    import os
+    want = [l for l in open(os.path.join(golden_dir, "facade_trace_unet34c.txt")).read().splitlines() if not l.startswith("#")]
+    got = _one_step_trace()
+    assert len(got) == len(want) == 314
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g == w, (i, g, w)
+
+
+if __name__ == "__main__":
+    import sys
+    if "--regen" in sys.argv:
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "facade_trace_unet34c.txt")
+        head = [l for l in open(path).read().splitlines() if l.startswith("#")]
+        open(path, "w").write("\n".join(head + _one_step_trace()) + "\n")
+        print("regenerated", path)
