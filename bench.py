@@ -404,6 +404,7 @@ def run_engine(args, rank, world, local_rank):
         "warmup": warm_done, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.dtype == "f32" else "bf16", "data": "synthetic",
         "config": {"workload": workload_string(args.model, n_vox, args.voxel_size, args.voxels), "voxels_per_gpu": n_vox, "algo": args.algo,
+                   "binding": _lib.binding() + " (Python -> C ABI)",
                    "math": {"tc": "tcgen05 3xTF32 products (fp32-grade) fwd/dgrad, TF32 wgrad, fp32 accumulate in TMEM",
                             "tf32": "tcgen05 single-pass TF32, fp32 accumulate", "simt": "fp32 FMA"}[args.algo]
                    if args.dtype == "f32" else "tcgen05 bf16 products, fp32 accumulate in TMEM",

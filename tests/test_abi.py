@@ -93,3 +93,61 @@ def test_native_binding_matches_ctypes(lib):
     assert res["0"][0] == "ctypes" and res["1"][0] == "native"
     assert res["0"][1:] == res["1"][1:]
     assert all(rc != 0 for _, rc, _ in res["0"][1:])
+
+
+_SITES_PROBE = r'''
+import sys, re
+sys.path.insert(0, ROOT)
+import torch
+from tests import stub_engine
+from languagegroundedsemseg_b200 import _lib, losses, minkowski as E
+stub_engine.install(setattr, real_library=True)
+losses._stream = lambda: None
+with _lib.trace() as t:
+    # kernel-map call sites (CoordinateManager._table / ._transpose) on hand-made coordinate maps
+    mgr = E.CoordinateManager(D=3)
+    for ts, n in ((1, 40), (2, 12)):
+        cm = E._CoordMap()
+        cm.coords = torch.zeros((n, 4), dtype=torch.int32)
+        cm.tkeys, cm.tvals = torch.zeros(128, dtype=torch.int64), torch.zeros(128, dtype=torch.int32)
+        cm.n, cm.capacity = n, 128
+        mgr._maps[E.CoordinateMapKey([ts] * 3)] = cm
+    k1, k2 = E.CoordinateMapKey([1, 1, 1]), E.CoordinateMapKey([2, 2, 2])
+    mgr.kernel_map(k1, k1, [3, 3, 3], [1, 1, 1])
+    mgr.kernel_map(k1, k2, [2, 2, 2], [1, 1, 1])
+    mgr.kernel_map(k2, k1, [2, 2, 2], [1, 1, 1], True)
+    # loss call sites
+    x = torch.randn(33, 200, requires_grad=True)
+    y = torch.randint(-1, 200, (33,))
+    losses._SegCEFn.apply(x, y, -1).backward()
+    f = torch.randn(50, 96, requires_grad=True)
+    a = torch.nn.functional.normalize(torch.randn(200, 96), dim=1)
+    lab = torch.randint(-1, 200, (50,))
+    for algo in ("tc", "simt"):
+        losses.set_clip_algo(algo)
+        losses._ClipCEFn.apply(f, a, lab, -1)
+    neg = torch.randint(0, 200, (50, 3), dtype=torch.int32)
+    losses._ClipHingeFn.apply(f, a, lab, neg, -1, 0.0, 0.6, 1.0)
+lines = [re.sub(r"0x[0-9a-f]+", "A", l).replace("(nil)", "0") for l in t.lines]
+print(_lib.binding())
+print(*lines, sep=chr(10))
+'''
+
+
+def test_remaining_call_sites_through_both_bindings(lib):
+    """kernel-map construction and the three loss entry points as the facade calls them, recorded by the library
+    (lgs_trace_begin): same calls and argument values through ctypes and through the native binding"""
+    import subprocess
+    import sys
+    res = {}
+    for mode in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", f"ROOT={ROOT!r}\n" + _SITES_PROBE], capture_output=True, text=True,
+                           env=dict(os.environ, LGS_FAST_BIND=mode), timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out = r.stdout.strip().splitlines()
+        res[mode] = (out[0], out[1:])
+    assert (res["0"][0], res["1"][0]) == ("ctypes", "native")
+    assert res["0"][1] == res["1"][1]
+    names = [l.split()[0] for l in res["0"][1]]
+    assert names == ["lgs_kmap_build", "lgs_kmap_build", "lgs_kmap_transpose", "lgs_seg_ce", "lgs_clip_ce_tc", "lgs_clip_ce",
+                     "lgs_clip_hinge"], names
