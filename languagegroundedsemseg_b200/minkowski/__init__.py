@@ -514,7 +514,7 @@ class SparseTensor:
         if p is not None:
             if p.plain is None:
                 if type(p) is _PendingConv:      # materialise the deferred convolution
-                    p.plain = sparse_conv(p.x, p.conv.kernel, p.conv.bias, p.km, module=p.conv)
+                    p.plain = sparse_conv(p.x, p.conv._parameters["kernel"], p.conv.bias, p.km, module=p.conv)
                 else:                            # materialise the deferred BatchNorm (+ residual), no ReLU
                     p.plain = _bn_act(p, relu=False)
             self._F, self._pending = p.plain, None
@@ -593,14 +593,15 @@ def _bn_fwd_impl(x, res, gamma, beta, bn, relu, update_running):
         res = res.contiguous()
     z = torch.empty_like(x)
     stats = torch.empty((2, c), dtype=torch.float32, device=x.device)       # save_mean, save_invstd
-    rm = bn.running_mean if update_running else None
-    rv = bn.running_var if update_running else None
+    bufs = bn._buffers                    # plain dict reads: nn.Module.__getattr__ costs ~1 us per parameter / buffer access
+    rm = bufs["running_mean"] if update_running else None
+    rv = bufs["running_var"] if update_running else None
     sc = _scratch64(x.device.index)
     acc, nxt = sc.pair()
     rc = lib.lgs_bn_fwd(_lib.ptr(x), _lib.ptr(res), n, c, _lib.ptr(gamma), _lib.ptr(beta), float(bn.eps),
                         float(bn.momentum), 1 if relu else 0, _lib.ptr(rm), _lib.ptr(rv), _lib.ptr(z),
                         ctypes.c_void_p(stats.data_ptr()), ctypes.c_void_p(stats.data_ptr() + 4 * c), acc, nxt,
-                        _lib.ptr(bn.num_batches_tracked) if update_running else None, _stream())
+                        _lib.ptr(bufs["num_batches_tracked"]) if update_running else None, _stream())
     sc.done(rc == _lib.OK)
     _lib.check(rc)
     return x, z, stats
@@ -643,10 +644,12 @@ class _BNActFn(torch.autograd.Function):
 def _bn_act(p: _PendingBN, relu: bool):
     if p.conv is not None:
         c = p.conv
-        out = _ConvBNActFn.apply(c.x, c.conv.kernel, p.bn.weight, p.bn.bias, p.res, c.km, _state["algo"], p.bn, relu,
-                                 not p.consumed, c.conv)
+        bp = p.bn._parameters
+        out = _ConvBNActFn.apply(c.x, c.conv._parameters["kernel"], bp["weight"], bp["bias"], p.res, c.km, _state["algo"],
+                                 p.bn, relu, not p.consumed, c.conv)
     else:
-        out = _BNActFn.apply(p.x, p.res, p.bn.weight, p.bn.bias, p.bn, relu, not p.consumed)
+        bp = p.bn._parameters
+        out = _BNActFn.apply(p.x, p.res, bp["weight"], bp["bias"], p.bn, relu, not p.consumed)
     p.consumed = True          # running statistics are updated once per BatchNorm call
     return out
 
@@ -679,7 +682,7 @@ class _WeightPrep:
 
     def __init__(self):
         self.mods = weakref.WeakSet()
-        self.desc = {}          # (device, dt, nsplit) -> (key, device descriptor table, n_layers, total tiles, entries)
+        self.desc = {}          # (device, dt, nsplit) -> descriptor cache, see refresh()
         self.epoch = 0          # bumped whenever the parameters may have changed
         self.dirty = False      # a weight gradient was computed / an optimiser stepped since the last refresh
         self.hooked = False
@@ -717,10 +720,30 @@ class _WeightPrep:
 
     def refresh(self, device, dt, nsplit, tdtype):
         lib = _lib.load()
+        ck = (device, dt, nsplit)
+        cached = self.desc.get(ck)
+        if cached is not None and cached[4] == len(self.mods):
+            # fast path (every training step): same set of layers, weights still at the same addresses -> reuse the
+            # device descriptor table, relaunch, stamp every layer's operands with the new epoch / version
+            live = []
+            for ref, wptr, fb, bb in cached[5]:
+                m = ref()
+                if m is None:
+                    break
+                w = m._parameters["kernel"]
+                if w.data_ptr() != wptr or w.dtype is not torch.float32:
+                    break
+                live.append((m, w, wptr, fb, bb))
+            else:
+                _lib.check(lib.lgs_weight_prep_batch(_lib.ptr(cached[1]), cached[2], cached[3], nsplit, dt, _stream()))
+                ep = self.epoch
+                for m, w, wptr, fb, bb in live:
+                    m._prep = ((ep, w._version, wptr, dt, nsplit), fb, bb)
+                return
         es = 2 if dt == _lib.BF16 else 4
         entries = []
         for m in list(self.mods):
-            w = m.kernel
+            w = m._parameters["kernel"]
             if w.device != device or w.dtype is not torch.float32 or not w.is_contiguous():
                 continue
             K, c_in, c_out = (1,) + tuple(w.shape) if w.dim() == 2 else tuple(w.shape)
@@ -736,18 +759,21 @@ class _WeightPrep:
                 bufs = m._prep_bufs[(dt, nsplit)] = (fb, bb, w.data_ptr())
             entries.append((m, w, K, c_in, c_out, bufs[0], bufs[1]))
         if not entries:
+            self.desc.pop(ck, None)
             return
         # shapes belong in the key: a new layer's tensors can land on a dead layer's addresses
         key = tuple((e[1].data_ptr(), e[5].data_ptr() if e[5] is not None else 0,
                      e[6].data_ptr() if e[6] is not None else 0, e[2], e[3], e[4]) for e in entries)
-        cached = self.desc.get((device, dt, nsplit))
         if cached is None or cached[0] != key:
             rows, tile0 = [], 0
             for (_, w, K, c_in, c_out, fb, bb), k3 in zip(entries, key):
                 rows.append([k3[0], k3[1], k3[2], K, c_in, c_out, tile0, 0])
                 tile0 += K * ((c_in + 31) // 32) * ((c_out + 31) // 32)
             table = torch.tensor(rows, dtype=torch.int64).to(device)
-            cached = self.desc[(device, dt, nsplit)] = (key, table, len(rows), tile0)
+            cached = (key, table, len(rows), tile0)
+        # (key, descriptor table, layers, tiles, registered modules at build time, [(weakref(layer), weight address, operands)])
+        cached = self.desc[ck] = cached[:4] + (len(self.mods), [(weakref.ref(e[0]), e[1].data_ptr(), e[5], e[6])
+                                                                for e in entries])
         _lib.check(lib.lgs_weight_prep_batch(_lib.ptr(cached[1]), cached[2], cached[3], nsplit, dt, _stream()))
         for m, w, _, _, _, fb, bb in entries:
             m._prep = ((self.epoch, w._version, w.data_ptr(), dt, nsplit), fb, bb)
@@ -986,7 +1012,7 @@ class _ConvBase(nn.Module):
         if self.bias is None and _state["fuse_conv_bn"] and F.dtype is torch.float32:
             # deferred: a following fusable BatchNorm turns conv + BN (+ residual) (+ ReLU) into one autograd node
             return SparseTensor._make(None, out_key, mgr, _PendingConv(self, F, km))
-        return SparseTensor._make(sparse_conv(F, self.kernel, self.bias, km, module=self), out_key, mgr)
+        return SparseTensor._make(sparse_conv(F, self._parameters["kernel"], self.bias, km, module=self), out_key, mgr)
 
     def extra_repr(self):
         kg = self.kernel_generator
@@ -1013,13 +1039,14 @@ class MinkowskiBatchNorm(nn.Module):
 
     def forward(self, x: SparseTensor):
         p = x._pending
+        bn = self._modules["bn"]
         if (type(p) is _PendingConv and p.plain is None
-                and _bn_fusable_meta(self.bn, p.x.dtype, p.out_rows(), p.conv.out_channels)):
-            return SparseTensor._make(None, x.coordinate_map_key, x.coordinate_manager, _PendingBN(self.bn, p.x, p))
+                and _bn_fusable_meta(bn, p.x.dtype, p.out_rows(), p.conv.out_channels)):
+            return SparseTensor._make(None, x.coordinate_map_key, x.coordinate_manager, _PendingBN(bn, p.x, p))
         F = x.F
-        if _bn_fusable(self.bn, F):
-            return SparseTensor._make(None, x.coordinate_map_key, x.coordinate_manager, _PendingBN(self.bn, F))
-        return x._like(self.bn(F))
+        if _bn_fusable(bn, F):
+            return SparseTensor._make(None, x.coordinate_map_key, x.coordinate_manager, _PendingBN(bn, F))
+        return x._like(bn(F))
 
 
 class MinkowskiSyncBatchNorm(MinkowskiBatchNorm):
