@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from languagegroundedsemseg_b200 import _lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -151,3 +153,35 @@ def test_remaining_call_sites_through_both_bindings(lib):
     names = [l.split()[0] for l in res["0"][1]]
     assert names == ["lgs_kmap_build", "lgs_kmap_build", "lgs_kmap_transpose", "lgs_seg_ce", "lgs_clip_ce_tc", "lgs_clip_ce",
                      "lgs_clip_hinge"], names
+
+
+def test_native_binding_fuzz_against_ctypes(lib):
+    """random argument tuples (full int32 / int64 ranges, pointers up to 2^63, floats) through every wrapper of the native
+    binding and through ctypes, in one process: traced entries must record identical lines, untraced ones (the *_supported
+    queries) must return the same value"""
+    import ctypes as C
+    import random
+    if _lib.binding() != "native":
+        pytest.skip("native binding not built")
+    fast, cdll = _lib._fast, lib._cdll
+    rng = random.Random(1234)
+    gen = {C.c_void_p: lambda: rng.choice([None, 0, rng.randrange(1, 2 ** 63), rng.randrange(1, 2 ** 47)]),
+           C.c_int64: lambda: rng.choice([0, -1, 2 ** 63 - 1, -2 ** 63, rng.randrange(-2 ** 40, 2 ** 40)]),
+           C.c_int32: lambda: rng.choice([0, 1, -1, 2 ** 31 - 1, -2 ** 31, rng.randrange(-10 ** 6, 10 ** 6)]),
+           C.c_float: lambda: rng.choice([0.0, 1e-5, -3.5, 0.1, 1e30, rng.random()])}
+    wrapped = [n for n in _lib.SIGNATURES if hasattr(fast, n)]
+    assert len(wrapped) >= 15
+    for name in wrapped:
+        res, argtypes = _lib.SIGNATURES[name]
+        cfn = getattr(cdll, name)
+        for _ in range(40):
+            args = [gen[t]() for t in argtypes]
+            outs = []
+            for fn in (cfn, getattr(fast, name)):
+                lib.lgs_trace_begin()
+                rc = fn(*args)
+                need = lib.lgs_trace_end(None, 0)
+                buf = C.create_string_buffer(int(need))
+                lib.lgs_trace_end(buf, need)
+                outs.append((rc, buf.value))
+            assert outs[0] == outs[1], (name, args, outs)
