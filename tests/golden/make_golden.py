@@ -173,6 +173,14 @@ def augment():
         c, f, l = augment_pipeline(RT)(c0.copy(), f0.copy(), l0.copy())
         out.update({f"s{seed}_coords": c, f"s{seed}_feats": f, f"s{seed}_labels": l})
         print("augment", seed, c.shape)
+        random.seed(seed)
+        out[f"s{seed}_hue"] = RT.HueSaturationTranslation(0.5, 0.2)(None, np.floor(f0).copy(), None)[1]
+    # batch assembly with a point budget (cfl_collate_fn_factory): 4 scenes, limits that keep 4 / 3 / 2 of them
+    items = [(c0[:n].astype(np.int32), f0[:n], l0[:n], f"scene{n}") for n in (100, 250, 70, 400)]
+    for limit in (0, 500, 360):
+        bc, bf, bl, names = RT.cfl_collate_fn_factory(limit)(items)
+        out.update({f"collate{limit}_coords": bc.numpy(), f"collate{limit}_feats": bf.numpy(),
+                    f"collate{limit}_labels": bl.numpy(), f"collate{limit}_names": np.array(names)})
     np.savez_compressed(os.path.join(HERE, "augment.npz"), **out)
 
 
