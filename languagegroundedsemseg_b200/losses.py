@@ -213,3 +213,44 @@ def feature_sim_argmax(feats, anchor_feats):
     with torch.no_grad():
         _, pred = clip_ce(feats.detach(), labels, anchor_feats, -1)
     return pred.long()
+
+
+def sample_categories_for_balancing(loss, config, dataset, targets, outputs=None, generator=None):
+    """lib/losses/utils.py:13-77 without the per-class host loop (`.item()` syncs, np.random.choice on the CPU):
+    per-point loss [n] (or only the valid points'), targets [n]; `dataset.frequency_organized_cats` bool [NUM_LABELS,3]
+    marks head / common / tail categories.  Head (common) points are kept with probability mass
+    `config.balanced_sample_head_ratio` (`..._common_ratio`): exactly round(ratio * count) points of every head (common)
+    class, chosen uniformly on the device; ratio <= 0 keeps them all (the reference's default, -1); tail points are always
+    kept.  Returns (mean of the masked loss, (head, common, tail) losses detached, [n_valid,3] membership) like the
+    reference.  With ratios <= 0 the result equals the reference's exactly; with sampling the kept COUNT per class is the
+    reference's and the choice is uniform, but the random stream is torch's, not numpy's."""
+    ignore = config.ignore_label
+    if loss.shape[0] != targets.shape[0]:
+        targets = targets[targets != ignore]
+    dev = loss.device
+    valid = targets != ignore
+    cats = dataset.frequency_organized_cats.to(dev)
+    t = targets.long().clamp(min=0)
+    member = cats[t] & valid[:, None]                              # [n,3] head / common / tail
+    member[:, 2] = valid & ~member[:, 0] & ~member[:, 1]           # the reference's `else` branch: everything else is tail
+    keep = member[:, 2].clone()
+    n_labels = cats.shape[0]
+    for col, ratio in ((0, config.balanced_sample_head_ratio), (1, config.balanced_sample_common_ratio)):
+        sel = member[:, col]
+        if ratio > 0.0:
+            # rank every selected point inside its class by a random key; keep the first round(ratio * count) of each class
+            counts = torch.bincount(t[sel], minlength=n_labels)
+            quota = torch.round(ratio * counts.double()).long()   # python's round() of the reference is half-to-even too
+            key = torch.rand(t.shape[0], device=dev, generator=generator)
+            order = torch.argsort(torch.where(sel, t.double() + key.double(), torch.full_like(key, float("inf")).double()))
+            sorted_cls = t[order]
+            first = torch.searchsorted(sorted_cls[: int(sel.sum())].contiguous(), torch.arange(n_labels, device=dev))
+            rank = torch.empty_like(t)
+            n_sel = int(sel.sum())
+            rank[order[:n_sel]] = torch.arange(n_sel, device=dev) - first[sorted_cls[:n_sel]]
+            keep |= sel & (rank < quota[t])
+        else:
+            keep |= sel
+    head_loss, common_loss, tail_loss = (loss[member[:, c]].detach() for c in range(3))
+    masked = loss * keep.to(loss.dtype)
+    return masked.mean(), (head_loss, common_loss, tail_loss), member[valid]
