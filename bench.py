@@ -128,9 +128,19 @@ def _aten_criterion(logits, labels):
     return torch.nn.functional.cross_entropy(logits.float(), labels, ignore_index=-1)
 
 
-def train_step(ST, net, opt, coords, feats, labels, reducer=None, st=None, criterion=_aten_criterion):
+def train_step(ST, net, opt, coords, feats, labels, reducer=None, st=None, criterion=_aten_criterion, program=None):
     if st is None:
         st = ST(feats, coords)                               # pl_BaselineTrainer.py:300
+    if program is not None:
+        # opt-in (--step-program): forward + loss + backward as one explicit program over the same entry points
+        # (languagegroundedsemseg_b200/step.py), no autograd graph / module dispatch
+        opt.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            loss = program.run(st, labels, ignore_index=-1)
+        if reducer is not None:
+            reducer()
+        opt.step()
+        return loss
     out, _ = net(st)                                         # res16unet.py:196
     loss = criterion(out.F, labels)                          # :350  CrossEntropyLoss(ignore_index)
     opt.zero_grad(set_to_none=True)
@@ -219,16 +229,21 @@ def run_engine(args, rank, world, local_rank):
     # the engine's fused softmax cross-entropy (lgs_seg_ce: one pass over the logits) unless LGS_ATEN_CE=1
     crit = _aten_criterion if os.environ.get("LGS_ATEN_CE") else (lambda x, y: lgs_losses.cross_entropy(x, y, ignore_index=-1))
 
+    program = None
+    if args.step_program:
+        from languagegroundedsemseg_b200.step import StepProgram
+        program = StepProgram(model)
+
     def staged_step(key, src):
         flush.fill_(0.0)
         if pf is None:
             c, f, lab = (t.to(dev, non_blocking=True) for t in src)
-            return train_step(E.SparseTensor, model, opt, c, f.to(fdtype), lab, reducer, criterion=crit)
+            return train_step(E.SparseTensor, model, opt, c, f.to(fdtype), lab, reducer, criterion=crit, program=program)
         if key not in tickets:
             tickets[key] = pf.stage(*src)
         st, lab = pf.get(tickets[key])
         tickets[key] = pf.stage(*src)                        # next step's batch, overlapped with this step
-        return train_step(None, model, opt, None, None, lab, reducer, st=st, criterion=crit)
+        return train_step(None, model, opt, None, None, lab, reducer, st=st, criterion=crit, program=program)
 
     def resident_step():
         return staged_step("resident", (d_coords, d_feats, d_labels))
@@ -405,6 +420,7 @@ def run_engine(args, rank, world, local_rank):
         "vs_baseline": None, "dtype": "f32" if args.dtype == "f32" else "bf16", "data": "synthetic",
         "config": {"workload": workload_string(args.model, n_vox, args.voxel_size, args.voxels), "voxels_per_gpu": n_vox, "algo": args.algo,
                    "binding": _lib.binding() + " (Python -> C ABI)",
+                   "driver": "StepProgram (explicit program, no autograd)" if args.step_program else "MinkowskiEngine facade + autograd",
                    "math": {"tc": "tcgen05 3xTF32 products (fp32-grade) fwd/dgrad, TF32 wgrad, fp32 accumulate in TMEM",
                             "tf32": "tcgen05 single-pass TF32, fp32 accumulate", "simt": "fp32 FMA"}[args.algo]
                    if args.dtype == "f32" else "tcgen05 bf16 products, fp32 accumulate in TMEM",
@@ -496,6 +512,9 @@ def main():
     ap.add_argument("--voxel-size", type=float, default=0.02)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="build the coordinate manager on the training stream")
+    ap.add_argument("--step-program", action="store_true",
+                    help="forward + loss + backward through languagegroundedsemseg_b200.step.StepProgram (explicit program over "
+                         "the same C-ABI calls, no autograd graph) instead of the module-by-module facade")
     ap.add_argument("--profile-run", action="store_true",
                     help="for ncu launch lists: allow fewer warm-up steps and skip the e2e / map-build / roofline legs")
     args = ap.parse_args()

@@ -30,7 +30,7 @@ def main():
     a = ap.parse_args()
     args = argparse.Namespace(gpus=1, steps=20, warmup=5, impl="engine", algo="tc", dtype="f32", cpu_sample_voxels=0,
                               model=bench.MODEL, voxels=bench.TARGET_VOXELS, voxel_size=0.02, no_cpu_baseline=True,
-                              no_prefetch=False, profile_run=False)
+                              no_prefetch=False, profile_run=False, step_program=False)
     for name, flags, env in VARIANTS:
         if a.only and name not in a.only.split(","):
             continue
