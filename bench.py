@@ -273,7 +273,7 @@ def run_engine(args, rank, world, local_rank):
     # W untimed warm-up steps, never fewer than 10: the caching allocator's per-stream pools (training stream + staging
     # stream, blocks handed over with record_stream) take several steps to stop growing, and a cudaMalloc inside the
     # timed region costs milliseconds (seen as a 19 ms outlier in one of four runs with 5 warm-up steps)
-    warm_done = max(args.warmup, 10)
+    warm_done = args.warmup if args.profile_run else max(args.warmup, 10)   # --profile-run: launch lists under ncu
     clk.wait_first_sample()             # the poller's start-up must not overlap a timed region
     for _ in range(warm_done):
         resident_step()
