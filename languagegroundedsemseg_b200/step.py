@@ -7,9 +7,10 @@ facade issues for the same network (tests/test_step_program.py compares the reco
 gradients of the whole program against autograd on the CPU oracle engine), so it is also the executable specification of
 the native (C++) step driver planned next.
 
-Scope: the 'seg' flavour of nets.Res16UNet (Res16UNet14A/18A/34A/34C: BASELINE configs 1, 2, 4) with a mean
-cross-entropy criterion; training mode; one call = forward + loss + backward, parameter gradients accumulated into
-`.grad` like `loss.backward()` would.  Opt-in (`StepProgram(net).run(st, labels)`); the module-by-module facade path
+Scope: nets.Res16UNet topologies in training mode.  `run` = segmentation nets (Res16UNet14A/18A/34A/34C: BASELINE
+configs 1, 2, 4) with the fused mean cross-entropy; `run_features` = any flavour with a caller-supplied head (the CLIP
+pre-training nets of configs 3 / 5).  One call = forward + loss + backward, parameter gradients accumulated into `.grad`
+like `loss.backward()` would.  Opt-in (`StepProgram(net).run(st, labels)`); the module-by-module facade path
 remains the default and the reference-facing one.
 
 Backward order.  Nodes run in reverse creation order (what autograd does for this graph: among the ready nodes the one
@@ -83,8 +84,8 @@ def _acc(p, g):
 
 class StepProgram:
     def __init__(self, net, backend=None):
-        if getattr(net, "flavour", None) != "seg":
-            raise NotImplementedError("StepProgram covers the segmentation flavour of nets.Res16UNet (final classifier head)")
+        if not hasattr(net, "_enc") or not hasattr(net, "_dec"):
+            raise NotImplementedError("StepProgram drives nets.Res16UNet topologies")
         self.net = net
         self.B = backend if backend is not None else FacadeBackend()
 
@@ -133,9 +134,9 @@ class StepProgram:
             d = self._block_bwd(n, d)
         return d
 
-    # ---- the step -----------------------------------------------------------------------------------------------
-    def run(self, st, labels, ignore_index=-1):
-        """forward + mean cross-entropy (ignore_index) + backward; returns the loss (0-dim tensor on the device)"""
+    # ---- the U-Net body -------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _features_fwd(self, st):
         net, B = self.net, self.B
         x, key = B.begin(st)
         a, key, n0 = self._cbr_fwd(net.conv0p1s1, net.bn0.bn, x, key, True, need_dgrad=False)
@@ -152,15 +153,13 @@ class StepProgram:
             a = B.cat(a, skips[3 - lvl])
             a, nb = self._stage_fwd(getattr(net, bl), a, key)
             dec.append((nt, width, nb))
-        _, km = B.maps(net.final, key)
-        logits, fsave = B.conv_fwd(a, net.final, km, True)
-        loss, d = B.ce(logits, labels, ignore_index)
+        return a, key, (n0, enc, dec)
 
-        # ---- backward: reverse creation order ---------------------------------------------------------------
-        d, gw, gb = B.conv_bwd(fsave, d, True, net.final.bias is not None)
-        _acc(net.final._parameters["kernel"], gw)
-        if net.final.bias is not None:
-            _acc(net.final._parameters["bias"], gb)
+    @torch.no_grad()
+    def _features_bwd(self, nodes, d):
+        """backward of the body in reverse creation order; `d` = gradient w.r.t. the per-point features"""
+        B = self.B
+        n0, enc, dec = nodes
         dskip = [None] * 4
         for lvl in (3, 2, 1, 0):
             nt, width, nb = dec[lvl]
@@ -175,5 +174,37 @@ class StepProgram:
             d = self._cbr_bwd(nd, d)[0]
         d = B.add(d, dskip[0])
         self._cbr_bwd(n0, d, need_gin=False)
+
+    # ---- the steps --------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def run(self, st, labels, ignore_index=-1):
+        """segmentation flavour: forward + `final` classifier + mean cross-entropy (ignore_index) + backward; returns the
+        loss (0-dim tensor on the device); the logits are left in `self.logits`"""
+        net, B = self.net, self.B
+        if getattr(net, "flavour", None) != "seg" or net.final is None:
+            raise NotImplementedError("run() needs the segmentation flavour (final classifier); use run_features()")
+        a, key, nodes = self._features_fwd(st)
+        _, km = B.maps(net.final, key)
+        logits, fsave = B.conv_fwd(a, net.final, km, True)
+        loss, d = B.ce(logits, labels, ignore_index)
+        d, gw, gb = B.conv_bwd(fsave, d, True, net.final.bias is not None)
+        _acc(net.final._parameters["kernel"], gw)
+        if net.final.bias is not None:
+            _acc(net.final._parameters["bias"], gb)
+        self._features_bwd(nodes, d)
         self.logits = logits
         return loss
+
+    def run_features(self, st, head):
+        """any flavour (the CLIP pre-training nets of BASELINE configs 3 / 5: Res16UNet34CR / 34CR_Proj / 34D with
+        representation_only): the U-Net body runs as the explicit program, `head(features) -> scalar loss` runs under
+        autograd (it is tiny: anchor projection + the fused text-anchor loss, or any criterion) and its gradient w.r.t.
+        the features is fed to the body's backward.  Returns the loss; the features are left in `self.features`."""
+        a, _, nodes = self._features_fwd(st)
+        leaf = a.detach().requires_grad_(True)
+        with torch.enable_grad():
+            loss = head(leaf)
+            loss.backward()
+        self._features_bwd(nodes, leaf.grad)
+        self.features = a
+        return loss.detach()

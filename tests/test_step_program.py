@@ -49,6 +49,40 @@ def test_program_gradients_equal_autograd_on_the_oracle_engine(name, voxels):
         assert torch.allclose(p[3][k].float(), v.float(), rtol=1e-5, atol=1e-7), k
 
 
+@pytest.mark.parametrize("name", ["Res16UNet34CR_Proj", "Res16UNet34D"])
+def test_program_with_clip_head_equals_autograd_on_the_oracle_engine(name):
+    """BASELINE configs 3 / 5 in small: the CLIP pre-training nets (representation_only) with the text-anchor
+    cross-entropy as the head of `run_features` — incl. the learned anchor projection of 34CR_Proj"""
+    from oracle import losses_cpu
+    coords, feats, labels = scenes.synthetic_voxel_scene(seed=9, target_voxels=700)
+    c, f, lab = torch.from_numpy(coords), torch.from_numpy(feats), torch.from_numpy(labels)
+    torch.manual_seed(1)
+    anchors = torch.nn.functional.normalize(torch.randn(200, 512), dim=1)
+    res = {}
+    for mode in ("autograd", "program"):
+        torch.manual_seed(42)
+        net = nets.build_model(name, 3, 200, nets.DefaultConfig(), engine=me_cpu).train()
+        net.representation_only(True)
+        st = me_cpu.SparseTensor(f, c)
+
+        def head(x):
+            anc = net.projection_layer(anchors.unsqueeze(-1)).squeeze() if name.endswith("Proj") else anchors
+            return losses_cpu.clip_ce_loss(x, lab, anc, ignore_label=-1, reduction="mean")
+        if mode == "autograd":
+            out = net(st, anchors)[0] if name.endswith("Proj") else net(st)
+            loss = head(out.F)
+            loss.backward()
+        else:
+            loss = step.StepProgram(net, OracleBackend()).run_features(st, head)
+        res[mode] = (loss.item(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None})
+    a, p = res["autograd"], res["program"]
+    assert abs(a[0] - p[0]) < 1e-6 * abs(a[0]) and a[1].keys() == p[1].keys()
+    if name.endswith("Proj"):
+        assert "projection_layer.weight" in p[1]
+    worst = max(((p[1][k] - g).norm() / g.norm().clamp(min=1e-20)).item() for k, g in a[1].items())
+    assert worst < 1e-4, worst
+
+
 _TRACE = r'''
 import sys, re
 sys.path.insert(0, ROOT)
@@ -62,17 +96,28 @@ torch.manual_seed(0)
 net = nets.build_model(NAME, 3, 200, nets.DefaultConfig()).train()
 mgr = stub_engine.FakeManager(SIZES)
 lab = torch.randint(-1, 200, (SIZES[1],))
+anchors = torch.nn.functional.normalize(torch.randn(200, 512), dim=1)
+if net.flavour != "seg":
+    net.representation_only(True)
 prog = step.StepProgram(net)
 with _lib.trace() as t:
     for _ in range(2):
         for p in net.parameters():
             p.grad = None
-        if MODE == "facade":
-            out, _ = net(stub_engine.sparse_input(SIZES[1], 3, mgr))
-            losses._SegCEFn.apply(out.F, lab, -1).backward()
-        else:
-            with torch.no_grad():
+        if net.flavour == "seg":
+            if MODE == "facade":
+                out, _ = net(stub_engine.sparse_input(SIZES[1], 3, mgr))
+                losses._SegCEFn.apply(out.F, lab, -1).backward()
+            else:
                 prog.run(stub_engine.sparse_input(SIZES[1], 3, mgr), lab, -1)
+        else:
+            crit = losses.ContrastiveLanguageCELoss(num_labels=200, ignore_label=-1)
+            if MODE == "facade":
+                feat, anc = net(stub_engine.sparse_input(SIZES[1], 3, mgr), anchors)
+                crit(feat.F, lab, anc)[0].backward()
+            else:
+                prog.run_features(stub_engine.sparse_input(SIZES[1], 3, mgr),
+                                  lambda x: crit(x, lab, net.projection_layer(anchors.unsqueeze(-1)).squeeze())[0])
         assert not [k for k, p in net.named_parameters() if p.grad is None or p.grad.shape != p.shape]
         E.invalidate_weight_cache()              # what an optimiser step would do
 names = {}
@@ -94,7 +139,7 @@ print(*[re.sub(r"0x[0-9a-f]+|\(nil\)", canon, l) for l in t.lines], sep=chr(10))
 '''
 
 
-@pytest.mark.parametrize("name", ["Res16UNet34C", "Res16UNet14A"])
+@pytest.mark.parametrize("name", ["Res16UNet34C", "Res16UNet14A", "Res16UNet34CR_Proj"])
 def test_program_issues_the_facades_calls(lib, name):
     out = {}
     for mode in ("facade", "program"):
@@ -109,4 +154,4 @@ def test_program_issues_the_facades_calls(lib, name):
     a, b = a[len(a) // 2:], b[len(b) // 2:]
     for i, (x, y) in enumerate(zip(a, b)):
         assert x == y, (i, x, y)
-    assert sum(l.startswith("lgs_seg_ce") for l in a) == 1
+    assert sum(l.startswith("lgs_seg_ce" if name != "Res16UNet34CR_Proj" else "lgs_clip_ce_tc") for l in a) == 1
