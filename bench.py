@@ -173,6 +173,61 @@ def launch_work(meta, pair_cache):
     return flops, byts, P
 
 
+def roofline_report(prof, ms_per_step, algo, dtype, PROF_STEPS, pair_counts=None):
+    """`roofline` entry of the JSON line from the per-launch records [(meta, (start event, end event))] of PROF_STEPS
+    profiled steps (meta = kind, K, c_in, c_out, n_in, n_out, kernel map, feature dtype)."""
+    # Launches are grouped by (kernel kind, K, c_in, c_out, n_out); the group with the largest summed duration is "the
+    # dominant kernel".  achieved = SURVEY §8(d) gather-model bytes of ONE launch / its average CUDA-event duration.
+    hbm_gbs, tf_peak, peak_src = load_peaks()
+    pair_cache = {} if pair_counts is None else pair_counts
+    groups, agg = {}, {}
+    for meta, (a, b) in prof:
+        fl, by, _ = launch_work(meta, pair_cache)
+        dt_ms = a.elapsed_time(b)
+        kname = "wgrad" if meta[0] == "wgrad" else "conv"
+        d = agg.setdefault(kname, [0.0, 0.0, 0.0, 0])
+        d[0] += dt_ms; d[1] += by; d[2] += fl; d[3] += 1
+        g = groups.setdefault((kname,) + tuple(meta[1:6]), [0.0, by, fl, 0, meta[7]])
+        g[0] += dt_ms; g[3] += 1
+    if os.environ.get("LGS_BENCH_LAYERS"):
+        for key, g in sorted(groups.items(), key=lambda kv: -kv[1][0])[:40]:
+            print(f"LAYER {key[0]:6s} K={key[1]:2d} {key[2]:4d}->{key[3]:4d} n_out={key[5]:7d} launches/step={g[3] // PROF_STEPS:3d} "
+                  f"ms/step={g[0] / PROF_STEPS:7.3f}", file=sys.stderr)
+    step_flops = sum(v[2] for v in agg.values()) / PROF_STEPS
+    step_bytes = sum(v[1] for v in agg.values()) / PROF_STEPS
+    conv_ms, conv_bytes, conv_flops, conv_n = agg.get("conv", [1e-9, 0, 0, 1])
+    wg = agg.get("wgrad", [0, 0, 0, 0])
+    dom_key, dom = max(((k, g) for k, g in groups.items() if k[0] == "conv"), key=lambda kg: kg[1][0])
+    dom_ms = dom[0] / dom[3]
+    achieved = dom[1] / (dom_ms * 1e-3) / 1e9
+    # DRAM traffic of that launch from the committed `ncu --set full` capture (profiles/ncu_traffic.json), if present
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    shape_tag = f"conv K={dom_key[1]} {dom_key[2]}->{dom_key[3]} n_out={dom_key[5]} {algo} {dtype}"
+    traffic_src = None
+    if os.path.exists(tpath):
+        t = json.load(open(tpath)).get(f"K={dom_key[1]} {dom_key[2]}->{dom_key[3]} {algo} {dtype}")
+        if t:
+            traffic, traffic_src = t["bytes"], t["source"]      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch
+    roofline = {"bound": "hbm", "kernel": "conv_tc2_kernel (output-stationary gather -> tcgen05 GEMM, fwd and dgrad): " + shape_tag,
+                "achieved": round(achieved, 1), "peak": hbm_gbs, "unit": "GB/s", "frac": round(achieved / hbm_gbs, 4),
+                "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(dom[1]), "avg_launch_ms": round(dom_ms, 4), "launches_per_step": dom[3] // PROF_STEPS,
+                "share_of_step": round((dom[0] / PROF_STEPS) / ms_per_step, 3),
+                "tflops": round(dom[2] / (dom_ms * 1e-3) / 1e12, 2),
+                "timed_over": f"{PROF_STEPS} extra steps right after the timed region, CUDA events around every launch",
+                "all_conv_fwd_dgrad": {"share_of_step": round((conv_ms / PROF_STEPS) / ms_per_step, 3), "launches_per_step": conv_n // PROF_STEPS,
+                                       "achieved_gbs": round(conv_bytes / max(conv_ms, 1e-9) / 1e6, 1),
+                                       "tflops": round(conv_flops / max(conv_ms, 1e-9) / 1e9, 2)},
+                "all_wgrad": {"share_of_step": round((wg[0] / PROF_STEPS) / ms_per_step, 3),
+                              "achieved_gbs": round(wg[1] / max(wg[0], 1e-9) / 1e6, 1), "tflops": round(wg[2] / max(wg[0], 1e-9) / 1e9, 2)},
+                "step_model": {"gflop": round(step_flops / 1e9, 1), "gbyte": round(step_bytes / 1e9, 2),
+                               "hbm_floor_ms": round(step_bytes / hbm_gbs / 1e6, 3),
+                               "frac_of_floor": round((step_bytes / hbm_gbs / 1e6) / ms_per_step, 3)}}
+    return roofline
+
+
 def run_engine(args, rank, world, local_rank):
     from languagegroundedsemseg_b200 import _lib, minkowski as E
     from languagegroundedsemseg_b200.csrc import build as _build
@@ -360,56 +415,11 @@ def run_engine(args, rank, world, local_rank):
     if rank != 0:
         return None
 
-    # ---- roofline of the dominant kernel ------------------------------------------------------------------------
-    # Launches are grouped by (kernel kind, K, c_in, c_out, n_out); the group with the largest summed duration is "the
-    # dominant kernel".  achieved = SURVEY §8(d) gather-model bytes of ONE launch / its average CUDA-event duration.
-    hbm_gbs, tf_peak, peak_src = load_peaks()
-    pair_cache = {}
-    groups, agg = {}, {}
-    for meta, (a, b) in prof:
-        fl, by, _ = launch_work(meta, pair_cache)
-        dt_ms = a.elapsed_time(b)
-        kname = "wgrad" if meta[0] == "wgrad" else "conv"
-        d = agg.setdefault(kname, [0.0, 0.0, 0.0, 0])
-        d[0] += dt_ms; d[1] += by; d[2] += fl; d[3] += 1
-        g = groups.setdefault((kname,) + tuple(meta[1:6]), [0.0, by, fl, 0, meta[7]])
-        g[0] += dt_ms; g[3] += 1
-    if os.environ.get("LGS_BENCH_LAYERS"):
-        for key, g in sorted(groups.items(), key=lambda kv: -kv[1][0])[:40]:
-            print(f"LAYER {key[0]:6s} K={key[1]:2d} {key[2]:4d}->{key[3]:4d} n_out={key[5]:7d} launches/step={g[3] // PROF_STEPS:3d} "
-                  f"ms/step={g[0] / PROF_STEPS:7.3f}", file=sys.stderr)
-    step_flops = sum(v[2] for v in agg.values()) / PROF_STEPS
-    step_bytes = sum(v[1] for v in agg.values()) / PROF_STEPS
-    conv_ms, conv_bytes, conv_flops, conv_n = agg.get("conv", [1e-9, 0, 0, 1])
-    wg = agg.get("wgrad", [0, 0, 0, 0])
-    dom_key, dom = max(((k, g) for k, g in groups.items() if k[0] == "conv"), key=lambda kg: kg[1][0])
-    dom_ms = dom[0] / dom[3]
-    achieved = dom[1] / (dom_ms * 1e-3) / 1e9
-    # DRAM traffic of that launch from the committed `ncu --set full` capture (profiles/ncu_traffic.json), if present
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    shape_tag = f"conv K={dom_key[1]} {dom_key[2]}->{dom_key[3]} n_out={dom_key[5]} {args.algo} {args.dtype}"
-    traffic_src = None
-    if os.path.exists(tpath):
-        t = json.load(open(tpath)).get(f"K={dom_key[1]} {dom_key[2]}->{dom_key[3]} {args.algo} {args.dtype}")
-        if t:
-            traffic, traffic_src = t["bytes"], t["source"]      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch
-    roofline = {"bound": "hbm", "kernel": "conv_tc2_kernel (output-stationary gather -> tcgen05 GEMM, fwd and dgrad): " + shape_tag,
-                "achieved": round(achieved, 1), "peak": hbm_gbs, "unit": "GB/s", "frac": round(achieved / hbm_gbs, 4),
-                "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
-                "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(dom[1]), "avg_launch_ms": round(dom_ms, 4), "launches_per_step": dom[3] // PROF_STEPS,
-                "share_of_step": round((dom[0] / PROF_STEPS) / (ms / args.steps), 3),
-                "tflops": round(dom[2] / (dom_ms * 1e-3) / 1e12, 2),
-                "timed_over": f"{PROF_STEPS} extra steps right after the timed region, CUDA events around every launch",
-                "all_conv_fwd_dgrad": {"share_of_step": round((conv_ms / PROF_STEPS) / (ms / args.steps), 3), "launches_per_step": conv_n // PROF_STEPS,
-                                       "achieved_gbs": round(conv_bytes / max(conv_ms, 1e-9) / 1e6, 1),
-                                       "tflops": round(conv_flops / max(conv_ms, 1e-9) / 1e9, 2)},
-                "all_wgrad": {"share_of_step": round((wg[0] / PROF_STEPS) / (ms / args.steps), 3),
-                              "achieved_gbs": round(wg[1] / max(wg[0], 1e-9) / 1e6, 1), "tflops": round(wg[2] / max(wg[0], 1e-9) / 1e9, 2)},
-                "step_model": {"gflop": round(step_flops / 1e9, 1), "gbyte": round(step_bytes / 1e9, 2),
-                               "hbm_floor_ms": round(step_bytes / hbm_gbs / 1e6, 3),
-                               "frac_of_floor": round((step_bytes / hbm_gbs / 1e6) / (ms / args.steps), 3)}}
+    # ---- roofline of the dominant kernel (roofline_report above; a failure there must not lose the measured line) ------
+    try:
+        roofline = roofline_report(prof, ms / args.steps, args.algo, args.dtype, PROF_STEPS)
+    except Exception as e:  # noqa: BLE001
+        roofline = {"error": f"{type(e).__name__}: {e}"}
 
     value = tot_vox * args.steps / (ms * 1e-3)
     e2e_value = tot_vox * args.steps / (ms_e2e * 1e-3)

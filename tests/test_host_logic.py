@@ -197,3 +197,43 @@ if __name__ == "__main__":
         head = [l for l in open(path).read().splitlines() if l.startswith("#")]
         open(path, "w").write("\n".join(head + _one_step_trace()) + "\n")
         print("regenerated", path)
+
+
+def test_bench_roofline_report_on_synthetic_launch_records():
+    """bench.py's post-processing (the `roofline` object of the JSON line) on hand-made per-launch records: the dominant
+    group is the one with the largest summed time, achieved = gather-model bytes of one launch / its mean duration"""
+    import os
+    import sys
+    import types
+    import torch
+    sys_path_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if sys_path_root not in sys.path:
+        sys.path.insert(0, sys_path_root)
+    import bench
+
+    class Ev:
+        def __init__(self, t):
+            self.t = t
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+    km_l0 = types.SimpleNamespace(K=27)
+    km_l1 = types.SimpleNamespace(K=27)
+    pairs = {id(km_l0): 2_218_378, id(km_l1): 600_000}
+    prof = []
+    for step in range(2):
+        for _ in range(6):
+            prof.append((("fwd", 27, 96, 96, 149106, 149106, km_l0, torch.float32), (Ev(0.0), Ev(0.37))))
+        for _ in range(6):
+            prof.append((("dgrad", 27, 96, 96, 38506, 38506, km_l1, torch.float32), (Ev(0.0), Ev(0.14))))
+        for _ in range(3):
+            prof.append((("wgrad", 27, 96, 96, 149106, 149106, km_l0, torch.float32), (Ev(0.0), Ev(0.345))))
+        prof.append((("fwd", 1, 96, 200, 149106, 149106, None, torch.float32), (Ev(0.0), Ev(0.137))))
+    r = bench.roofline_report(prof, 16.0, "tc", "f32", 2, pair_counts=pairs)
+    by = 2_218_378 * (96 + 96) * 4 + 8 * 2_218_378 + 27 * 96 * 96 * 4
+    assert r["algorithmic_bytes_per_launch"] == by and r["launches_per_step"] == 6
+    assert abs(r["avg_launch_ms"] - 0.37) < 1e-9 and abs(r["achieved"] - by / 0.37e-3 / 1e9) < 0.1
+    assert "96->96" in r["kernel"] and r["bound"] == "hbm" and 0 < r["frac"] < 1.5
+    assert abs(r["share_of_step"] - 6 * 0.37 / 16.0) < 1e-3
+    assert r["all_wgrad"]["share_of_step"] == round(3 * 0.345 / 16.0, 3)
+    assert r["traffic"] is None or isinstance(r["traffic"], int)
