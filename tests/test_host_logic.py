@@ -150,15 +150,23 @@ def test_both_bindings_issue_identical_calls(lib):
         res[mode] = (out[0], out[1:])
     assert res["0"][0] == "ctypes" and res["1"][0] == "native"
     a, b = res["0"][1], res["1"][1]
-    assert len(a) == len(b) == 2 * (125 + 63 + 62 + 62 + 1 + 1)
+    per_step = 125 + 63 + 62 + 62 + 1 + 1
+    assert len(a) == len(b) == 2 * per_step
+    # the entry names and every non-pointer argument must agree over both steps; the NAMED pointers are compared on the
+    # second step only: in the first one a freed temporary can share its address with a persistent tensor allocated
+    # later (cached weight operands, tables), and which temporaries do differs from process to process
+    strip = lambda l: " ".join(t if (t[0].isdigit() or t[0] == "-" or t.startswith("lgs_")) else "P" for t in l.split())  # noqa: E731
+    for x, y in zip(a, b):
+        assert strip(x) == strip(y)
+    a, b = a[per_step:], b[per_step:]
     for x, y in zip(a, b):
         assert x == y
     names = [l.split()[0] for l in a]
-    assert names.count("lgs_conv_fwd") == 2 * (63 + 62) and names.count("lgs_conv_wgrad") == 2 * 63
-    assert names.count("lgs_bn_fwd") == names.count("lgs_bn_bwd") == 2 * 62 and names.count("lgs_weight_prep_batch") == 2
+    assert names.count("lgs_conv_fwd") == 63 + 62 and names.count("lgs_conv_wgrad") == 63
+    assert names.count("lgs_bn_fwd") == names.count("lgs_bn_bwd") == 62 and names.count("lgs_weight_prep_batch") == 1
     named = sum(tok not in ("A", "0") and not tok[0].isdigit() and not tok.startswith("lgs_") and not tok.startswith("-")
                 for l in a for tok in l.split())
-    assert named > 1500                  # parameters, buffers, weight operands, tables and scratch halves were all recognised
+    assert named > 750                   # parameters, buffers, weight operands, tables and scratch halves were all recognised
     # BatchNorm scratch halves alternate: the half a call clears is the half the next call accumulates into
     bn = [l.split() for l in a if l.startswith("lgs_bn_")]
     for prev, nxt in zip(bn, bn[1:]):
