@@ -431,7 +431,8 @@ def run_engine(args, rank, world, local_rank):
         "config": {"workload": workload_string(args.model, n_vox, args.voxel_size, args.voxels), "voxels_per_gpu": n_vox, "algo": args.algo,
                    "binding": _lib.binding() + " (Python -> C ABI)",
                    "driver": "StepProgram (explicit program, no autograd)" if args.step_program else "MinkowskiEngine facade + autograd",
-                   "math": {"tc": "tcgen05 3xTF32 products (fp32-grade) fwd/dgrad, TF32 wgrad, fp32 accumulate in TMEM",
+                   "math": {"bx3": "tcgen05 bf16x3 error-compensated products (2^-16) fwd/dgrad, TF32 wgrad, fp32 accumulate in TMEM",
+                            "tc": "tcgen05 3xTF32 products (2^-21) fwd/dgrad, TF32 wgrad, fp32 accumulate in TMEM",
                             "tf32": "tcgen05 single-pass TF32, fp32 accumulate", "simt": "fp32 FMA"}[args.algo]
                    if args.dtype == "f32" else "tcgen05 bf16 products, fp32 accumulate in TMEM",
                    "l2": "256 MB buffer written between steps (L2 flush); per-step activations >> 126 MB L2",
@@ -514,7 +515,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--algo", default="tc", choices=["tc", "tf32", "simt"])
+    ap.add_argument("--algo", default="bx3", choices=["bx3", "tc", "tf32", "simt"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--cpu-sample-voxels", type=int, default=60_000)
     ap.add_argument("--model", default=MODEL, help="topology (default: the BASELINE metric's Res16UNet34C)")

@@ -37,11 +37,15 @@ extern "C" {
 /* conv algorithms */
 #define LGS_ALGO_SIMT 0  /* fp32 FMA, exact: the parity anchor */
 #define LGS_ALGO_TC 1    /* tcgen05 tensor cores, TMEM accumulators (TF32 for LGS_F32 features, BF16 for LGS_BF16) */
-#define LGS_ALGO_TC3 2   /* tcgen05, 3xTF32 error-compensated products (hi*hi + lo*hi + hi*lo): fp32-grade, LGS_F32 only */
+#define LGS_ALGO_TC3 2   /* tcgen05, 3xTF32 error-compensated products (hi*hi + lo*hi + hi*lo): 2^-21 products, LGS_F32 only */
+#define LGS_ALGO_BX3 3   /* tcgen05, bf16x3 error-compensated products (bf16 hi/lo pairs, fp32 accumulate): 2^-16 products at half
+                            the tensor-core time and weight traffic of LGS_ALGO_TC3; LGS_F32 features only */
 /* weight layouts */
 #define LGS_W_KCN 0      /* [K, c_in, c_out]: MinkowskiEngine's parameter layout */
 #define LGS_W_KNC 1      /* [K, c_out, c_in]: per-offset transpose (the K-major B operand the tensor-core path loads by TMA) */
 #define LGS_W_KNC_SPLIT 2 /* [2, K, c_out, c_in]: TF32 hi / lo halves of LGS_W_KNC, for LGS_ALGO_TC3 (see lgs_weight_prep) */
+#define LGS_W_BX3 3      /* bf16 [K, c_out, ceil(c_in/32), 64]: per output channel and 32-channel block [hi x32 | lo x32],
+                            zero-padded channels, for LGS_ALGO_BX3 (lgs_weight_prep with nsplit = 3) */
 
 int lgs_version(void);
 const char* lgs_last_error(void);
@@ -56,6 +60,11 @@ int lgs_trace_begin(void);
 int64_t lgs_trace_end(char* buf, int64_t capacity);
 /* 1 if the library was built with the tcgen05 path */
 int lgs_has_tc(void);
+/* Override a work-decomposition heuristic of the tensor-core kernels (tests and tuning; 0 restores the heuristic).
+ * Keys: "bx3_tm" (row tiles per CTA), "bx3_rt" (rows per tile), "bx3_ks" (kernel-offset splits), "bx3_ns" (output-channel
+ * slices), "bx3_sa" (gather ring depth), "bx3_no_balance".  Process-wide; the same knobs are read once from the environment
+ * variables LGS_BX3_TM ... at first use. */
+int lgs_tune(const char* key, int32_t value);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Coordinate maps.   Replaces ME CoordinateMapManagerGPU_c10::insert_and_map / ::stride
@@ -109,6 +118,9 @@ int lgs_conv_tc_supported(int32_t c_in, int32_t c_out, int32_t dtype);
  * Outputs have the feature dtype.  (ME keeps one fp32 [K,Cin,Cout] kernel and re-reads it per offset.) */
 int lgs_weight_prep(const float* d_weight, int32_t K, int32_t c_in, int32_t c_out, int32_t nsplit,
                     void* d_fwd, void* d_bwd, int32_t dtype, void* stream);
+/*   nsplit 3 (dtype LGS_F32): the LGS_W_BX3 operand forms, bf16 elements:
+ *   d_fwd [K, c_out, ceil(c_in/32), 64], d_bwd [K, c_in, ceil(c_out/32), 64]; lgs_weight_bx3_elems(K, rows, reduced) each. */
+int64_t lgs_weight_bx3_elems(int32_t K, int32_t c_rows, int32_t c_reduced);
 
 /* The same for every layer of a network in ONE launch (63 per-layer launches per Res16UNet34C step otherwise).
  *   d_desc: device int64 [n_layers][8] = { d_weight, d_fwd, d_bwd (0 = skip), K, c_in, c_out, first_tile, 0 } where a
@@ -134,6 +146,17 @@ int lgs_conv_fwd(const void* d_in, int64_t n_in, int32_t c_in,
                  const void* d_weight, int32_t weight_layout, int32_t K, int32_t c_out,
                  const int32_t* d_table, int64_t n_out, int32_t reverse_k,
                  const float* d_bias, void* d_out, int32_t dtype, int32_t algo, void* stream);
+
+/* LGS_ALGO_BX3 with its two extensions (fp32 features, LGS_W_BX3 weights of the full input width c_in + c_in2):
+ *   - two gather sources: input channels [0, c_in) come from d_in [n_in, c_in], channels [c_in, c_in + c_in2) from d_in2
+ *     [n_in, c_in2] (c_in % 32 == 0) — the convolution of cat(d_in, d_in2) without materialising the concatenation
+ *     (ME.cat at models/res16unet.py:237,247,257,267 feeding block5..block8).  c_in2 == 0: one source.
+ *   - d_bn_sums (may be NULL): BatchNorm accumulators [8][2][c_out] doubles (the d_scratch layout of lgs_bn_fwd, zero on
+ *     entry) that receive the column sums and sums of squares of the OUTPUT from the accumulator registers, so the
+ *     BatchNorm that follows (models/modules/common.py:17-19) needs no statistics pass: lgs_bn_fwd(..., stats_ready).  */
+int lgs_conv_fwd2(const float* d_in, int32_t c_in, const float* d_in2, int32_t c_in2, int64_t n_in, const void* d_weight,
+                  int32_t K, int32_t c_out, const int32_t* d_table, int64_t n_out, int32_t reverse_k, const float* d_bias,
+                  float* d_out, double* d_bn_sums, void* stream);
 
 /* grad_w[k] = sum_o in[table[k][o], :]^T (outer) grad_out[o, :]   -> fp32 [K,c_in,c_out], overwritten. */
 int lgs_conv_wgrad(const void* d_in, int64_t n_in, int32_t c_in,

@@ -8,8 +8,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liblgs_b200.so")
 
 OK, E_INVALID, E_CUDA, E_RANGE, E_HASH_FULL, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 F32, BF16 = 0, 1
-ALGO_SIMT, ALGO_TC, ALGO_TC3 = 0, 1, 2
-W_KCN, W_KNC, W_KNC_SPLIT = 0, 1, 2
+ALGO_SIMT, ALGO_TC, ALGO_TC3, ALGO_BX3 = 0, 1, 2, 3
+W_KCN, W_KNC, W_KNC_SPLIT, W_BX3 = 0, 1, 2, 3
 
 _p, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 
@@ -21,6 +21,7 @@ SIGNATURES = {
     "lgs_trace_begin": (C.c_int, []),
     "lgs_trace_end": (_i64, [C.c_char_p, _i64]),
     "lgs_has_tc": (C.c_int, []),
+    "lgs_tune": (C.c_int, [C.c_char_p, _i32]),
     "lgs_coord_limit": (_i32, []),
     "lgs_hash_capacity": (_i64, [_i64]),
     "lgs_coordmap_scratch_elems": (_i64, [_i64]),
@@ -31,6 +32,8 @@ SIGNATURES = {
     "lgs_weight_prep": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _i32, _p]),
     "lgs_weight_prep_batch": (C.c_int, [_p, _i32, _i64, _i32, _i32, _p]),
     "lgs_conv_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i32, _p, _i64, _i32, _p, _p, _i32, _i32, _p]),
+    "lgs_conv_fwd2": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _i32, _p, _i64, _i32, _p, _p, _p, _p]),
+    "lgs_weight_bx3_elems": (_i64, [_i32, _i32, _i32]),
     "lgs_conv_wgrad": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _p, _i32, _p, _i32, _i32, _p]),
     "lgs_bn_fwd": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _f32, _f32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "lgs_bn_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),

@@ -111,7 +111,8 @@ class _SegCEFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss):
         (g,) = ctx.saved_tensors
-        return (g.mul_(gloss) if g is not None else None), None, None     # g is this node's own buffer
+        # out of place: a second backward through this node (retain_graph, two losses sharing it) must see the same `g`
+        return (g * gloss if g is not None else None), None, None
 
 
 def cross_entropy(input, target, ignore_index=-100):
@@ -136,6 +137,11 @@ class CrossEntropyLoss(nn.Module):
 
 
 class _ClipHingeFn(torch.autograd.Function):
+    """per-point hinge loss  total_i = pos_i + neg_weight * neg_i  (differentiable) and its two parts (for logging).
+    Gradients: features from the kernel; anchors as a scatter-add of coef * normalize(F_i) rows —
+    d pos_i / dA[y_i] = -[pos_i > 0] F^_i,  d neg_i / dA[n_ij] = [neg_i > 0] F^_i / n_neg  (ContrastiveLanguageLoss.py:
+    184-192 backpropagates through `anchor_feats`, which trains `projection_layer` of Res16UNet34CR_Proj)."""
+
     @staticmethod
     def forward(ctx, feats, anchors_n, labels, neg_ids, ignore_label, pos_thresh, neg_thresh, neg_weight):
         lib = _lib.load()
@@ -151,20 +157,27 @@ class _ClipHingeFn(torch.autograd.Function):
                                       _lib.ptr(neg_ids), neg_ids.shape[1], int(ignore_label), float(pos_thresh),
                                       float(neg_thresh), float(neg_weight), _lib.ptr(pos), _lib.ptr(neg),
                                       _lib.ptr(gf), _stream()))
-        ctx.save_for_backward(gf, pos, neg)
-        ctx.neg_weight = float(neg_weight)
-        return pos, neg
+        ctx.save_for_backward(gf, pos, neg, feats, labels, neg_ids)
+        ctx.neg_weight, ctx.n_anchors, ctx.ignore = float(neg_weight), anchors_n.shape[0], int(ignore_label)
+        ctx.mark_non_differentiable(pos, neg)
+        return pos + float(neg_weight) * neg, pos, neg
 
     @staticmethod
-    def backward(ctx, gpos, gneg):
-        # the kernel's gradient is d(pos + neg_weight*neg)/dF; callers combine the two outputs that way
-        gf, pos, neg = ctx.saved_tensors
-        if gf is None:
-            return (None,) * 8
-        # d pos/dF and d neg/dF are both folded into gf with weights (1, neg_weight); rescale by upstream grads
-        # when they are the uniform weights of the reference's reductions (mean / none).
-        w = gpos[:, None]
-        return gf * w, None, None, None, None, None, None, None
+    def backward(ctx, gtot, _gpos, _gneg):
+        gf, pos, neg, feats, labels, neg_ids = ctx.saved_tensors
+        g_feats = gf * gtot[:, None] if (gf is not None and ctx.needs_input_grad[0]) else None
+        g_anch = None
+        if ctx.needs_input_grad[1]:
+            fh = F.normalize(feats, p=2, dim=1)
+            valid = labels != ctx.ignore
+            g_anch = torch.zeros((ctx.n_anchors, feats.shape[1]), dtype=torch.float32, device=feats.device)
+            cp = torch.where(valid & (pos > 0), -gtot, torch.zeros_like(gtot))
+            g_anch.index_add_(0, labels.clamp(min=0), fh * cp[:, None])
+            n_neg = neg_ids.shape[1]
+            cn = torch.where(valid & (neg > 0), gtot * (ctx.neg_weight / n_neg), torch.zeros_like(gtot))
+            for j in range(n_neg):
+                g_anch.index_add_(0, neg_ids[:, j].long(), fh * cn[:, None])
+        return g_feats, g_anch, None, None, None, None, None, None
 
 
 class ContrastiveLanguageLoss(nn.Module):
@@ -178,6 +191,8 @@ class ContrastiveLanguageLoss(nn.Module):
         self.ignore_label = ignore_label if ignore_label is not None else g("ignore_label", -1)
         self.num_labels, self.reduction = num_labels, reduction
         self.num_negative_samples = g("num_negative_samples", num_negative_samples)
+        if self.num_negative_samples < 0:      # 'use all labels' (ContrastiveLanguageLoss.py:33-36)
+            self.num_negative_samples = num_labels
         self.pos_thresh = g("contrast_pos_thresh", pos_thresh)
         self.neg_thresh = g("contrast_neg_thresh", neg_thresh)
         self.neg_weight = g("contrast_neg_weight", neg_weight)
@@ -196,13 +211,9 @@ class ContrastiveLanguageLoss(nn.Module):
         if neg_ids is None:
             neg_ids = self.sample_negatives(labels)
         an = F.normalize(anchor_feats.float(), p=2, dim=1)
-        pos, neg = _ClipHingeFn.apply(features, an, labels, neg_ids, self.ignore_label, self.pos_thresh,
-                                      self.neg_thresh, self.neg_weight)
-        if self.reduction == "mean":
-            # loss = pos.mean() + w*neg.mean(): route the whole gradient through `pos` (see _ClipHingeFn.backward)
-            loss = pos.mean() + (neg.detach() * self.neg_weight).mean()
-        else:
-            loss = pos + neg.detach() * self.neg_weight
+        total, pos, neg = _ClipHingeFn.apply(features, an, labels, neg_ids, self.ignore_label, self.pos_thresh,
+                                             self.neg_thresh, self.neg_weight)
+        loss = total.mean() if self.reduction == "mean" else total      # = pos.mean() + w * neg.mean()
         return loss, pos, neg
 
 

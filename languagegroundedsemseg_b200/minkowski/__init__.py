@@ -42,10 +42,12 @@ for _n in ("Sequence", "Iterable"):
 # engine-wide settings
 # ----------------------------------------------------------------------------------------------------------
 # 'simt'  exact fp32 FMA kernels (parity anchor, slow)
-# 'tc'    tcgen05 tensor cores, parity-grade: 3xTF32 products for fp32 features (bf16 MMA for bf16 features)  [default]
-# 'tf32'  tcgen05 single-pass TF32 (fast, ~7e-4 relative error per layer)
-_ALGO = {"simt": _lib.ALGO_SIMT, "tc": _lib.ALGO_TC3, "tf32": _lib.ALGO_TC}
-_state = {"algo": _lib.ALGO_TC3, "profile": None, "fuse_bn": True,
+# 'bx3'   tcgen05 tensor cores, parity-grade: bf16x3 error-compensated products for fp32 features (2^-16 per product,
+#         fp32 accumulate; whole-net logits ~1e-4 of the fp32 reference); bf16 MMA for bf16 features             [default]
+# 'tc'    tcgen05 3xTF32 products (2^-21 per product) at twice the tensor-core time and weight traffic of 'bx3'
+# 'tf32'  tcgen05 single-pass TF32 (fast, ~7e-4 relative error per layer; not parity grade)
+_ALGO = {"simt": _lib.ALGO_SIMT, "tc": _lib.ALGO_TC3, "tf32": _lib.ALGO_TC, "bx3": _lib.ALGO_BX3}
+_state = {"algo": _ALGO[os.environ.get("LGS_CONV_ALGO", "bx3")], "profile": None, "fuse_bn": True,
           # conv -> BatchNorm (+ residual) (+ ReLU) as ONE autograd node (the conv is evaluated lazily); kernels unchanged
           "fuse_conv_bn": os.environ.get("LGS_FUSE_CONV_BN", "1") != "0",
           # backward: wgrad on a side stream while dgrad runs on the training stream (joined before the node returns)
@@ -104,7 +106,7 @@ class _Timed:
 
 
 def set_conv_algo(name: str):
-    """'simt' exact fp32 FMA | 'tc' tcgen05 3xTF32 (default, fp32-grade) | 'tf32' tcgen05 single-pass TF32."""
+    """'simt' exact fp32 FMA | 'bx3' tcgen05 bf16x3 (default, parity grade) | 'tc' tcgen05 3xTF32 | 'tf32' single-pass TF32."""
     _state["algo"] = _ALGO[name]
 
 
@@ -754,8 +756,8 @@ class _WeightPrep:
                 continue
             bufs = m._prep_bufs.get((dt, nsplit))
             if bufs is None or bufs[2] != w.data_ptr():
-                fb = torch.empty((nsplit, K, c_out, c_in), dtype=tdtype, device=device) if f_ok else None
-                bb = torch.empty((nsplit, K, c_in, c_out), dtype=tdtype, device=device) if b_ok else None
+                fb = _operand_buffer(lib, nsplit, K, c_out, c_in, tdtype, device) if f_ok else None
+                bb = _operand_buffer(lib, nsplit, K, c_in, c_out, tdtype, device) if b_ok else None
                 bufs = m._prep_bufs[(dt, nsplit)] = (fb, bb, w.data_ptr())
             entries.append((m, w, K, c_in, c_out, bufs[0], bufs[1]))
         if not entries:
@@ -792,6 +794,13 @@ class _ConvMeta:
     __slots__ = ("km", "algo", "bwd_tc", "tc_layout", "dims", "w_shape", "w_dtype", "has_bias", "c_in_true")
 
 
+def _operand_buffer(lib, nsplit, K, rows, red, dtype, device):
+    """tensor-core weight operand of one direction: [nsplit, K, rows, red] in the feature dtype, or the LGS_W_BX3 form"""
+    if nsplit == 3:
+        return torch.empty(lib.lgs_weight_bx3_elems(K, rows, red), dtype=torch.bfloat16, device=device)
+    return torch.empty((nsplit, K, rows, red), dtype=dtype, device=device)
+
+
 def _conv_fwd_impl(feats, weight, bias, km, algo, need_dgrad, module=None):
     """one convolution launch (+ weight operand prep); returns (out, feats as saved for wgrad, dgrad weights, meta)"""
     lib = _lib.load()
@@ -800,7 +809,7 @@ def _conv_fwd_impl(feats, weight, bias, km, algo, need_dgrad, module=None):
     w3 = weight.view(1, *weight.shape) if weight.dim() == 2 else weight
     K, c_in, c_out = w3.shape
     dt = _lib.F32 if feats.dtype is torch.float32 else _dtype_code(feats)
-    if algo == _lib.ALGO_TC3 and dt == _lib.BF16:
+    if (algo == _lib.ALGO_TC3 or algo == _lib.ALGO_BX3) and dt == _lib.BF16:
         algo = _lib.ALGO_TC                                   # bf16 features: plain bf16 tensor-core products
     n_in = feats.shape[0]
     n_out = km.n_out if km is not None else n_in
@@ -827,7 +836,7 @@ def _conv_fwd_impl(feats, weight, bias, km, algo, need_dgrad, module=None):
     # exact SIMT kernel with the parameter itself
     fwd_tc = algo != _lib.ALGO_SIMT and _tc_supported(lib, c_in, c_out, dt)
     bwd_tc = algo != _lib.ALGO_SIMT and need_dgrad and _tc_supported(lib, c_out, c_in, dt)
-    nsplit = 2 if algo == _lib.ALGO_TC3 else 1
+    nsplit = 3 if algo == _lib.ALGO_BX3 else (2 if algo == _lib.ALGO_TC3 else 1)
     w_fwd = w_bwd = None
     if fwd_tc or bwd_tc:
         pre = None
@@ -838,13 +847,13 @@ def _conv_fwd_impl(feats, weight, bias, km, algo, need_dgrad, module=None):
             w_fwd, w_bwd = pre[0], (pre[1] if bwd_tc else None)
         else:
             if fwd_tc:
-                w_fwd = torch.empty((nsplit, K, c_out, c_in), dtype=feats.dtype, device=feats.device)
+                w_fwd = _operand_buffer(lib, nsplit, K, c_out, c_in, feats.dtype, feats.device)
             if bwd_tc:
-                w_bwd = torch.empty((nsplit, K, c_in, c_out), dtype=feats.dtype, device=feats.device)
+                w_bwd = _operand_buffer(lib, nsplit, K, c_in, c_out, feats.dtype, feats.device)
             w32 = weights32()
             _lib.check(lib.lgs_weight_prep(_lib.ptr(w32), K, c_in, c_out, nsplit, _lib.ptr(w_fwd), _lib.ptr(w_bwd), dt,
                                            _stream()))
-    tc_layout = _lib.W_KNC_SPLIT if nsplit == 2 else _lib.W_KNC
+    tc_layout = _lib.W_BX3 if nsplit == 3 else (_lib.W_KNC_SPLIT if nsplit == 2 else _lib.W_KNC)
     if fwd_tc:
         wf, layout, a = w_fwd, tc_layout, algo
     else:

@@ -82,15 +82,19 @@ def test_clip_hinge_vs_oracle(L):
     crit = L.ContrastiveLanguageLoss(num_labels=200)
     neg = crit.sample_negatives(y.cuda())
     assert torch.all(neg.cpu() != y.clamp(min=0)[:, None]) and neg.min() >= 0 and neg.max() < 200
-    Fo = F_.clone().requires_grad_(True)
-    lo, po, no = losses_cpu.clip_hinge_loss(Fo, y, A, neg.cpu())
+    Fo, Ao = F_.clone().requires_grad_(True), A.clone().requires_grad_(True)
+    lo, po, no = losses_cpu.clip_hinge_loss(Fo, y, Ao, neg.cpu())
     lo.backward()
-    Fg = F_.cuda().requires_grad_(True)
-    lg, pg, ng = crit(Fg, y.cuda(), A.cuda(), neg_ids=neg)
+    Fg, Ag = F_.cuda().requires_grad_(True), A.cuda().requires_grad_(True)
+    lg, pg, ng = crit(Fg, y.cuda(), Ag, neg_ids=neg)
     lg.backward()
     assert abs(lg.item() - lo.item()) < 1e-5
     assert rel_err(pg.cpu(), po) < 1e-5 and rel_err(ng.cpu(), no) < 1e-5
     assert rel_err(Fg.grad.cpu(), Fo.grad) < 1e-4
+    # the anchors get their gradient too (it trains projection_layer of Res16UNet34CR_Proj, clip_models.py:197-200)
+    assert Ag.grad is not None and rel_err(Ag.grad.cpu(), Ao.grad) < 1e-4
+    # 'use all labels' setting of the reference (ContrastiveLanguageLoss.py:33-36)
+    assert L.ContrastiveLanguageLoss(num_labels=200, num_negative_samples=-1).num_negative_samples == 200
 
 
 @pytest.mark.parametrize("n,c,a", [(1, 96, 200), (127, 96, 200), (129, 16, 20), (1000, 100, 200), (333, 512, 200),

@@ -1,5 +1,7 @@
 """CPU tests of the facade's host logic against a stub of the C-ABI library (tests/stub_engine.py): no arithmetic, but
 the autograd plumbing, call counts and cache-invalidation rules are the real code."""
+import os
+
 import pytest
 import torch
 
@@ -87,22 +89,39 @@ def test_weight_operand_cache_invalidation(stub):
 
 
 _TRACE_PROBE = r'''
-import sys, re
+import os, sys, re, types
 sys.path.insert(0, ROOT)
 import torch
 from tests import stub_engine
 from languagegroundedsemseg_b200 import _lib, minkowski as E, nets
 stub_engine.install(setattr, real_library=True)
 SIZES = {1: 600, 2: 200, 4: 70, 8: 25, 16: 9}
+MODEL = os.environ.get("LGS_PROBE_MODEL", "Res16UNet34C")
 torch.manual_seed(0)
-net = nets.build_model("Res16UNet34C", 3, 200, nets.DefaultConfig()).train()
+if os.environ.get("LGS_PROBE_REFERENCE"):
+    # the reference's own, unmodified models/ package over the facade installed as `MinkowskiEngine`
+    import languagegroundedsemseg_b200 as lgs
+    lgs.install_as_minkowski()
+    sys.path.insert(0, os.environ["LGS_PROBE_REFERENCE"])
+    import models
+    cfg = types.SimpleNamespace(bn_momentum=0.02, conv1_kernel_size=3, dilations=[1, 1, 1, 1])
+    net = models.load_model(MODEL)(3, 200, cfg).train()
+else:
+    net = nets.build_model(MODEL, 3, 200, nets.DefaultConfig()).train()
 opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9)
 mgr = stub_engine.FakeManager(SIZES)
+anchors = torch.randn(200, 512)
 with _lib.trace() as t:
     for _ in range(2):
-        out, _ = net(stub_engine.sparse_input(SIZES[1], 3, mgr))
+        x = stub_engine.sparse_input(SIZES[1], 3, mgr)
+        if MODEL == "Res16UNet34CR_Proj":
+            (out, _), proj = net(x, anchors)
+            extra = proj.float().mean()
+        else:
+            out, _ = net(x)
+            extra = 0.0
         opt.zero_grad(set_to_none=True)
-        out.F.float().mean().backward()
+        (out.F.float().mean() + extra).backward()
         opt.step()
 # canonical form (addresses differ from process to process and the allocator re-uses them): a pointer that is the address
 # of a persistent tensor — parameter, buffer, cached weight operand, neighbour table, BatchNorm scratch half — becomes that
@@ -175,15 +194,21 @@ def test_both_bindings_issue_identical_calls(lib):
         assert p_next == n_acc and p_next.startswith("bn_scratch")
 
 
-def _one_step_trace(mode="0"):
+def _one_step_trace(mode="0", model="Res16UNet34C", reference=None):
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LGS_FAST_BIND=mode, LGS_PROBE_MODEL=model)
+    env.pop("LGS_PROBE_REFERENCE", None)
+    if reference:
+        env["LGS_PROBE_REFERENCE"] = reference
     r = subprocess.run([sys.executable, "-c", f"ROOT={root!r}\n" + _TRACE_PROBE], capture_output=True, text=True,
-                       env=dict(os.environ, LGS_FAST_BIND=mode), timeout=600)
+                       env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
-    return r.stdout.strip().splitlines()[1:][314:]          # the second (steady-state) step
+    lines = r.stdout.strip().splitlines()[1:]
+    assert len(lines) % 2 == 0
+    return lines[len(lines) // 2:]          # the second (steady-state) step
 
 
 def test_facade_call_sequence_is_the_committed_one(lib, golden_dir):
@@ -195,6 +220,28 @@ def test_facade_call_sequence_is_the_committed_one(lib, golden_dir):
     assert len(got) == len(want) == 314
     for i, (g, w) in enumerate(zip(got, want)):
         assert g == w, (i, g, w)
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), reason="reference checkout not present")
+@pytest.mark.parametrize("model", ["Res16UNet34C", "Res16UNet14A", "Res16UNet34CR_Proj", "Res16UNet34D"])
+def test_reference_models_run_through_the_facade_like_nets(lib, golden_dir, model):
+    """The drop-in claim, exercised: the reference's UNMODIFIED models/ package (models/res16unet.py:196-270,
+    models/clip_models.py:95-215, models/modules/resnet_block.py:41-57) runs forward + backward + SGD through the facade
+    installed as `MinkowskiEngine`, with the library recording every C-ABI call, and must issue exactly the call sequence
+    nets.py issues for the same topology — same entry points, sizes, flags, tables, weight operands, BatchNorm tensors.
+    This fails if the lazy conv / BatchNorm deferral reacts differently to the reference's own call pattern (separate
+    module calls, `out += residual`, NoReluBlock, me.cat).  For Res16UNet34C that sequence is also the committed golden."""
+    got = _one_step_trace(model=model, reference=REF)
+    mine = _one_step_trace(model=model)
+    assert len(got) == len(mine) > 150
+    for i, (g, w) in enumerate(zip(got, mine)):
+        assert g == w, (i, g, w)
+    if model == "Res16UNet34C":
+        want = [l for l in open(os.path.join(golden_dir, "facade_trace_unet34c.txt")).read().splitlines() if not l.startswith("#")]
+        assert got == want
 
 
 if __name__ == "__main__":
