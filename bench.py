@@ -128,13 +128,22 @@ def _aten_criterion(logits, labels):
     return torch.nn.functional.cross_entropy(logits.float(), labels, ignore_index=-1)
 
 
-def train_step(ST, net, opt, coords, feats, labels, reducer=None, st=None, criterion=_aten_criterion, program=None):
+def train_step(ST, net, opt, coords, feats, labels, reducer=None, st=None, criterion=_aten_criterion, program=None, native=None):
     if st is None:
         st = ST(feats, coords)                               # pl_BaselineTrainer.py:300
+    if native is not None:
+        # default driver: the whole forward + loss + backward is ONE C-ABI call (languagegroundedsemseg_b200/program.py);
+        # gradients are written into the flat gradient buffer, the all-reduce buckets go out from inside run()
+        loss = native.run(st, labels)
+        opt.step()
+        return loss
     if program is not None:
         # opt-in (--step-program): forward + loss + backward as one explicit program over the same entry points
         # (languagegroundedsemseg_b200/step.py), no autograd graph / module dispatch
-        opt.zero_grad(set_to_none=True)
+        if reducer is not None:
+            reducer.zero_grad()
+        else:
+            opt.zero_grad(set_to_none=True)
         with torch.no_grad():
             loss = program.run(st, labels, ignore_index=-1)
         if reducer is not None:
@@ -143,7 +152,10 @@ def train_step(ST, net, opt, coords, feats, labels, reducer=None, st=None, crite
         return loss
     out, _ = net(st)                                         # res16unet.py:196
     loss = criterion(out.F, labels)                          # :350  CrossEntropyLoss(ignore_index)
-    opt.zero_grad(set_to_none=True)
+    if reducer is not None:
+        reducer.zero_grad()                                  # gradients are views of the reducer's flat buffer: one memset
+    else:
+        opt.zero_grad(set_to_none=True)
     loss.backward()
     if reducer is not None:
         reducer()                                            # N > 1: the only collective (flat NCCL gradient all-reduce)
@@ -263,7 +275,8 @@ def run_engine(args, rank, world, local_rank):
         pass
     from languagegroundedsemseg_b200 import ddp
     model = net
-    reducer = ddp.GradAllReducer(net.parameters()) if world > 1 else None   # same seed on every rank => same init
+    # same seed on every rank => same init; the native driver launches the buckets itself, the facade path through hooks
+    reducer = ddp.GradAllReducer(net.parameters(), overlap=args.driver != "native") if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -284,21 +297,26 @@ def run_engine(args, rank, world, local_rank):
     # the engine's fused softmax cross-entropy (lgs_seg_ce: one pass over the logits) unless LGS_ATEN_CE=1
     crit = _aten_criterion if os.environ.get("LGS_ATEN_CE") else (lambda x, y: lgs_losses.cross_entropy(x, y, ignore_index=-1))
 
-    program = None
+    program = native = None
     if args.step_program:
         from languagegroundedsemseg_b200.step import StepProgram
         program = StepProgram(model)
+    elif args.driver == "native" and args.dtype == "f32" and args.algo == "bx3":
+        from languagegroundedsemseg_b200.program import NativeStep
+        if reducer is None:
+            reducer = ddp.GradAllReducer(net.parameters(), overlap=False)
+        native = NativeStep(model, ignore_index=-1, reducer=reducer)
 
     def staged_step(key, src):
         flush.fill_(0.0)
         if pf is None:
             c, f, lab = (t.to(dev, non_blocking=True) for t in src)
-            return train_step(E.SparseTensor, model, opt, c, f.to(fdtype), lab, reducer, criterion=crit, program=program)
+            return train_step(E.SparseTensor, model, opt, c, f.to(fdtype), lab, reducer, criterion=crit, program=program, native=native)
         if key not in tickets:
             tickets[key] = pf.stage(*src)
         st, lab = pf.get(tickets[key])
         tickets[key] = pf.stage(*src)                        # next step's batch, overlapped with this step
-        return train_step(None, model, opt, None, None, lab, reducer, st=st, criterion=crit, program=program)
+        return train_step(None, model, opt, None, None, lab, reducer, st=st, criterion=crit, program=program, native=native)
 
     def resident_step():
         return staged_step("resident", (d_coords, d_feats, d_labels))
@@ -430,7 +448,9 @@ def run_engine(args, rank, world, local_rank):
         "vs_baseline": None, "dtype": "f32" if args.dtype == "f32" else "bf16", "data": "synthetic",
         "config": {"workload": workload_string(args.model, n_vox, args.voxel_size, args.voxels), "voxels_per_gpu": n_vox, "algo": args.algo,
                    "binding": _lib.binding() + " (Python -> C ABI)",
-                   "driver": "StepProgram (explicit program, no autograd)" if args.step_program else "MinkowskiEngine facade + autograd",
+                   "driver": ("StepProgram (explicit program, no autograd)" if args.step_program else
+                              "native step driver (one lgs_program_run per step, languagegroundedsemseg_b200/program.py)" if native is not None
+                              else "MinkowskiEngine facade + autograd"),
                    "math": {"bx3": "tcgen05 bf16x3 error-compensated products (2^-16) fwd/dgrad, TF32 wgrad, fp32 accumulate in TMEM",
                             "tc": "tcgen05 3xTF32 products (2^-21) fwd/dgrad, TF32 wgrad, fp32 accumulate in TMEM",
                             "tf32": "tcgen05 single-pass TF32, fp32 accumulate", "simt": "fp32 FMA"}[args.algo]
@@ -523,6 +543,9 @@ def main():
     ap.add_argument("--voxel-size", type=float, default=0.02)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="build the coordinate manager on the training stream")
+    ap.add_argument("--driver", default="native", choices=["native", "facade"],
+                    help="native: forward + loss + backward as one lgs_program_run per step (default; fp32 / bx3); facade: the "
+                         "reference's module-by-module path through the MinkowskiEngine facade and autograd")
     ap.add_argument("--step-program", action="store_true",
                     help="forward + loss + backward through languagegroundedsemseg_b200.step.StepProgram (explicit program over "
                          "the same C-ABI calls, no autograd graph) instead of the module-by-module facade")

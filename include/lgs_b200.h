@@ -181,6 +181,12 @@ int lgs_bn_fwd(const float* d_x, const float* d_residual, int64_t n, int32_t c, 
                float eps, float momentum, int32_t relu, float* d_running_mean, float* d_running_var, float* d_z,
                float* d_save_mean, float* d_save_invstd, double* d_scratch, double* d_scratch_next,
                int64_t* d_num_batches_tracked, void* stream);
+/* lgs_bn_fwd with stats_ready != 0: d_scratch already holds the column sums / sums of squares of d_x in the accumulator
+ * layout ([8][2][c] doubles; lgs_conv_fwd2 writes them from the convolution's epilogue), so only the apply kernel runs. */
+int lgs_bn_fwd2(const float* d_x, const float* d_residual, int64_t n, int32_t c, const float* d_gamma, const float* d_beta,
+                float eps, float momentum, int32_t relu, float* d_running_mean, float* d_running_var, float* d_z,
+                float* d_save_mean, float* d_save_invstd, double* d_scratch, double* d_scratch_next,
+                int64_t* d_num_batches_tracked, int32_t stats_ready, void* stream);
 int lgs_bn_bwd(const float* d_x, const float* d_z, const float* d_dz, int64_t n, int32_t c, const float* d_gamma,
                const float* d_save_mean, const float* d_save_invstd, int32_t relu, float* d_dx, float* d_dresidual,
                float* d_dgamma, float* d_dbeta, double* d_scratch, double* d_scratch_next, void* stream);
@@ -233,6 +239,50 @@ int lgs_clip_hinge(const float* d_feats, int64_t n, int32_t c, const float* d_an
  * --------------------------------------------------------------------------------------------------------- */
 int lgs_voxelize_affine(const float* d_xyz, int64_t n, const double* h_M, int32_t batch, int32_t* d_coords,
                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Row-wise helpers (fp32): strided 2-D copy (ME.cat at models/res16unet.py:237-267 and its backward split, channel padding),
+ * elementwise sum of two gradient matrices, column sums (bias gradient of `final`, models/res16unet.py:193).
+ * --------------------------------------------------------------------------------------------------------- */
+int lgs_copy2d(const float* d_src, int64_t src_ld, float* d_dst, int64_t dst_ld, int64_t rows, int32_t cols, void* stream);
+int lgs_add(const float* d_a, const float* d_b, float* d_out, int64_t n, void* stream);
+int lgs_colsum(const float* d_g, int64_t rows, int32_t c, float* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Native step driver.   Replaces the per-layer Python dispatch of one training step: forward + loss + backward of the
+ * reference trainer (lib/train_test/pl_BaselineTrainer.py:157-160, 288-309; the network's forward at
+ * models/res16unet.py:196-270) become ONE call that walks a straight-line program of the entry points above.
+ *   ops   int64 [n_ops][LGS_PROGRAM_OP_WORDS]: word 0 = LGS_OP_*, the others are that op's arguments — buffer ids, channel
+ *         counts, level ids, flags (languagegroundedsemseg_b200/program.py builds them from the network's modules and
+ *         documents every word; csrc/program.cu is the interpreter).
+ *   bufs  int64 [n_bufs][4] = { kind, level | slot, channels, element bytes }: kind 0 = external pointer taken from
+ *         ext[slot] at run time (parameters, gradients, BatchNorm buffers, weight operands, kernel-map tables, labels,
+ *         loss), kind 1 = intermediate of rows(level) x channels elements placed in the arena (level -1: one row).
+ * lgs_program_run executes ops [op_begin, op_end) — ranges let the caller launch a gradient all-reduce bucket between
+ * two parts of backward — on `stream`, weight gradients flagged for it on `side_stream` (joined before the call returns).
+ *   level_rows [n_levels] voxels per U-Net level of THIS batch;  d_arena: lgs_program_arena_bytes() bytes of scratch;
+ *   d_bn_scratch: 2 x 16384 doubles, all zero before the first run (the program alternates the halves like the facade).
+ * --------------------------------------------------------------------------------------------------------- */
+#define LGS_PROGRAM_OP_WORDS 16
+#define LGS_OP_WEIGHT_PREP 1
+#define LGS_OP_CONV 2
+#define LGS_OP_WGRAD 3
+#define LGS_OP_BN_FWD 4
+#define LGS_OP_BN_BWD 5
+#define LGS_OP_COPY2D 6
+#define LGS_OP_ADD 7
+#define LGS_OP_SEG_CE 8
+#define LGS_OP_COLSUM 9
+#define LGS_OP_JOIN 10
+typedef struct lgs_program lgs_program;
+int lgs_program_create(const int64_t* ops, int32_t n_ops, const int64_t* bufs, int32_t n_bufs, int32_t n_levels, int32_t n_ext,
+                       lgs_program** out);
+void lgs_program_destroy(lgs_program* p);
+int64_t lgs_program_arena_bytes(const lgs_program* p, const int64_t* level_rows);
+/* forget the BatchNorm scratch alternation state (after the caller re-zeroed the scratch, e.g. following a failed run) */
+void lgs_program_reset(lgs_program* p);
+int lgs_program_run(lgs_program* p, int32_t op_begin, int32_t op_end, const int64_t* level_rows, void* const* ext,
+                    void* d_arena, int64_t arena_bytes, void* d_bn_scratch, void* stream, void* side_stream);
 
 #ifdef __cplusplus
 }

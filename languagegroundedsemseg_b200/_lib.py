@@ -36,6 +36,15 @@ SIGNATURES = {
     "lgs_weight_bx3_elems": (_i64, [_i32, _i32, _i32]),
     "lgs_conv_wgrad": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _p, _i32, _p, _i32, _i32, _p]),
     "lgs_bn_fwd": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _f32, _f32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "lgs_bn_fwd2": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _f32, _f32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p]),
+    "lgs_copy2d": (C.c_int, [_p, _i64, _p, _i64, _i64, _i32, _p]),
+    "lgs_add": (C.c_int, [_p, _p, _p, _i64, _p]),
+    "lgs_colsum": (C.c_int, [_p, _i64, _i32, _p, _p]),
+    "lgs_program_create": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, C.POINTER(_p)]),
+    "lgs_program_destroy": (None, [_p]),
+    "lgs_program_arena_bytes": (_i64, [_p, _p]),
+    "lgs_program_reset": (None, [_p]),
+    "lgs_program_run": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i64, _p, _p, _p]),
     "lgs_bn_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "lgs_seg_ce_supported": (C.c_int, [_i32]),
     "lgs_seg_ce": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _p, _p]),

@@ -310,19 +310,35 @@ static inline bool bn_use_vec(const void* a, const void* b, const void* d, int c
 
 extern "C" {
 
+int lgs_bn_fwd2(const float* d_x, const float* d_residual, int64_t n, int32_t c, const float* d_gamma, const float* d_beta,
+                float eps, float momentum, int32_t relu, float* d_running_mean, float* d_running_var, float* d_z,
+                float* d_save_mean, float* d_save_invstd, double* d_scratch, double* d_scratch_next,
+                int64_t* d_num_batches_tracked, int32_t stats_ready, void* stream_);
+
 int lgs_bn_fwd(const float* d_x, const float* d_residual, int64_t n, int32_t c, const float* d_gamma, const float* d_beta,
                float eps, float momentum, int32_t relu, float* d_running_mean, float* d_running_var, float* d_z,
                float* d_save_mean, float* d_save_invstd, double* d_scratch /*[16c]*/, double* d_scratch_next /*[16384] or NULL*/,
                int64_t* d_num_batches_tracked, void* stream_) {
+  return lgs_bn_fwd2(d_x, d_residual, n, c, d_gamma, d_beta, eps, momentum, relu, d_running_mean, d_running_var, d_z, d_save_mean,
+                     d_save_invstd, d_scratch, d_scratch_next, d_num_batches_tracked, 0, stream_);
+}
+
+int lgs_bn_fwd2(const float* d_x, const float* d_residual, int64_t n, int32_t c, const float* d_gamma, const float* d_beta,
+                float eps, float momentum, int32_t relu, float* d_running_mean, float* d_running_var, float* d_z,
+                float* d_save_mean, float* d_save_invstd, double* d_scratch /*[16c]*/, double* d_scratch_next /*[16384] or NULL*/,
+                int64_t* d_num_batches_tracked, int32_t stats_ready, void* stream_) {
+  if (stats_ready) LGS_TRACE("lgs_bn_fwd2 %p %p %lld %d %p %p %.9g %.9g %d %p %p %p %p %p %p %p %p %d %p", (const void*)d_x, (const void*)d_residual, (long long)n, (int)c, (const void*)d_gamma, (const void*)d_beta, (double)eps, (double)momentum, (int)relu, (const void*)d_running_mean, (const void*)d_running_var, (const void*)d_z, (const void*)d_save_mean, (const void*)d_save_invstd, (const void*)d_scratch, (const void*)d_scratch_next, (const void*)d_num_batches_tracked, (int)stats_ready, (const void*)stream_);
   LGS_TRACE("lgs_bn_fwd %p %p %lld %d %p %p %.9g %.9g %d %p %p %p %p %p %p %p %p %p", (const void*)d_x, (const void*)d_residual, (long long)n, (int)c, (const void*)d_gamma, (const void*)d_beta, (double)eps, (double)momentum, (int)relu, (const void*)d_running_mean, (const void*)d_running_var, (const void*)d_z, (const void*)d_save_mean, (const void*)d_save_invstd, (const void*)d_scratch, (const void*)d_scratch_next, (const void*)d_num_batches_tracked, (const void*)stream_);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n < 1 || c < 4 || (c & 3) || c > 1024) return fail(LGS_E_UNSUPPORTED, "lgs_bn_fwd: n=%lld c=%d (need c %% 4 == 0, c <= 1024)", (long long)n, c);
   if (!d_x || !d_z || !d_save_mean || !d_save_invstd || !d_scratch) return fail(LGS_E_INVALID, "lgs_bn_fwd: null pointer");
   // with d_scratch_next the caller guarantees d_scratch is already zero (cleared by the previous call's apply kernel)
-  if (!d_scratch_next) LGS_CUDA(cudaMemsetAsync(d_scratch, 0, size_t(BN_COPIES) * 2 * c * sizeof(double), stream));
+  if (!d_scratch_next && !stats_ready) LGS_CUDA(cudaMemsetAsync(d_scratch, 0, size_t(BN_COPIES) * 2 * c * sizeof(double), stream));
   const dim3 grid{unsigned((c + BN_TX - 1) / BN_TX), unsigned(cdiv(n, BN_ROWS)), 1u}, block{BN_TX, BN_TY, 1u};
   static const int unroll = getenv("LGS_BN_UNROLL") ? atoi(getenv("LGS_BN_UNROLL")) : 4;
-  if (bn_use_vec(d_x, nullptr, nullptr, c)) {
+  if (stats_ready) {
+    // the column sums were accumulated by the producing convolution's epilogue (lgs_conv_fwd2, d_bn_sums): no statistics pass
+  } else if (bn_use_vec(d_x, nullptr, nullptr, c)) {
     LGS_LAUNCH(bn_stats_vec_kernel<4>, unsigned(cdiv(n, BN_VROWS)), BN_VTHREADS, 0, stream,
                reinterpret_cast<const float4*>(d_x), n, c, bn_vec_threads(c), d_scratch);
   } else if (unroll == 1) {

@@ -39,6 +39,9 @@ class FakeManager:
         self.sizes = sizes          # rows per tensor stride
         self.cache = {}
 
+    def size(self, key):
+        return self.sizes[key.tensor_stride[0]]
+
     def conv_maps(self, in_key, ks, stride, dil, transpose):
         ts = in_key.tensor_stride[0]
         out_ts = ts // stride if transpose else ts * stride
