@@ -4,7 +4,7 @@ Tolerances (max-norm relative error per layer):
   'bx3'   tcgen05 bf16x3 (default)               1e-4  fwd/dgrad (measured 5e-6 .. 2e-5)
   'tc'    tcgen05 3xTF32                         1e-4  fwd/dgrad (measured ~1e-5)
   'tf32'  tcgen05 single-pass TF32 (fast mode)   2e-3
-  wgrad: see TOL_GW
+  wgrad: 1e-3 (TOL_GW)
 north_star's 1e-3 bound is on whole-network logits and is checked in test_gpu_nets.py."""
 import numpy as np
 import pytest
@@ -15,7 +15,10 @@ from tests.helpers import random_sparse_coords, rel_err
 pytestmark = pytest.mark.gpu
 
 TOL = {"simt": 2e-5, "bx3": 1e-4, "tc": 1e-4, "tf32": 2e-3}
-TOL_GW = {"simt": 2e-5, "bx3": 2e-3, "tc": 2e-3, "tf32": 2e-3}
+# weight gradients of 'bx3' / 'tc' are single-pass TF32 products (fp32 accumulation): the hardware TRUNCATES both operands to
+# TF32, a systematic -7..9e-4 relative scale error on every entry (measured on all shapes below and on the 149 106-voxel map:
+# test_full_size_layer_vs_oracle_and_simt) — inside north_star's 1e-3, which is the gate
+TOL_GW = {"simt": 2e-5, "bx3": 1e-3, "tc": 1e-3, "tf32": 2e-3}
 ALGOS = ["simt", "bx3", "tc", "tf32"]
 
 
@@ -80,6 +83,8 @@ def test_conv_layer_parity(E, algo, cin, cout, ks, stride, transpose, bias):
     o, g = r["oracle"], r["cuda"]
     assert torch.equal(o["C"], g["C"])
     tol = TOL[algo]
+    print(f"[layer {cin}->{cout} ks={ks} s={stride} tr={int(transpose)} {algo}] out {rel_err(g['out'], o['out']):.1e} gin {rel_err(g['gin'], o['gin']):.1e} "
+          f"gw {rel_err(g['gw'], o['gw']):.1e}")
     assert rel_err(g["out"], o["out"]) < tol
     assert rel_err(g["gin"], o["gin"]) < tol
     assert rel_err(g["gw"], o["gw"]) < TOL_GW[algo]
@@ -225,3 +230,93 @@ def test_bx3_small_map_decompositions(E, lib, ks_split, ns, tm, cin, cout, nvox)
         for k in ("bx3_ks", "bx3_ns", "bx3_tm"):
             lib.lgs_tune(k.encode(), 0)
     assert rel_err(out, ref) < TOL["bx3"]
+
+
+@pytest.mark.parametrize("cin,cout", [(96, 96), (128, 96)])
+def test_full_size_layer_vs_oracle_and_simt(E, cin, cout):
+    """The configuration that produces the headline number — the 3^3 layers of block8 on the 149 106-voxel map of BASELINE
+    configs[1], with the heuristic's own decomposition (4 row tiles per CTA) — forward, dgrad and wgrad against the CPU
+    oracle (oracle/me_cpu.sparse_conv: gather -> GEMM -> scatter-add per offset, autograd for the gradients) AND against
+    the exact-fp32 SIMT kernels, 1e-3 relative (north_star's bound; measured values are printed)."""
+    from languagegroundedsemseg_b200 import scenes
+    from oracle import me_cpu
+    c, _, _ = scenes.synthetic_voxel_scene(0, 150000)
+    assert c.shape[0] == 149106
+    torch.manual_seed(cin)
+    f = torch.randn(c.shape[0], cin)
+    gy = torch.randn(c.shape[0], cout)
+    w = torch.randn(27, cin, cout) / np.sqrt(27 * cin)
+    # oracle
+    xo = me_cpu.SparseTensor(f.clone().requires_grad_(True), torch.from_numpy(c))
+    km = xo.coordinate_manager.kernel_map(xo.coordinate_map_key, xo.coordinate_map_key, [3, 3, 3], [1, 1, 1])
+    fo, wo = f.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yo = me_cpu.sparse_conv(fo, wo, km, c.shape[0])
+    yo.backward(gy)
+    ref = dict(out=yo.detach(), gin=fo.grad, gw=wo.grad)
+    res = {}
+    cc = torch.from_numpy(c).cuda()
+    x0 = E.SparseTensor(torch.zeros(c.shape[0], 1).cuda(), cc)
+    gk = x0.coordinate_manager.kernel_map(x0.coordinate_map_key, x0.coordinate_map_key, [3, 3, 3], [1, 1, 1])
+    for algo in ("simt", "bx3", "tc"):
+        E.set_conv_algo(algo)
+        fg, wg = f.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+        y = E.sparse_conv(fg, wg, None, gk)
+        y.backward(gy.cuda())
+        res[algo] = dict(out=y.detach().cpu(), gin=fg.grad.cpu(), gw=wg.grad.cpu())
+    E.set_conv_algo("bx3")
+    for algo in ("simt", "bx3", "tc"):
+        e = {k: (rel_err(res[algo][k], ref[k]), rel_err(res[algo][k], res["simt"][k])) for k in ("out", "gin", "gw")}
+        print(f"[full size {cin}->{cout} {algo}] vs oracle / vs simt: " + "  ".join(f"{k} {a:.1e}/{b:.1e}" for k, (a, b) in e.items()))
+        for k, (a, b) in e.items():
+            assert a < 1e-3 and b < 1e-3, (algo, k, a, b)
+
+
+@pytest.mark.parametrize("cin,cout,ks,stride,transpose", [(64, 96, 3, 1, False), (96, 96, 3, 1, False), (32, 32, 2, 2, False), (128, 96, 3, 1, False),
+                                                          (96, 200, 1, 1, False)])
+def test_bf16_layer_fwd_dgrad_wgrad(E, cin, cout, ks, stride, transpose):
+    """BASELINE configs[3] computes in bf16 (features and tensor-core operands bf16, fp32 accumulation, fp32 master
+    weights): forward, dgrad and wgrad of one layer against the oracle evaluated on the SAME bf16-rounded inputs and
+    weights in fp32.  What remains is the rounding of each OUTPUT to bf16 (2^-9 relative, max-norm 1e-2) and, for wgrad
+    (kept in fp32), the accumulation order."""
+    from oracle import me_cpu
+    rng = np.random.default_rng(cin + cout + ks)
+    c = random_sparse_coords(rng, 5000, extent=24, batches=1)
+    torch.manual_seed(cin * 3 + cout)
+    pre = cin if transpose else None
+    res = {}
+    f0 = torch.randn(c.shape[0], cin).bfloat16()
+    for name, eng, dev in (("oracle", me_cpu, "cpu"), ("cuda", E, "cuda")):
+        torch.manual_seed(5)
+        cls = eng.MinkowskiConvolutionTranspose if transpose else eng.MinkowskiConvolution
+        down = eng.MinkowskiConvolution(cin, cin, kernel_size=2, stride=2, dimension=3).to(dev) if transpose else None
+        conv = cls(cin, cout, kernel_size=ks, stride=stride, dimension=3).to(dev)
+        with torch.no_grad():
+            conv.kernel.copy_(conv.kernel.bfloat16().float())          # bf16-representable master weights
+        if name == "cuda":
+            E.set_conv_algo("bx3")                                      # bf16 features -> bf16 tensor-core products
+            f = f0.cuda().requires_grad_(True)
+        else:
+            f = f0.float().requires_grad_(True)
+        x = eng.SparseTensor(f, torch.from_numpy(c).to(dev))
+        if down is not None:
+            with torch.no_grad():
+                h = down(x)
+            hf = h.F.detach().to(f.dtype).float().bfloat16()
+            hf = (hf if name == "cuda" else hf.float()).requires_grad_(True)
+            x = eng.SparseTensor(hf, coordinate_map_key=h.coordinate_map_key, coordinate_manager=h.coordinate_manager)
+            f = hf
+        y = conv(x)
+        torch.manual_seed(9)
+        gy = torch.randn(y.F.shape).bfloat16()
+        y.F.backward(gy.to(dev).to(y.F.dtype))
+        res[name] = dict(out=y.F.detach().float().cpu(), gin=f.grad.float().cpu(), gw=conv.kernel.grad.float().cpu())
+    if transpose:
+        # the two engines' strided inputs differ by one bf16 rounding of the down-conv output: compare loosely
+        tol_o, tol_w = 3e-2, 3e-2
+    else:
+        tol_o, tol_w = 1e-2, 2e-3
+    o, g = res["oracle"], res["cuda"]
+    assert res["cuda"]["out"].dtype == torch.float32
+    assert rel_err(g["out"], o["out"]) < tol_o
+    assert rel_err(g["gin"], o["gin"]) < tol_o
+    assert rel_err(g["gw"], o["gw"]) < tol_w
