@@ -35,9 +35,12 @@ MODEL = "Res16UNet34C"
 TARGET_VOXELS = 150_000
 
 
-def workload_string(model, n_vox, voxel_size, voxels_target):
-    return (f"{model} fwd+bwd+SGD, 1 synthetic ScanNet-shaped scene/GPU, {n_vox} voxels @{voxel_size * 100:g}cm, 200 classes"
-            + (" (BASELINE configs[1])" if (model == MODEL and voxels_target == TARGET_VOXELS) else ""))
+def workload_string(model, n_vox, voxel_size, voxels_target, config=2):
+    tag = {2: " (BASELINE configs[1])", 3: " + CLIP text-anchor CE loss, 200 x 512 anchors, learned projection (BASELINE configs[2])",
+           4: " (BASELINE configs[3]: bf16)", 5: " + CLIP text-anchor CE loss (BASELINE configs[4])"}.get(config, "")
+    if config == 2 and not (model == MODEL and voxels_target == TARGET_VOXELS):
+        tag = ""
+    return f"{model} fwd+bwd+SGD, 1 synthetic ScanNet-shaped scene/GPU, {n_vox} voxels @{voxel_size * 100:g}cm, 200 classes" + tag
 
 
 def load_peaks():
@@ -128,7 +131,7 @@ def _aten_criterion(logits, labels):
     return torch.nn.functional.cross_entropy(logits.float(), labels, ignore_index=-1)
 
 
-def train_step(ST, net, opt, coords, feats, labels, reducer=None, st=None, criterion=_aten_criterion, program=None, native=None):
+def train_step(ST, net, opt, coords, feats, labels, reducer=None, st=None, criterion=_aten_criterion, program=None, native=None, clip=None):
     if st is None:
         st = ST(feats, coords)                               # pl_BaselineTrainer.py:300
     if native is not None:
@@ -150,8 +153,17 @@ def train_step(ST, net, opt, coords, feats, labels, reducer=None, st=None, crite
             reducer()
         opt.step()
         return loss
-    out, _ = net(st)                                         # res16unet.py:196
-    loss = criterion(out.F, labels)                          # :350  CrossEntropyLoss(ignore_index)
+    if clip is not None:
+        # pl_RepresentationTrainer.py:183-216: features (+ projected anchors) -> text-anchor loss
+        crit, anchors = clip
+        if hasattr(net, "projection_layer"):
+            feat, anc = net(st, anchors)
+        else:
+            feat, anc = net(st), anchors
+        loss = crit(feat.F, labels, anc)[0]
+    else:
+        out, _ = net(st)                                     # res16unet.py:196
+        loss = criterion(out.F, labels)                      # :350  CrossEntropyLoss(ignore_index)
     if reducer is not None:
         reducer.zero_grad()                                  # gradients are views of the reducer's flat buffer: one memset
     else:
@@ -216,15 +228,22 @@ def roofline_report(prof, ms_per_step, algo, dtype, PROF_STEPS, pair_counts=None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     shape_tag = f"conv K={dom_key[1]} {dom_key[2]}->{dom_key[3]} n_out={dom_key[5]} {algo} {dtype}"
-    traffic_src = None
+    traffic_src = tensor_pct = None
     if os.path.exists(tpath):
         t = json.load(open(tpath)).get(f"K={dom_key[1]} {dom_key[2]}->{dom_key[3]} {algo} {dtype}")
         if t:
             traffic, traffic_src = t["bytes"], t["source"]      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch
-    roofline = {"bound": "hbm", "kernel": "conv_tc2_kernel (output-stationary gather -> tcgen05 GEMM, fwd and dgrad): " + shape_tag,
+            tensor_pct = t.get("tensor_pipe_pct")
+    kname = {"bx3": "conv_bx3_kernel (output-stationary gather -> bf16x3 tcgen05 GEMM in TS form, fwd and dgrad): ",
+             "simt": "conv_simt_kernel: "}.get(algo, "conv_tc2_kernel (output-stationary gather -> tcgen05 GEMM, fwd and dgrad): ")
+    roofline = {"bound": "hbm", "kernel": kname + shape_tag,
                 "achieved": round(achieved, 1), "peak": hbm_gbs, "unit": "GB/s", "frac": round(achieved / hbm_gbs, 4),
                 "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                 "traffic_source": traffic_src, "peak_source": peak_src,
+                "tensor_pipe_active_pct": tensor_pct,   # sm__pipe_tensor_cycles_active of the same ncu capture: what the SM actually did
+                "note": "achieved/peak is the SURVEY 8(d) per-offset gather model (bytes an ME-style gather -> GEMM -> scatter would move) over "
+                        "the measured HBM copy bandwidth; the kernel itself is output-stationary and serves the gather from L2 (see traffic), "
+                        "so what binds is the L2->SM cp.async gather rate and the tensor pipe, not DRAM",
                 "algorithmic_bytes_per_launch": int(dom[1]), "avg_launch_ms": round(dom_ms, 4), "launches_per_step": dom[3] // PROF_STEPS,
                 "share_of_step": round((dom[0] / PROF_STEPS) / ms_per_step, 3),
                 "tflops": round(dom[2] / (dom_ms * 1e-3) / 1e12, 2),
@@ -269,6 +288,7 @@ def run_engine(args, rank, world, local_rank):
     h_labels = torch.from_numpy(labels_np).pin_memory()
     d_coords, d_feats, d_labels = h_coords.to(dev), h_feats.to(dev).to(fdtype), h_labels.to(dev)
 
+    from languagegroundedsemseg_b200 import losses as lgs_losses
     net, opt = build_net(None, dev, fdtype, args.model)
     if args.dtype == "bf16":
         # bf16 features; parameters stay fp32 (master weights), BN in fp32 statistics via autocast-free mixed dtype
@@ -293,7 +313,6 @@ def run_engine(args, rank, world, local_rank):
           if not args.no_prefetch else None)
     tickets = {}
 
-    from languagegroundedsemseg_b200 import losses as lgs_losses
     # the engine's fused softmax cross-entropy (lgs_seg_ce: one pass over the logits) unless LGS_ATEN_CE=1
     crit = _aten_criterion if os.environ.get("LGS_ATEN_CE") else (lambda x, y: lgs_losses.cross_entropy(x, y, ignore_index=-1))
 
@@ -301,22 +320,40 @@ def run_engine(args, rank, world, local_rank):
     if args.step_program:
         from languagegroundedsemseg_b200.step import StepProgram
         program = StepProgram(model)
-    elif args.driver == "native" and args.dtype == "f32" and args.algo == "bx3":
+    clip = None
+    if args.clip:
+        net.representation_only(True)                       # models/clip_models.py:106-109
+        torch.manual_seed(1)
+        anchors = torch.nn.functional.normalize(torch.randn(200, 512, device=dev), dim=1)     # CLIP text features stand-in
+        clip = (lgs_losses.ContrastiveLanguageCELoss(num_labels=200, ignore_label=-1), anchors)
+    if not args.step_program and args.driver == "native" and args.dtype == "f32" and args.algo == "bx3":
         from languagegroundedsemseg_b200.program import NativeStep
         if reducer is None:
             reducer = ddp.GradAllReducer(net.parameters(), overlap=False)
-        native = NativeStep(model, ignore_index=-1, reducer=reducer)
+        head = None
+        if clip is not None:
+            crit_c, anc_c = clip
+            proj = getattr(net, "projection_layer", None)
+
+            def head(feats, labels):
+                a = proj(anc_c.unsqueeze(-1)).squeeze() if proj is not None else anc_c
+                return crit_c(feats, labels, a)[0]
+        native = NativeStep(model, ignore_index=-1, reducer=reducer, head=head)
+    native_step = native
+
+    prof_mode = {"on": False}     # per-launch CUDA events need the facade's hooks: the profiled steps run module by module
 
     def staged_step(key, src):
         flush.fill_(0.0)
+        native = None if prof_mode["on"] else native_step
         if pf is None:
             c, f, lab = (t.to(dev, non_blocking=True) for t in src)
-            return train_step(E.SparseTensor, model, opt, c, f.to(fdtype), lab, reducer, criterion=crit, program=program, native=native)
+            return train_step(E.SparseTensor, model, opt, c, f.to(fdtype), lab, reducer, criterion=crit, program=program, native=native, clip=clip)
         if key not in tickets:
             tickets[key] = pf.stage(*src)
         st, lab = pf.get(tickets[key])
         tickets[key] = pf.stage(*src)                        # next step's batch, overlapped with this step
-        return train_step(None, model, opt, None, None, lab, reducer, st=st, criterion=crit, program=program, native=native)
+        return train_step(None, model, opt, None, None, lab, reducer, st=st, criterion=crit, program=program, native=native, clip=clip)
 
     def resident_step():
         return staged_step("resident", (d_coords, d_feats, d_labels))
@@ -393,11 +430,14 @@ def run_engine(args, rank, world, local_rank):
     # ---- per-launch CUDA-event timing of the engine's conv kernels (same process, same data, right after the timed
     # region; kept out of it because ~380 event records per step starve the launch queue and double the step time)
     PROF_STEPS = 2
+    prof_mode["on"] = True
+    resident_step()                      # the facade's lazily built state (weight-operand cache) outside the profile
     E.profile_begin()
     for _ in range(PROF_STEPS):
         resident_step()
     torch.cuda.synchronize()
     prof = E.profile_end() or []
+    prof_mode["on"] = False
 
     # ---- kernel-map build time (coordinate map + 4 strided maps + 9 kernel maps of one scene) -------------
     def build_maps():
@@ -446,7 +486,7 @@ def run_engine(args, rank, world, local_rank):
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": warm_done, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.dtype == "f32" else "bf16", "data": "synthetic",
-        "config": {"workload": workload_string(args.model, n_vox, args.voxel_size, args.voxels), "voxels_per_gpu": n_vox, "algo": args.algo,
+        "config": {"workload": workload_string(args.model, n_vox, args.voxel_size, args.voxels, args.config), "voxels_per_gpu": n_vox, "algo": args.algo,
                    "binding": _lib.binding() + " (Python -> C ABI)",
                    "driver": ("StepProgram (explicit program, no autograd)" if args.step_program else
                               "native step driver (one lgs_program_run per step, languagegroundedsemseg_b200/program.py)" if native is not None
@@ -458,7 +498,7 @@ def run_engine(args, rank, world, local_rank):
                    "l2": "256 MB buffer written between steps (L2 flush); per-step activations >> 126 MB L2",
                    "parallelism": f"dp{world}" + (" (one scene per rank, one flat NCCL gradient all-reduce per step)" if world > 1 else ""),
                    "step": "coordinate+kernel maps" + ("" if args.no_prefetch else " (staged on a side stream during the previous step)")
-                           + ", fwd, CE loss (fused lgs_seg_ce), bwd, SGD"},
+                           + (", fwd, CLIP text-anchor CE loss (fused tcgen05 kernel), bwd, SGD" if args.clip else ", fwd, CE loss (fused lgs_seg_ce), bwd, SGD")},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": e2e_state["last"], "clocks": clocks_e2e,
                 "how": "pinned host coords/feats/labels -> H2D every step (staged on a side stream one step ahead), "
@@ -537,7 +577,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--algo", default="bx3", choices=["bx3", "tc", "tf32", "simt"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
-    ap.add_argument("--cpu-sample-voxels", type=int, default=60_000)
+    ap.add_argument("--cpu-sample-voxels", type=int, default=TARGET_VOXELS,
+                    help="scene size of the CPU arm (default: the full BASELINE configs[1] scene, ~4 s per step on 16 cores)")
     ap.add_argument("--model", default=MODEL, help="topology (default: the BASELINE metric's Res16UNet34C)")
     ap.add_argument("--voxels", type=int, default=TARGET_VOXELS)
     ap.add_argument("--voxel-size", type=float, default=0.02)
@@ -551,7 +592,18 @@ def main():
                          "the same C-ABI calls, no autograd graph) instead of the module-by-module facade")
     ap.add_argument("--profile-run", action="store_true",
                     help="for ncu launch lists: allow fewer warm-up steps and skip the e2e / map-build / roofline legs")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configs[] (1-based): 2 Res16UNet34C fwd+bwd ~150K voxels (default, the metric's config); "
+                         "3 Res16UNet34CR_Proj + CLIP text-anchor loss (200 x 512 anchors, learned projection); 4 config 2 in bf16 "
+                         "(launch with torchrun for DDP); 5 Res16UNet34D @1cm ~600K voxels + CLIP loss")
     args = ap.parse_args()
+    args.clip = False
+    if args.config == 3:
+        args.model, args.clip = "Res16UNet34CR_Proj", True
+    elif args.config == 4:
+        args.dtype, args.driver = "bf16", "facade"
+    elif args.config == 5:
+        args.model, args.clip, args.voxels, args.voxel_size = "Res16UNet34D", True, 600_000, 0.01
     args.warmup = max(args.warmup, 3) if (args.impl == "engine" and not args.profile_run) else args.warmup
 
     rank = int(os.environ.get("RANK", 0))
@@ -562,12 +614,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        steps = max(1, min(args.steps, 3))
+        steps = max(1, min(args.steps, 2))
         cb, n, dt = cpu_arm(steps, min(args.warmup, 1), args.cpu_sample_voxels)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt / steps * 1e3, 1),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                # same workload as the engine arm; each step runs on a bounded sample of it (cpu_baseline.sample)
+                # same workload as the engine arm: the full scene of BASELINE configs[1], fewer steps (cpu_baseline.sample)
                 "config": {"workload": workload_string(MODEL, make_scene(0, TARGET_VOXELS)[0].shape[0], 0.02, TARGET_VOXELS),
                            "sample_voxels": n,
                            "implementation": "CPU restatement of MinkowskiEngine 0.5.4's CPU algorithm (oracle/me_cpu.py; the "

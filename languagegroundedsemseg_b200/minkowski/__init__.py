@@ -487,6 +487,14 @@ class SparseTensor:
     def __init__(self, features, coordinates=None, coordinate_map_key=None, coordinate_manager=None,
                  tensor_stride=1, device=None, _pending=None, **_ignored):
         self._pending = _pending
+        for k, v in _ignored.items():
+            # ME arguments that change semantics must not vanish silently: duplicates are always resolved by keeping the
+            # first row (RANDOM_SUBSAMPLE, ME's default and what the reference relies on)
+            if k == "quantization_mode" and "RANDOM_SUBSAMPLE" not in str(v) and v is not None:
+                raise NotImplementedError(f"SparseTensor(quantization_mode={v}): lgs_b200 implements RANDOM_SUBSAMPLE only")
+            if k not in ("quantization_mode", "minkowski_algorithm", "allocator_type", "requires_grad"):
+                import warnings
+                warnings.warn(f"lgs_b200 SparseTensor ignores the argument {k!r}", stacklevel=2)
         if coordinate_map_key is None:
             if coordinates is None:
                 raise ValueError("SparseTensor needs coordinates or a coordinate_map_key")
@@ -1000,6 +1008,16 @@ class _ConvBase(nn.Module):
         self._prep, self._prep_bufs = None, {}      # cached tensor-core weight operands (_WeightPrep)
         _weight_prep.register(self)
         self.reset_parameters()
+
+    def __getstate__(self):
+        # derived operand caches (up to 4x the weight bytes) are not state: keep them out of pickles / deep copies
+        d = self.__dict__.copy()
+        d["_prep"], d["_prep_bufs"] = None, {}
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        _weight_prep.register(self)
 
     def reset_parameters(self):
         with torch.no_grad():

@@ -7,8 +7,9 @@ order (hence RNG consumption at init) match the reference classes
     Res16UNet34CR / 34CR_Proj / 34D   models/clip_models.py:95-215
     BasicBlock / NoReluBlock      models/modules/resnet_block.py:10-57, 134-161
     _make_layer                   models/resnet.py:84-125
-which tests/test_nets_vs_reference.py checks key-for-key and output-for-output (in the build container, where the
-reference is mounted).  With `engine=None` the CUDA facade is used.
+which tests/test_reference_models_on_facade.py checks key-for-key and value-for-value, tests/test_host_logic.py
+(test_reference_models_run_through_the_facade_like_nets) call-for-call through the C ABI, and tests/golden/make_golden.py
+output-for-output through the oracle (all in the build container, where the reference is mounted).  With `engine=None` the CUDA facade is used.
 """
 import torch
 import torch.nn as nn

@@ -51,10 +51,17 @@ class _Buf:
 class NativeStep:
     LEVELS = 5
 
-    def __init__(self, net, ignore_index=-1, reducer=None, fuse_bn_stats=True, keep_logits=False, overlap_wgrad=True, _dry=False):
+    def __init__(self, net, ignore_index=-1, reducer=None, fuse_bn_stats=True, keep_logits=False, overlap_wgrad=True, head=None,
+                 _dry=False):
+        """head=None: segmentation step (classifier `final` + mean cross-entropy with ignore_index, BASELINE configs 1/2/4).
+        head=callable(features [n0, C] requiring grad, labels) -> scalar loss: the U-Net body runs natively, the head under
+        autograd (the CLIP pre-training nets of configs 3 / 5: anchor projection + fused text-anchor loss; it is tiny), and its
+        gradient w.r.t. the features feeds the native backward."""
         convs = [m for m in net.modules() if isinstance(m, (E.MinkowskiConvolution, E.MinkowskiConvolutionTranspose))]
-        if not convs or getattr(net, "final", None) is None:
-            raise NotImplementedError("NativeStep drives Res16UNet segmentation topologies built on the lgs_b200 facade")
+        if not convs or (head is None and getattr(net, "final", None) is None):
+            raise NotImplementedError("NativeStep drives Res16UNet topologies built on the lgs_b200 facade (segmentation flavour, or any "
+                                      "flavour with a `head`)")
+        self.head = head
         p0 = next(net.parameters())
         if p0.dtype is not torch.float32 or (not p0.is_cuda and not _dry):
             # _dry: host-logic tests run the program with the library's call recorder on (lgs_trace_begin), nothing executes
@@ -289,27 +296,37 @@ class NativeStep:
             width = a.c
             a, nb = self._stage_fwd(getattr(net, bl), cat, level)
             dec.append((nt, width, nb, cat.c))
-        # -- classifier + loss
-        fin = net.final
-        rf = self._conv_info(fin)
-        bias = self._param(fin._parameters["bias"]) if fin._parameters.get("bias") is not None else None
-        self._logits = self._ext(name="logits") if self.keep_logits else None
-        if self._logits is not None:
-            self._logits.level, self._logits.c = 0, rf["c_out"]
-            self._op(OP_CONV, a, a.c, None, 0, 0, rf["w_fwd"], rf["K"], rf["c_out"], None, 0, 0, bias, self._logits, 0)
-            logits = self._logits
+        self._logits = None
+        if self.head is None:
+            # -- classifier + loss
+            fin = net.final
+            rf = self._conv_info(fin)
+            bias = self._param(fin._parameters["bias"]) if fin._parameters.get("bias") is not None else None
+            if self.keep_logits:
+                self._logits = self._ext(name="logits")
+                self._logits.level, self._logits.c = 0, rf["c_out"]
+                self._op(OP_CONV, a, a.c, None, 0, 0, rf["w_fwd"], rf["K"], rf["c_out"], None, 0, 0, bias, self._logits, 0)
+                logits = self._logits
+            else:
+                logits, _ = self._conv_fwd(fin, a, 0, bias=bias)
+            self.n_classes = rf["c_out"]
+            self._loss_t = torch.zeros((), dtype=torch.float32, device=self.device)
+            ws = self._new(-1, 4, 8)
+            dlog = self._new(0, rf["c_out"])
+            self._op(OP_SEG_CE, logits, 0, rf["c_out"], self._ext(name="labels"), self.ignore_index, ws, self._tensor(self._loss_t), dlog)
+            self.marks["forward_end"] = len(self._ops)
+            # -- backward (reverse creation order, as autograd runs this graph)
+            d = self._conv_bwd(fin, a, 0, dlog)
+            if bias is not None:
+                self._op(OP_COLSUM, dlog, 0, rf["c_out"], self._grad(fin._parameters["bias"]))
         else:
-            logits, _ = self._conv_fwd(fin, a, 0, bias=bias)
-        self.n_classes = rf["c_out"]
-        self._loss_t = torch.zeros((), dtype=torch.float32, device=self.device)
-        ws = self._new(-1, 4, 8)
-        dlog = self._new(0, rf["c_out"])
-        self._op(OP_SEG_CE, logits, 0, rf["c_out"], self._ext(name="labels"), self.ignore_index, ws, self._tensor(self._loss_t), dlog)
-        self.marks["forward_end"] = len(self._ops)
-        # -- backward (reverse creation order, as autograd runs this graph)
-        d = self._conv_bwd(fin, a, 0, dlog)
-        if bias is not None:
-            self._op(OP_COLSUM, dlog, 0, rf["c_out"], self._grad(fin._parameters["bias"]))
+            # -- per-point features out to the head, their gradient back in
+            self.feat_channels = a.c
+            fo = self._ext(name="features")
+            self._op(OP_COPY2D, a, a.c, 0, fo, a.c, 0, 0, 0, a.c)
+            self.marks["forward_end"] = len(self._ops)
+            d = self._ext(name="dfeatures")
+            d.level, d.c = 0, a.c
         dskip = [None] * 4
         for i in (3, 2, 1, 0):
             nt, width, nb, cat_c = dec[i]
@@ -356,6 +373,13 @@ class NativeStep:
         self._sig = None
         ids = {id(p): i for i, p in enumerate(self.reducer.params)}
         self._enc_last = max(ids[id(p)] for p in self.net.block4.parameters())
+        written = set()
+        for r in self._layers:
+            written.add(id(r["mod"]._parameters["kernel"]))
+        for key in self._ext_cache:
+            if key[0] == "g":
+                written.add(key[1])
+        self._unwritten = [p for p in self.reducer.params if id(p) not in written]
         self._bind_static()
 
     def __del__(self):
@@ -407,10 +431,15 @@ class NativeStep:
         lab = labels.long().contiguous()
         keep = [f, lab]
         ext[dyn["feats"]] = f.data_ptr()
-        ext[dyn["labels"]] = lab.data_ptr()
+        if "labels" in dyn:
+            ext[dyn["labels"]] = lab.data_ptr()
         if self._logits is not None:
             self.logits = torch.empty((self._rows_arr[0], self.n_classes), dtype=torch.float32, device=self.device)
             ext[dyn["logits"]] = self.logits.data_ptr()
+        if self.head is not None:
+            self.features = torch.empty((self._rows_arr[0], self.feat_channels), dtype=torch.float32, device=self.device)
+            ext[dyn["features"]] = self.features.data_ptr()
+            ext[dyn["dfeatures"]] = self.features.data_ptr()       # placeholder until the head has run
         need = int(self.lib.lgs_program_arena_bytes(self._handle, ctypes.addressof(self._rows_arr)))
         if self._arena is None or self._arena.numel() < need:
             self._arena = torch.empty(int(need * 1.1) + 4096, dtype=torch.uint8, device=self.device)
@@ -427,9 +456,9 @@ class NativeStep:
             _lib.check(rc)
 
     def run(self, st, labels):
-        """forward + mean cross-entropy (ignore_index) + backward; gradients are WRITTEN into every parameter's .grad
-        (views of the reducer's flat buffer).  With more than one rank the all-reduce buckets are launched between the two
-        halves of backward and joined before returning.  Returns the loss (0-dim device tensor, valid on the current stream)."""
+        """forward + loss + backward; gradients are WRITTEN into every parameter's .grad (views of the reducer's flat
+        buffer).  With more than one rank the all-reduce buckets are launched between the two halves of backward and joined
+        before returning.  Returns the loss (0-dim device tensor, valid on the current stream)."""
         if self._signature() != self._sig:
             self._bind_static()
         self._keepalive = self._bind_batch(st, labels)
@@ -437,8 +466,24 @@ class NativeStep:
         red = self.reducer
         if red.world > 1:
             red._arm()
+        begin = 0
+        loss = self._loss_t if self.head is None else None
+        if self.head is not None:
+            fwd_end = self.marks["forward_end"]
+            self.run_range(0, fwd_end)
+            for p in self._unwritten:                      # parameters only the head (or nothing) touches: autograd accumulates
+                p.grad.zero_()
+            leaf = self.features.requires_grad_(True)
+            with torch.enable_grad():
+                loss = self.head(leaf, labels)
+                loss.backward()
+            self._dfeat = leaf.grad.contiguous()
+            self._ext_arr[self._ext_dynamic["dfeatures"]] = self._dfeat.data_ptr()
+            loss = loss.detach()
+            begin = fwd_end
+        if red.world > 1:
             mid = self.marks["decoder_done"]
-            self.run_range(0, mid)
+            self.run_range(begin, mid)
             # buckets that hold only decoder / classifier parameters are complete: send them while the encoder's backward runs
             for b in range(len(red._pending)):
                 if red.bounds[b] > self._enc_last:
@@ -446,5 +491,5 @@ class NativeStep:
             self.run_range(mid, self.n_ops)
             red.wait()
         else:
-            self.run_range(0, self.n_ops)
-        return self._loss_t
+            self.run_range(begin, self.n_ops)
+        return loss

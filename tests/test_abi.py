@@ -169,7 +169,8 @@ def test_native_binding_fuzz_against_ctypes(lib):
            C.c_int64: lambda: rng.choice([0, -1, 2 ** 63 - 1, -2 ** 63, rng.randrange(-2 ** 40, 2 ** 40)]),
            C.c_int32: lambda: rng.choice([0, 1, -1, 2 ** 31 - 1, -2 ** 31, rng.randrange(-10 ** 6, 10 ** 6)]),
            C.c_float: lambda: rng.choice([0.0, 1e-5, -3.5, 0.1, 1e30, rng.random()])}
-    wrapped = [n for n in _lib.SIGNATURES if hasattr(fast, n)]
+    # lgs_program_run dereferences its handle (it IS the caller of the recorded entry points): not fuzzable with random pointers
+    wrapped = [n for n in _lib.SIGNATURES if hasattr(fast, n) and not n.startswith("lgs_program_")]
     assert len(wrapped) >= 15
     for name in wrapped:
         res, argtypes = _lib.SIGNATURES[name]
