@@ -158,6 +158,34 @@ int lgs_conv_fwd2(const float* d_in, int32_t c_in, const float* d_in2, int32_t c
                   int32_t K, int32_t c_out, const int32_t* d_table, int64_t n_out, int32_t reverse_k, const float* d_bias,
                   float* d_out, double* d_bn_sums, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Neighbourhood plans (large same-map 3x3x3 kernel maps; replaces nothing in ME — its kernel maps are per-offset pair lists,
+ * this is a second form of the same map for the cache-based kernel).   Call sites served: the 3x3x3 stride-1 convolutions of
+ * the fine U-Net levels, models/modules/common.py:195-203 via models/modules/resnet_block.py:23-34 and res16unet.py:38.
+ * A plan regroups the output rows of a kernel map into spatially compact supertiles (Morton order over coarse cells), lists
+ * the unique input rows each supertile touches and rewrites the table in supertile-local 16-bit indices; lgs_conv_fwd3 then
+ * loads each supertile's rows into shared memory once per channel block instead of once per (row, offset) pair.
+ * Tensor row order is unchanged; results equal lgs_conv_fwd2's (same products, same accumulation order per row).
+ *   lgs_nbplan_supported: 1 if a plan is worth building for this map (K == 27, n_out >= 148 * 128 unless tuned).
+ *   lgs_nbplan_build: d_plan lgs_nbplan_bytes() bytes, d_scratch lgs_nbplan_scratch_bytes() bytes (both 16-byte aligned);
+ *   h_status (host, may be NULL; synchronises the stream when given): [0] = 1 if some supertile touches more unique rows than
+ *   the cache holds (the plan must then NOT be used), [1] = largest unique-row count of a supertile.
+ *   lgs_tune keys: "nb_rt" rows per tile, "nb_umax" cache rows, "nb_min_rows", "nb_off".
+ * --------------------------------------------------------------------------------------------------------- */
+int lgs_nbplan_supported(int64_t n_out, int32_t K);
+int64_t lgs_nbplan_bytes(int64_t n_out, int32_t K);
+int64_t lgs_nbplan_scratch_bytes(int64_t n_out);
+int lgs_nbplan_build(const int32_t* d_out_coords, int64_t n_out, const int32_t* d_table, int32_t K, void* d_plan, void* d_scratch,
+                     int32_t* h_status, void* stream);
+/* out[0..8] = tm, rt, RS, S, umax, then the int32-word offsets of order [S][RS], ucount [S], uniq [S][umax] and loc
+ * (uint16 [S][K][RS]) inside the plan buffer (tests, tools) */
+int lgs_nbplan_geometry(int64_t n_out, int32_t K, int64_t* out);
+/* lgs_conv_fwd2 with an optional plan of (d_table, n_out): with d_plan != NULL, n_in == n_out and a supported shape the
+ * neighbourhood-cache kernel runs; otherwise exactly lgs_conv_fwd2. */
+int lgs_conv_fwd3(const float* d_in, int32_t c_in, const float* d_in2, int32_t c_in2, int64_t n_in, const void* d_weight,
+                  int32_t K, int32_t c_out, const int32_t* d_table, const void* d_plan, int64_t n_out, int32_t reverse_k,
+                  const float* d_bias, float* d_out, double* d_bn_sums, void* stream);
+
 /* grad_w[k] = sum_o in[table[k][o], :]^T (outer) grad_out[o, :]   -> fp32 [K,c_in,c_out], overwritten. */
 int lgs_conv_wgrad(const void* d_in, int64_t n_in, int32_t c_in,
                    const void* d_grad_out, int64_t n_out, int32_t c_out,

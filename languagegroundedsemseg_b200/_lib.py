@@ -33,6 +33,12 @@ SIGNATURES = {
     "lgs_weight_prep_batch": (C.c_int, [_p, _i32, _i64, _i32, _i32, _p]),
     "lgs_conv_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i32, _p, _i64, _i32, _p, _p, _i32, _i32, _p]),
     "lgs_conv_fwd2": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _i32, _p, _i64, _i32, _p, _p, _p, _p]),
+    "lgs_conv_fwd3": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _i32, _p, _p, _i64, _i32, _p, _p, _p, _p]),
+    "lgs_nbplan_supported": (C.c_int, [_i64, _i32]),
+    "lgs_nbplan_bytes": (_i64, [_i64, _i32]),
+    "lgs_nbplan_scratch_bytes": (_i64, [_i64]),
+    "lgs_nbplan_build": (C.c_int, [_p, _i64, _p, _i32, _p, _p, _p, _p]),
+    "lgs_nbplan_geometry": (C.c_int, [_i64, _i32, C.POINTER(_i64)]),
     "lgs_weight_bx3_elems": (_i64, [_i32, _i32, _i32]),
     "lgs_conv_wgrad": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _p, _i32, _p, _i32, _i32, _p]),
     "lgs_bn_fwd": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _f32, _f32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -24,6 +24,10 @@ int conv_fwd_bx3(const void* in, int c_in, const void* in2, int c_in2, const voi
 int bx3_tune(const char* key, int value);
 int weight_prep_bx3(const float* w, int K, int c_in, int c_out, void* fwd, void* bwd, cudaStream_t stream);
 int weight_prep_bx3_batch(const int64_t* desc, int n_layers, int64_t total_tiles, cudaStream_t stream);
+// neighbourhood-cache path (conv_nb.cu, nbplan.cu)
+int conv_nb_shape_ok(int c_in, int c_in2, int c_out, int K);
+int conv_fwd_nb(const void* in, int c_in, const void* in2, int c_in2, const void* w, int K, int c_out, const void* d_plan,
+                int64_t n_out, int reverse_k, const float* bias, float* out, double* stats, cudaStream_t stream);
 }  // namespace lgs
 
 using namespace lgs;
@@ -35,6 +39,7 @@ int lgs_has_tc(void) { return tc_built() ? 1 : 0; }
 int lgs_tune(const char* key, int32_t value) {
   if (!key) return fail(LGS_E_INVALID, "lgs_tune: null key");
   if (bx3_tune(key, value)) return LGS_OK;
+  if (nb_tune(key, value)) return LGS_OK;
   return fail(LGS_E_INVALID, "lgs_tune: unknown key %s", key);
 }
 
@@ -155,6 +160,21 @@ int lgs_conv_fwd2(const float* d_in, int32_t c_in, const float* d_in2, int32_t c
   const int rc = conv_fwd_bx3(d_in, c_in, c_in2 > 0 ? d_in2 : nullptr, c_in2, d_weight, K, c_out, d_table, n_out, reverse_k,
                               d_bias, d_out, d_bn_sums, static_cast<cudaStream_t>(stream_));
   if (rc == LGS_E_UNSUPPORTED) return fail(rc, "lgs_conv_fwd2: shape %d+%d->%d not supported", c_in, c_in2, c_out);
+  return rc;
+}
+
+
+int lgs_conv_fwd3(const float* d_in, int32_t c_in, const float* d_in2, int32_t c_in2, int64_t n_in, const void* d_weight,
+                  int32_t K, int32_t c_out, const int32_t* d_table, const void* d_plan, int64_t n_out, int32_t reverse_k,
+                  const float* d_bias, float* d_out, double* d_bn_sums, void* stream_) {
+  if (!d_plan || !lgs_nbplan_supported(n_out, K) || n_in != n_out || !conv_nb_shape_ok(c_in, c_in2, c_out, K))
+    return lgs_conv_fwd2(d_in, c_in, d_in2, c_in2, n_in, d_weight, K, c_out, d_table, n_out, reverse_k, d_bias, d_out, d_bn_sums, stream_);
+  LGS_TRACE("lgs_conv_fwd3 %p %d %p %d %lld %p %d %d %p %p %lld %d %p %p %p %p", (const void*)d_in, (int)c_in, (const void*)d_in2, (int)c_in2, (long long)n_in, (const void*)d_weight, (int)K, (int)c_out, (const void*)d_table, (const void*)d_plan, (long long)n_out, (int)reverse_k, (const void*)d_bias, (const void*)d_out, (const void*)d_bn_sums, (const void*)stream_);
+  if (!d_in || (c_in2 > 0 && !d_in2) || !d_weight || !d_out) return fail(LGS_E_INVALID, "lgs_conv_fwd3: null pointer");
+  const int rc = conv_fwd_nb(d_in, c_in, c_in2 > 0 ? d_in2 : nullptr, c_in2, d_weight, K, c_out, d_plan, n_out, reverse_k, d_bias,
+                             d_out, d_bn_sums, static_cast<cudaStream_t>(stream_));
+  if (rc == LGS_E_UNSUPPORTED)
+    return lgs_conv_fwd2(d_in, c_in, d_in2, c_in2, n_in, d_weight, K, c_out, d_table, n_out, reverse_k, d_bias, d_out, d_bn_sums, stream_);
   return rc;
 }
 

@@ -53,6 +53,16 @@ void trace_record(const char* fmt, ...);
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// geometry of a neighbourhood plan (nbplan.cu): offsets in int32 words from the start of the plan buffer
+struct NbGeom {
+  int K, tm, rt, RS, umax;
+  int64_t S, off_order, off_ucount, off_uniq, off_loc, words;
+};
+NbGeom nb_geometry(int64_t n_out, int K);
+int nb_tune(const char* key, int value);
+int nb_min_rows();
+int nb_disabled();
+
 // ---- coordinate keys ---------------------------------------------------------------------------------
 // 64-bit key: batch 10 bit | x 18 bit | y 18 bit | z 18 bit (two's complement fields).
 constexpr int kCoordBits = 18;

@@ -1,0 +1,449 @@
+// conv_nb: 3x3x3 same-map sparse convolution on the large coordinate maps, bf16x3 products (LGS_ALGO_BX3 numerics), with the
+// gather served from a shared-memory NEIGHBOURHOOD CACHE instead of one cp.async per (row, offset) pair.
+//
+// conv_bx3.cu is bound by the number of (row, offset) slots it copies: 27 x 128 rows x 128 B per channel block and tile,
+// ~45 % of them zero-fill, a warp-level cp.async costing ~17 cycles whatever its lanes do (profiles/r2_bx3_kernel_variants.txt)
+// — 870 cycles per (tile, offset, channel block) stage where the three MMAs need 288.  The neighbourhood plan (nbplan.cu)
+// groups output rows into spatially compact supertiles whose 27-neighbourhoods overlap almost entirely: ~415 unique input
+// rows per 256 output rows instead of 3 800 gathered ones.  This kernel therefore
+//   - loads the supertile's unique rows ONCE per 32-channel block into shared memory (2 fill warps, 16-byte cp.async:
+//     ~50 copies per row tile and channel block instead of 864),
+//   - builds every offset's A operand from that cache: splitter thread <-> output row <-> TMEM lane reads its neighbour's
+//     128 bytes by LOCAL index (16 bit, plan `loc`), splits into bf16 hi / lo and tcgen05.st's them behind the accumulators
+//     (TS-form MMAs as in conv_bx3.cu).  Cache rows are unswizzled and thread t reads chunk (i ^ (t & 7)) in step i, so the
+//     eight threads of a quarter-warp always hit eight different 16-byte bank groups whatever rows they read; a 3-level
+//     select network puts the chunks back in channel order,
+//   - runs TWO CTAs per SM (256 threads, <= 113 KB of shared memory, 256 TMEM columns each): one CTA's cache refill between
+//     channel blocks hides behind the other CTA's MMAs.
+// Loop nest per CTA: channel block -> offset -> row tile (TM = 2); one weight block [n_tile x (hi|lo)] per (channel block,
+// offset) by TMA, shared by both row tiles.  Output rows are written to their own positions (`order`), so tensors keep
+// MinkowskiEngine's row order; every output row accumulates its 27 x c_in products in the same sequence as in conv_bx3.cu.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace lgs {
+namespace nb {
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int ROW_BYTES = 128;                    // fp32 bytes of one channel block (32 channels) per cached row
+constexpr int THREADS = 256;                      // warps 0-3 splitters + epilogue, 4 MMA, 5 weight TMA, 6-7 cache fill
+constexpr int FILL_THREADS = 64;
+constexpr int MAX_B = 4, MAX_TA = 4;
+constexpr int TA_COLS = 32;
+
+struct Params {
+  const uint8_t* in;
+  const uint8_t* in2;
+  int32_t row_bytes, row_bytes2;
+  int32_t nkb1, num_kb;
+  int32_t K, c_out;
+  const int32_t* order;      // [S][RS] output row of every slot, -1 = padding
+  const int32_t* ucount;     // [S]
+  const int32_t* uniq;       // [S][umax] input rows of the supertile
+  const uint16_t* loc;       // [S][K][RS] local index of slot's neighbour at offset k, 0xFFFF = none
+  int32_t RS, rt, TM, umax;
+  int32_t reverse_k;
+  const float* bias;
+  float* out;
+  int32_t n_tile, b_stages, ta_stages, ta_col0, tmem_cols, b_stage_bytes;
+  double* stats;
+};
+
+__device__ __forceinline__ void umma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void split2(float e0, float e1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
+  const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+  const float r0 = e0 - __uint_as_float(hb << 16);
+  const float r1 = e1 - __uint_as_float(hb & 0xFFFF0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+  hi = hb;
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+__device__ __forceinline__ float4 sel4(bool c, const float4& a, const float4& b) {
+  return make_float4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w);
+}
+
+__global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int SB = p.b_stages, TM = p.TM, STA = p.ta_stages, K = p.K, num_kb = p.num_kb, umax = p.umax;
+  const uint32_t b_bytes = uint32_t(p.b_stage_bytes);
+  uint8_t* b_ring = smem;                                           // 1024-aligned (SWIZZLE_128B TMA destination)
+  uint8_t* cache = b_ring + size_t(SB) * b_bytes;                   // [(umax + 1)][128 B], row umax = zeros
+  int32_t* s_uniq = reinterpret_cast<int32_t*>(cache + size_t(umax + 1) * ROW_BYTES);
+  float* s_stats = reinterpret_cast<float*>(s_uniq + umax);         // [2][256]
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(s_stats + 512);
+  uint64_t* b_empty = b_full + MAX_B;
+  uint64_t* ta_full = b_empty + MAX_B;
+  uint64_t* ta_empty = ta_full + MAX_TA;
+  uint64_t* cache_full = ta_empty + MAX_TA;
+  uint64_t* cache_empty = cache_full + 1;
+  uint64_t* acc_bar = cache_empty + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t s = blockIdx.x;
+  const int n0 = blockIdx.y * p.n_tile;
+  const int U = min(__ldg(p.ucount + s), umax);
+
+  if (tid == 0) {
+    for (int i = 0; i < MAX_B; ++i) {
+      mbar_init(b_full + i, 1);
+      mbar_init(b_empty + i, 1);
+    }
+    for (int i = 0; i < MAX_TA; ++i) {
+      mbar_init(ta_full + i, 128);
+      mbar_init(ta_empty + i, 1);
+    }
+    mbar_init(cache_full, FILL_THREADS);
+    mbar_init(cache_empty, 128);
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(uint32_t(p.tmem_cols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 5 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+  for (int u = tid; u < U; u += THREADS) s_uniq[u] = __ldg(p.uniq + s * umax + u);
+  if (tid < 32) reinterpret_cast<float*>(cache + size_t(umax) * ROW_BYTES)[tid] = 0.f;     // the "no neighbour" row
+  if (p.stats)
+    for (int i = tid; i < 512; i += THREADS) s_stats[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < 4) {
+    // =================================== splitters: cache row -> bf16 hi / lo -> TMEM ===================================
+    const int r = warp * 32 + lane;                 // row of the tile = TMEM lane (warp w may touch lanes [32w, 32w + 32))
+    const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+    const uint32_t cache_base = smem_u32(cache);
+    const int rot = lane & 7;
+    const uint16_t* locb = p.loc + s * int64_t(K) * p.RS;
+    const bool row_in_tile = r < p.rt;
+    const int M = K * TM;                           // stages per channel block
+    auto fetch = [&](int m) -> uint32_t {
+      const int ki = m / TM, t = m - ki * TM;
+      const int kk = p.reverse_k ? K - 1 - ki : ki;
+      return row_in_tile ? uint32_t(__ldg(locb + int64_t(kk) * p.RS + t * p.rt + r)) : 0xFFFFu;
+    };
+    uint32_t nx0 = fetch(0), nx1 = fetch(1 % M);
+    int ts = 0;
+    uint32_t pht = 0, phc = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(cache_full, phc);                   // this channel block of every unique row has landed
+      phc ^= 1;
+      for (int m = 0; m < M; ++m) {
+        const uint32_t cur = nx0;
+        nx0 = nx1;
+        int m2 = m + 2;
+        if (m2 >= M) m2 -= M;
+        nx1 = fetch(m2);                            // two stages ahead (the index stream repeats per channel block)
+        const uint32_t j = cur < uint32_t(umax) ? cur : uint32_t(umax);
+        const uint32_t row_addr = cache_base + j * ROW_BYTES;
+        float4 q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = lds128(row_addr + (uint32_t(i ^ rot) << 4));
+        // q[i] holds chunk i ^ rot; chunk c = q[c ^ rot]: three conditional butterfly stages
+        float4 a[8], b[8], c[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = sel4(rot & 1, q[i ^ 1], q[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = sel4(rot & 2, a[i ^ 2], a[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = sel4(rot & 4, b[i ^ 4], b[i]);
+        uint32_t w[32];                             // [0,16): hi pairs, [16,32): lo pairs
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          split2(c[i].x, c[i].y, w[2 * i], w[16 + 2 * i]);
+          split2(c[i].z, c[i].w, w[2 * i + 1], w[16 + 2 * i + 1]);
+        }
+        mbar_wait(ta_empty + ts, pht ^ 1);          // MMAs that read this TMEM stage last time are done
+        tc_fence_after();
+        tmem_st32(tmem_base + lane_addr + uint32_t(p.ta_col0 + ts * TA_COLS), w);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(ta_full + ts);
+        if (++ts == STA) {
+          ts = 0;
+          pht ^= 1;
+        }
+      }
+      mbar_arrive(cache_empty);                     // every read of this channel block's cache is in registers / TMEM
+    }
+
+    // =================================== epilogue ===================================
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int ncols = min(p.n_tile, p.c_out - n0);
+    for (int t = 0; t < TM; ++t) {
+      const int32_t o = row_in_tile ? __ldg(p.order + s * p.RS + t * p.rt + r) : -1;
+      const bool row_ok = o >= 0;
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_addr + uint32_t(t * p.n_tile + c0), v);
+        if (p.bias) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj)
+            if (c0 + jj < ncols) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __ldg(p.bias + n0 + c0 + jj));
+        }
+        if (row_ok) {
+          float* orow = p.out + size_t(o) * p.c_out + n0 + c0;
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 4) {
+            if (c0 + jj + 3 < ncols) {
+              float4 x;
+              x.x = __uint_as_float(v[jj]);
+              x.y = __uint_as_float(v[jj + 1]);
+              x.z = __uint_as_float(v[jj + 2]);
+              x.w = __uint_as_float(v[jj + 3]);
+              *reinterpret_cast<float4*>(orow + jj) = x;
+            } else {
+              for (int e = jj; e < jj + 4; ++e)
+                if (c0 + e < ncols) orow[e] = __uint_as_float(v[e]);
+            }
+          }
+        }
+        if (p.stats) {
+          // BatchNorm statistics of the output from the accumulator registers (as in conv_bx3.cu): a butterfly over the
+          // warp's 32 rows leaves lane L with the sums of column c0 + L
+          float s1[32], s2[32];
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const float x = row_ok ? __uint_as_float(v[jj]) : 0.f;
+            s1[jj] = x;
+            s2[jj] = x * x;
+          }
+#pragma unroll
+          for (int w2 = 16; w2 >= 1; w2 >>= 1) {
+            const bool upper = (lane & w2) != 0;
+#pragma unroll
+            for (int jj = 0; jj < w2; ++jj) {
+              const float a1 = upper ? s1[jj] : s1[jj + w2], a2 = upper ? s2[jj] : s2[jj + w2];
+              const float k1 = upper ? s1[jj + w2] : s1[jj], k2 = upper ? s2[jj + w2] : s2[jj];
+              s1[jj] = k1 + __shfl_xor_sync(0xffffffffu, a1, w2);
+              s2[jj] = k2 + __shfl_xor_sync(0xffffffffu, a2, w2);
+            }
+          }
+          if (c0 + lane < ncols) {
+            atomicAdd(s_stats + c0 + lane, s1[0]);
+            atomicAdd(s_stats + 256 + c0 + lane, s2[0]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // =================================== MMA issuer (warp-uniform loop, one elected lane issues) ================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(p.n_tile >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+    const uint32_t desc_hi = uint32_t(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+    const uint32_t b_ring_base = smem_u32(b_ring);
+    int sb = 0, tsa = 0;
+    uint32_t phb = 0, phta = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const bool second = kb >= p.nkb1;
+      const int valid = min(ROW_BYTES, second ? p.row_bytes2 - (kb - p.nkb1) * ROW_BYTES : p.row_bytes - kb * ROW_BYTES);
+      const int ksteps = (valid + 63) >> 6;          // 16 channels (64 bytes of fp32) per instruction
+      for (int ki = 0; ki < K; ++ki) {
+        mbar_wait(b_full + sb, phb);
+        const uint32_t b_base = b_ring_base + uint32_t(sb) * b_bytes;
+        const uint32_t b_lo32 = ((b_base >> 4) & 0x3FFF) | (1u << 16);
+        const uint32_t acc_flag = (ki | kb) ? 1u : 0u;
+        for (int t = 0; t < TM; ++t) {
+          const uint32_t d_addr = tmem_base + uint32_t(t * p.n_tile);
+          mbar_wait(ta_full + tsa, phta);
+          tc_fence_after();
+          const uint32_t a_tm = tmem_base + uint32_t(p.ta_col0 + tsa * TA_COLS);
+          if (elect_one()) {
+#pragma unroll 2
+            for (int j = 0; j < ksteps; ++j) {
+              const uint64_t b_hi = desc_from(b_lo32 + 2 * j, desc_hi);
+              const uint64_t b_lo = desc_from(b_lo32 + 4 + 2 * j, desc_hi);
+              umma_ts_f16(d_addr, a_tm + 8 * j, b_hi, idesc, acc_flag | uint32_t(j));
+              umma_ts_f16(d_addr, a_tm + 16 + 8 * j, b_hi, idesc, 1u);
+              umma_ts_f16(d_addr, a_tm + 8 * j, b_lo, idesc, 1u);
+            }
+            umma_commit(ta_empty + tsa);
+          }
+          __syncwarp();
+          if (++tsa == STA) {
+            tsa = 0;
+            phta ^= 1;
+          }
+        }
+        if (elect_one()) umma_commit(b_empty + sb);
+        __syncwarp();
+        if (++sb == SB) {
+          sb = 0;
+          phb ^= 1;
+        }
+      }
+    }
+    if (elect_one()) umma_commit(acc_bar);
+    __syncwarp();
+  } else if (warp == 5) {
+    // =================================== weight TMA producer ===================================
+    const uint32_t b_ring_base = smem_u32(b_ring);
+    int sb = 0;
+    uint32_t phb = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      for (int ki = 0; ki < K; ++ki) {
+        mbar_wait(b_empty + sb, phb ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(b_full + sb, b_bytes);
+          tma_load_2d(b_ring_base + uint32_t(sb) * b_bytes, &tmap_w, b_full + sb, kb * 64, ki * p.c_out + n0);
+        }
+        __syncwarp();
+        if (++sb == SB) {
+          sb = 0;
+          phb ^= 1;
+        }
+      }
+    }
+  } else {
+    // =================================== cache fill (64 threads): unique rows of the supertile, one channel block ==========
+    const int ft = tid - 6 * 32;
+    const int chunk = ft & 7, rsub = ft >> 3;        // 8 lanes cover one 128-byte row segment; 8 rows per pass
+    const uint32_t cache_base = smem_u32(cache);
+    uint32_t phe = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      if (kb > 0) {
+        mbar_wait(cache_empty, phe);                 // the splitters are done with the previous channel block
+        phe ^= 1;
+      }
+      const bool second = kb >= p.nkb1;
+      const int kbl = second ? kb - p.nkb1 : kb;
+      const int rb = second ? p.row_bytes2 : p.row_bytes;
+      const bool col_ok = kbl * ROW_BYTES + chunk * 16 < rb;
+      const uint8_t* src = (second ? p.in2 : p.in) + kbl * ROW_BYTES + chunk * 16;
+      for (int u = rsub; u < U; u += FILL_THREADS / 8) {
+        const int32_t row = s_uniq[u];
+        cp_async16(cache_base + uint32_t(u) * ROW_BYTES + uint32_t(chunk << 4), src + size_t(col_ok ? row : 0) * rb, col_ok ? 16u : 0u);
+      }
+      cp_async_mbar_arrive_noinc(cache_full);
+    }
+  }
+
+  __syncthreads();
+  if (p.stats) {
+    const int ncols = min(p.n_tile, p.c_out - n0);
+    double* dst = p.stats + size_t(blockIdx.x & 7) * 2 * p.c_out + n0;
+    for (int i = tid; i < ncols; i += THREADS) {
+      atomicAdd(dst + i, double(s_stats[i]));
+      atomicAdd(dst + p.c_out + i, double(s_stats[256 + i]));
+    }
+  }
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(p.tmem_cols))
+                 : "memory");
+  }
+}
+
+}  // namespace nb
+
+int conv_bx3_shape_ok(int c_in, int c_out);
+
+// 1 if conv_fwd_nb takes this layer on a map with a neighbourhood plan
+int conv_nb_shape_ok(int c_in, int c_in2, int c_out, int K) {
+  if (K != 27 || !conv_bx3_shape_ok(c_in, c_out)) return 0;
+  if (c_in2 && (c_in % 32 != 0 || c_in2 % 4 != 0 || c_in2 < 4)) return 0;
+  if (c_out % 16 != 0 || c_out > 384) return 0;
+  return 1;
+}
+
+// in2 / c_in2: optional second gather source as in conv_fwd_bx3.  d_plan: lgs_nbplan_build output for (n_out, K).
+int conv_fwd_nb(const void* in, int c_in, const void* in2, int c_in2, const void* w, int K, int c_out, const void* d_plan,
+                int64_t n_out, int reverse_k, const float* bias, float* out, double* stats, cudaStream_t stream) {
+  using namespace nb;
+  if (!conv_nb_shape_ok(c_in, in2 ? c_in2 : 0, c_out, K)) return LGS_E_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(in2) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(d_plan) & 15))
+    return LGS_E_UNSUPPORTED;
+  if (n_out == 0) return LGS_OK;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return fail(LGS_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_nb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+  });
+  if (attr_err != cudaSuccess) return fail(LGS_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+
+  const NbGeom g = nb_geometry(n_out, K);
+  const int32_t* plan = static_cast<const int32_t*>(d_plan);
+  Params q;
+  q.in = static_cast<const uint8_t*>(in);
+  q.in2 = static_cast<const uint8_t*>(in2);
+  q.row_bytes = c_in * 4;
+  q.row_bytes2 = in2 ? c_in2 * 4 : 0;
+  q.nkb1 = (q.row_bytes + ROW_BYTES - 1) / ROW_BYTES;
+  q.num_kb = q.nkb1 + (in2 ? (q.row_bytes2 + ROW_BYTES - 1) / ROW_BYTES : 0);
+  q.K = K;
+  q.c_out = c_out;
+  q.order = plan + g.off_order;
+  q.ucount = plan + g.off_ucount;
+  q.uniq = plan + g.off_uniq;
+  q.loc = reinterpret_cast<const uint16_t*>(plan + g.off_loc);
+  q.RS = g.RS, q.rt = g.rt, q.TM = g.tm, q.umax = g.umax;
+  q.reverse_k = reverse_k;
+  q.bias = bias;
+  q.out = out;
+  q.stats = stats;
+  // output channels per CTA: TM accumulators + >= 2 split-A stages within 256 TMEM columns (two CTAs share an SM's 512)
+  const int max_nt = ((256 - 2 * TA_COLS) / g.tm) & ~15;          // 96 for TM = 2
+  const int ns = (c_out + max_nt - 1) / max_nt;
+  const int nt = ((((c_out + ns - 1) / ns) + 15) / 16) * 16;
+  q.n_tile = nt;
+  q.b_stage_bytes = nt * ROW_BYTES;
+  q.ta_col0 = ((g.tm * nt + 31) / 32) * 32;
+  q.ta_stages = std::min(MAX_TA, (256 - q.ta_col0) / TA_COLS);
+  int cols = 32;
+  while (cols < q.ta_col0 + q.ta_stages * TA_COLS) cols <<= 1;
+  q.tmem_cols = cols;
+  const size_t fixed = size_t(g.umax + 1) * ROW_BYTES + size_t(g.umax) * 4 + 2048 + (2 * MAX_B + 2 * MAX_TA + 3) * 8 + 16 + 1024;
+  int sb = 3;
+  while (sb > 2 && fixed + size_t(sb) * q.b_stage_bytes > 113 * 1024) --sb;
+  if (fixed + size_t(sb) * q.b_stage_bytes > 113 * 1024) return LGS_E_UNSUPPORTED;
+  q.b_stages = sb;
+  const size_t smem = fixed + size_t(sb) * q.b_stage_bytes;
+
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {cuuint64_t(q.num_kb) * 64, cuuint64_t(K) * cuuint64_t(c_out)};
+  const cuuint64_t gstride[1] = {cuuint64_t(q.num_kb) * 128};
+  const cuuint32_t box[2] = {64, cuuint32_t(nt)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(LGS_E_CUDA, "cuTensorMapEncodeTiled (nb) failed (%d) c_in=%d c_out=%d K=%d", int(cr), c_in + c_in2, c_out, K);
+  const dim3 grid{unsigned(g.S), unsigned((c_out + nt - 1) / nt), 1u};
+  LGS_LAUNCH(conv_nb_kernel, grid, THREADS, smem, stream, tmap, q);
+  return LGS_OK;
+}
+
+}  // namespace lgs

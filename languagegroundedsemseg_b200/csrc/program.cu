@@ -210,10 +210,10 @@ int lgs_program_run(lgs_program* p, int32_t op_begin, int32_t op_end, const int6
       case LGS_OP_WEIGHT_PREP:   // 1 desc, 2 n_layers, 3 total_tiles, 4 nsplit
         rc = lgs_weight_prep_batch(static_cast<const int64_t*>(P(o[1])), int32_t(o[2]), o[3], int32_t(o[4]), LGS_F32, stream);
         break;
-      case LGS_OP_CONV: {        // 1 in, 2 c_in, 3 in2, 4 c_in2, 5 lvl_in, 6 weight, 7 K, 8 c_out, 9 table, 10 lvl_out, 11 reverse_k, 12 bias, 13 out, 14 stats flag
+      case LGS_OP_CONV: {        // 1 in, 2 c_in, 3 in2, 4 c_in2, 5 lvl_in, 6 weight, 7 K, 8 c_out, 9 table, 10 lvl_out, 11 reverse_k, 12 bias, 13 out, 14 stats flag, 15 plan
         double* sums = (o[14] && rows_of(o[10]) >= kFuseStatsMinRows) ? half(p->bn_half) : nullptr;
-        rc = lgs_conv_fwd2(static_cast<const float*>(P(o[1])), int32_t(o[2]), static_cast<const float*>(P(o[3])), int32_t(o[4]), rows_of(o[5]),
-                           P(o[6]), int32_t(o[7]), int32_t(o[8]), static_cast<const int32_t*>(P(o[9])), rows_of(o[10]), int32_t(o[11]),
+        rc = lgs_conv_fwd3(static_cast<const float*>(P(o[1])), int32_t(o[2]), static_cast<const float*>(P(o[3])), int32_t(o[4]), rows_of(o[5]),
+                           P(o[6]), int32_t(o[7]), int32_t(o[8]), static_cast<const int32_t*>(P(o[9])), P(o[15]), rows_of(o[10]), int32_t(o[11]),
                            static_cast<const float*>(P(o[12])), static_cast<float*>(P(o[13])), sums, stream);
         break;
       }

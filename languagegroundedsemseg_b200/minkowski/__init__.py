@@ -282,7 +282,11 @@ class _CoordMap:
 class KernelMap:
     """Output-stationary neighbour tables of one (in map, out map, kernel) triple.
     fwd_table [K, n_out] rows of the input map; bwd_table [K, n_in] rows of the output map (dgrad)."""
-    __slots__ = ("K", "n_in", "n_out", "fwd_table", "bwd_table", "bwd_reverse", "counts")
+    __slots__ = ("K", "n_in", "n_out", "fwd_table", "bwd_table", "bwd_reverse", "counts", "plan", "plan_stats")
+    # plan: neighbourhood plan of a large same-map 3^3 table (lgs_nbplan_build; None when not built / not usable)
+
+    def __init__(self):
+        self.plan = self.plan_stats = None
 
 
 def _build_coordmap(coords: torch.Tensor, quant: int, want_maps: bool):
@@ -387,6 +391,22 @@ class CoordinateManager:
                                       _lib.ptr(table), _lib.ptr(counts), _stream()))
         return table, counts
 
+    def _plan(self, km, cmap):
+        """neighbourhood plan of a large same-map 3^3 kernel map: supertiles of spatially close output rows, their unique
+        input rows and the table in local indices (csrc/nbplan.cu), consumed by lgs_conv_fwd3.  One host sync (status)."""
+        lib = _lib.load()
+        if not _state.get("nbplan", True) or not lib.lgs_nbplan_supported(km.n_out, km.K):
+            return
+        dev = km.fwd_table.device
+        plan = torch.empty(lib.lgs_nbplan_bytes(km.n_out, km.K) // 4, dtype=torch.int32, device=dev)
+        scratch = torch.empty(lib.lgs_nbplan_scratch_bytes(km.n_out) // 4, dtype=torch.int32, device=dev)
+        status = (ctypes.c_int32 * 2)()
+        _lib.check(lib.lgs_nbplan_build(_lib.ptr(cmap.coords), km.n_out, _lib.ptr(km.fwd_table), km.K, _lib.ptr(plan),
+                                        _lib.ptr(scratch), ctypes.cast(status, ctypes.c_void_p), _stream()))
+        km.plan_stats = (int(status[0]), int(status[1]))
+        if status[0] == 0:
+            km.plan = plan
+
     def _transpose(self, table, n_in):
         lib = _lib.load()
         K, n_out = table.shape
@@ -416,6 +436,7 @@ class CoordinateManager:
             if in_key == out_key and ks % 2 == 1:
                 # C_in[i] = C[o] + off_k  <=>  C[o] = C_in[i] + off_{K-1-k}: dgrad reads the same table mirrored
                 km.bwd_table, km.bwd_reverse = km.fwd_table, True
+                self._plan(km, self._maps[out_key])
             else:
                 km.bwd_table, km.bwd_reverse = self._transpose(km.fwd_table, km.n_in), False
         self._kmaps[ck] = km
@@ -430,7 +451,7 @@ class CoordinateManager:
                     seen.add(id(t))
                     yield t
         for km in self._kmaps.values():
-            for t in (km.fwd_table, km.bwd_table, km.counts):
+            for t in (km.fwd_table, km.bwd_table, km.counts, km.plan):
                 if t is not None and id(t) not in seen:
                     seen.add(id(t))
                     yield t
@@ -868,9 +889,14 @@ def _conv_fwd_impl(feats, weight, bias, km, algo, need_dgrad, module=None):
         w32 = weights32() if w32 is None else w32
         wf, layout, a = w32.to(feats.dtype), _lib.W_KCN, _lib.ALGO_SIMT
     with _Timed("fwd", K, c_in, c_out, n_in, n_out, km, feats.dtype):
-        _lib.check(lib.lgs_conv_fwd(_lib.ptr(feats), n_in, c_in, _lib.ptr(wf), layout, K, c_out,
-                                    _lib.ptr(km.fwd_table) if km is not None else None, n_out, 0, _lib.ptr(b32),
-                                    _lib.ptr(out), dt, a, _stream()))
+        if a == _lib.ALGO_BX3 and km is not None and km.plan is not None and dt == _lib.F32:
+            # large same-map 3^3 map: neighbourhood-cache kernel (same products and per-row accumulation order)
+            _lib.check(lib.lgs_conv_fwd3(_lib.ptr(feats), c_in, None, 0, n_in, _lib.ptr(wf), K, c_out, _lib.ptr(km.fwd_table),
+                                         _lib.ptr(km.plan), n_out, 0, _lib.ptr(b32), _lib.ptr(out), None, _stream()))
+        else:
+            _lib.check(lib.lgs_conv_fwd(_lib.ptr(feats), n_in, c_in, _lib.ptr(wf), layout, K, c_out,
+                                        _lib.ptr(km.fwd_table) if km is not None else None, n_out, 0, _lib.ptr(b32),
+                                        _lib.ptr(out), dt, a, _stream()))
     if need_dgrad and not bwd_tc:
         w_bwd = (weights32() if w32 is None else w32).to(feats.dtype)                           # [K, c_in, c_out] read as LGS_W_KNC by the SIMT dgrad
     m = _ConvMeta()
@@ -911,10 +937,14 @@ def _conv_bwd_impl(m, feats, w_bwd, gout, need_gin, need_gw, need_gb):
         gin = torch.empty((n_in, c_in), dtype=feats.dtype, device=feats.device)
         layout, a = (m.tc_layout, algo) if m.bwd_tc else (_lib.W_KNC, _lib.ALGO_SIMT)
         with _Timed("dgrad", K, c_out, c_in, n_out, n_in, km, feats.dtype):
-            _lib.check(lib.lgs_conv_fwd(_lib.ptr(gout), n_out, c_out, _lib.ptr(w_bwd), layout, K, c_in,
-                                        _lib.ptr(km.bwd_table) if km is not None else None, n_in,
-                                        1 if (km is not None and km.bwd_reverse) else 0, None, _lib.ptr(gin), dt,
-                                        a, _stream()))
+            if a == _lib.ALGO_BX3 and km is not None and km.plan is not None and km.bwd_reverse and dt == _lib.F32:
+                _lib.check(lib.lgs_conv_fwd3(_lib.ptr(gout), c_out, None, 0, n_out, _lib.ptr(w_bwd), K, c_in, _lib.ptr(km.bwd_table),
+                                             _lib.ptr(km.plan), n_in, 1, None, _lib.ptr(gin), None, _stream()))
+            else:
+                _lib.check(lib.lgs_conv_fwd(_lib.ptr(gout), n_out, c_out, _lib.ptr(w_bwd), layout, K, c_in,
+                                            _lib.ptr(km.bwd_table) if km is not None else None, n_in,
+                                            1 if (km is not None and km.bwd_reverse) else 0, None, _lib.ptr(gin), dt,
+                                            a, _stream()))
     if need_gw:
         if joined is not None:
             joined.wait_event(ev_join)                        # training stream waits for the side-stream wgrad

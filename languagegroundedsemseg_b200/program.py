@@ -76,6 +76,7 @@ class NativeStep:
         self._ext_static, self._ext_dynamic, self._keep, self._ext_cache = [], {}, [], {}    # [(slot, getter)], name -> slot, ...
         self._n_ext = 0
         self._tables = {}             # (level_in, ks, stride, transpose, 'fwd'|'bwd') -> buffer
+        self._plans = {}              # level -> buffer (neighbourhood plan of the level's 3^3 same-map kernel map)
         self._layers = []             # (conv module, weight source tensor, K, c_in_padded, c_out, fwd operand, bwd operand)
         self.marks = {}
         self._build()
@@ -119,13 +120,25 @@ class NativeStep:
     def _op(self, code, *args):
         row = [code] + [a.id if isinstance(a, _Buf) else (-1 if a is None else int(a)) for a in args]
         assert len(row) <= OP_WORDS
-        self._ops.append(row + [0] * (OP_WORDS - len(row)))
+        row = row + [0] * (OP_WORDS - len(row))
+        if code == OP_CONV and len(args) < 15:
+            row[15] = -1                # no neighbourhood plan
+        self._ops.append(row)
 
     def _table(self, level_in, ks, stride, transpose, which):
         key = (level_in, ks, stride, transpose, which)
         if key not in self._tables:
             self._tables[key] = self._ext(name=("table",) + key)
         return self._tables[key]
+
+    def _plan(self, conv, level):
+        """external slot of the neighbourhood plan of a same-map 3^3 convolution's kernel map (NULL at run time when the
+        manager built none: small map, or a supertile overflowed the cache) — word 15 of OP_CONV"""
+        if conv.use_mm or conv._ks != 3 or conv._stride != 1 or conv.TRANSPOSE:
+            return None
+        if level not in self._plans:
+            self._plans[level] = self._ext(name=("plan", level))
+        return self._plans[level]
 
     # ---- layers ----------------------------------------------------------------------------------------------------
     def _conv_info(self, conv):
@@ -171,7 +184,8 @@ class NativeStep:
         out_level, t_fwd, _, _ = self._geometry(conv, level)
         assert x.c == rec["c_pad"], (x.c, rec["c_pad"])
         y = self._new(out_level, rec["c_out"])
-        self._op(OP_CONV, x, x.c, None, 0, level, rec["w_fwd"], rec["K"], rec["c_out"], t_fwd, out_level, 0, bias, y, 1 if stats else 0)
+        self._op(OP_CONV, x, x.c, None, 0, level, rec["w_fwd"], rec["K"], rec["c_out"], t_fwd, out_level, 0, bias, y, 1 if stats else 0,
+                 self._plan(conv, level))
         return y, out_level
 
     def _conv_bwd(self, conv, x, level, dy, need_gin=True):
@@ -190,7 +204,8 @@ class NativeStep:
             return None
         self._need_bwd_operand(rec)
         gin = self._new(level, rec["c_pad"])
-        self._op(OP_CONV, dy, rec["c_out"], None, 0, out_level, rec["w_bwd"], rec["K"], rec["c_pad"], t_bwd, level, rev, None, gin, 0)
+        self._op(OP_CONV, dy, rec["c_out"], None, 0, out_level, rec["w_bwd"], rec["K"], rec["c_pad"], t_bwd, level, rev, None, gin, 0,
+                 self._plan(conv, level))
         return gin
 
     def _cbr_fwd(self, conv, bn, x, level, relu, res=None):
@@ -422,6 +437,9 @@ class NativeStep:
             _, km = mgr.conv_maps(self._keys[level], ks, stride, 1, tr)
             t = km.fwd_table if which == "fwd" else km.bwd_table
             ext[self._bufs[buf.id][1]] = t.data_ptr()
+        for level, buf in self._plans.items():
+            _, km = mgr.conv_maps(self._keys[level], 3, 1, 1, False)
+            ext[self._bufs[buf.id][1]] = km.plan.data_ptr() if km.plan is not None else 0
         for l, key in enumerate(self._keys):
             self._rows_arr[l] = mgr.size(key)
         f = st.F
