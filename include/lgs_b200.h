@@ -163,8 +163,10 @@ int lgs_conv_fwd2(const float* d_in, int32_t c_in, const float* d_in2, int32_t c
  * this is a second form of the same map for the cache-based kernel).   Call sites served: the 3x3x3 stride-1 convolutions of
  * the fine U-Net levels, models/modules/common.py:195-203 via models/modules/resnet_block.py:23-34 and res16unet.py:38.
  * A plan regroups the output rows of a kernel map into spatially compact supertiles (Morton order over coarse cells), lists
- * the unique input rows each supertile touches and rewrites the table in supertile-local 16-bit indices; lgs_conv_fwd3 then
- * loads each supertile's rows into shared memory once per channel block instead of once per (row, offset) pair.
+ * the unique input rows each supertile touches and rewrites the table in supertile-local indices (uint16: 12-bit index, 0xFFF =
+ * no neighbour, | 3-bit bank colour << 12; uniq entries carry the row's colour << 28); lgs_conv_fwd3 then loads each
+ * supertile's rows into shared memory once per channel block instead of once per (row, offset) pair.  step = tensor stride x
+ * dilation of the map (the spacing of the kernel offsets, as in lgs_kmap_build).
  * Tensor row order is unchanged; results equal lgs_conv_fwd2's (same products, same accumulation order per row).
  *   lgs_nbplan_supported: 1 if a plan is worth building for this map (K == 27, n_out >= 148 * 128 unless tuned).
  *   lgs_nbplan_build: d_plan lgs_nbplan_bytes() bytes, d_scratch lgs_nbplan_scratch_bytes() bytes (both 16-byte aligned);
@@ -175,8 +177,8 @@ int lgs_conv_fwd2(const float* d_in, int32_t c_in, const float* d_in2, int32_t c
 int lgs_nbplan_supported(int64_t n_out, int32_t K);
 int64_t lgs_nbplan_bytes(int64_t n_out, int32_t K);
 int64_t lgs_nbplan_scratch_bytes(int64_t n_out);
-int lgs_nbplan_build(const int32_t* d_out_coords, int64_t n_out, const int32_t* d_table, int32_t K, void* d_plan, void* d_scratch,
-                     int32_t* h_status, void* stream);
+int lgs_nbplan_build(const int32_t* d_out_coords, int64_t n_out, const int32_t* d_table, int32_t K, int32_t step, void* d_plan,
+                     void* d_scratch, int32_t* h_status, void* stream);
 /* out[0..8] = tm, rt, RS, S, umax, then the int32-word offsets of order [S][RS], ucount [S], uniq [S][umax] and loc
  * (uint16 [S][K][RS]) inside the plan buffer (tests, tools) */
 int lgs_nbplan_geometry(int64_t n_out, int32_t K, int64_t* out);

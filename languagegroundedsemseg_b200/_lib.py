@@ -37,7 +37,7 @@ SIGNATURES = {
     "lgs_nbplan_supported": (C.c_int, [_i64, _i32]),
     "lgs_nbplan_bytes": (_i64, [_i64, _i32]),
     "lgs_nbplan_scratch_bytes": (_i64, [_i64]),
-    "lgs_nbplan_build": (C.c_int, [_p, _i64, _p, _i32, _p, _p, _p, _p]),
+    "lgs_nbplan_build": (C.c_int, [_p, _i64, _p, _i32, _i32, _p, _p, _p, _p]),
     "lgs_nbplan_geometry": (C.c_int, [_i64, _i32, C.POINTER(_i64)]),
     "lgs_weight_bx3_elems": (_i64, [_i32, _i32, _i32]),
     "lgs_conv_wgrad": (C.c_int, [_p, _i64, _i32, _p, _i64, _i32, _p, _i32, _p, _i32, _i32, _p]),

@@ -6,13 +6,15 @@
 // — 870 cycles per (tile, offset, channel block) stage where the three MMAs need 288.  The neighbourhood plan (nbplan.cu)
 // groups output rows into spatially compact supertiles whose 27-neighbourhoods overlap almost entirely: ~415 unique input
 // rows per 256 output rows instead of 3 800 gathered ones.  This kernel therefore
-//   - loads the supertile's unique rows ONCE per 32-channel block into shared memory (2 fill warps, 16-byte cp.async:
-//     ~50 copies per row tile and channel block instead of 864),
-//   - builds every offset's A operand from that cache: splitter thread <-> output row <-> TMEM lane reads its neighbour's
-//     128 bytes by LOCAL index (16 bit, plan `loc`), splits into bf16 hi / lo and tcgen05.st's them behind the accumulators
-//     (TS-form MMAs as in conv_bx3.cu).  Cache rows are unswizzled and thread t reads chunk (i ^ (t & 7)) in step i, so the
-//     eight threads of a quarter-warp always hit eight different 16-byte bank groups whatever rows they read; a 3-level
-//     select network puts the chunks back in channel order,
+//   - loads the supertile's unique rows ONCE per 32-channel block, splits them into bf16 hi / lo THERE (once per unique row and
+//     channel block instead of once per (row, offset): 16x less conversion work — the first version split in the row threads and
+//     was bound by the ALU pipe, 52 % active against 40 % tensor pipe, profiles/r2_conv_nb_v1_ncu.txt) and stores them in the
+//     shared-memory cache as [32 x hi | 32 x lo] = 128 bytes per row, chunk c at position (c + colour) mod 8,
+//   - builds every offset's A operand from that cache: row thread <-> output row <-> TMEM lane reads its neighbour's 128 bytes
+//     by LOCAL index (plan `loc`: 12-bit index + 3-bit colour) with eight 16-byte loads and tcgen05.st's them behind the
+//     accumulators (TS-form MMAs as in conv_bx3.cu) — no arithmetic on the data.  The plan orders the slots of a supertile so
+//     that the eight lanes of a quarter-warp read rows of eight different colours for every offset, i.e. eight different bank
+//     groups in every step (nbplan.cu, "Colours"),
 //   - runs TWO CTAs per SM (256 threads, <= 113 KB of shared memory, 256 TMEM columns each): one CTA's cache refill between
 //     channel blocks hides behind the other CTA's MMAs.
 // Loop nest per CTA: channel block -> offset -> row tile (TM = 2); one weight block [n_tile x (hi|lo)] per (channel block,
@@ -33,8 +35,10 @@ using namespace tc;
 
 constexpr int BM = 128;
 constexpr int ROW_BYTES = 128;                    // fp32 bytes of one channel block (32 channels) per cached row
-constexpr int THREADS = 256;                      // warps 0-3 splitters + epilogue, 4 MMA, 5 weight TMA, 6-7 cache fill
-constexpr int FILL_THREADS = 64;
+constexpr int THREADS = 256;                      // warps 0-3 row threads (fill, A operand, epilogue), 4 and 6 MMA, 5 weight TMA, 7 fill
+constexpr int FILL_THREADS = 160;                 // warps 0-3 and 7 refill the cache together between channel blocks
+constexpr int TM = 2;                             // row tiles per supertile (nb_geometry's tm)
+constexpr int FILL_UNROLL = 6;
 constexpr int MAX_B = 4, MAX_TA = 4;
 constexpr int TA_COLS = 32;
 
@@ -46,9 +50,9 @@ struct Params {
   int32_t K, c_out;
   const int32_t* order;      // [S][RS] output row of every slot, -1 = padding
   const int32_t* ucount;     // [S]
-  const int32_t* uniq;       // [S][umax] input rows of the supertile
-  const uint16_t* loc;       // [S][K][RS] local index of slot's neighbour at offset k, 0xFFFF = none
-  int32_t RS, rt, TM, umax;
+  const int32_t* uniq;       // [S][umax] input rows of the supertile | colour << 28
+  const uint16_t* loc;       // [S][K][RS] local index of slot's neighbour at offset k (0xFFF = none) | colour << 12
+  int32_t RS, rt, umax;
   int32_t reverse_k;
   const float* bias;
   float* out;
@@ -74,20 +78,119 @@ __device__ __forceinline__ void split2(float e0, float e1, uint32_t& hi, uint32_
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void fill_bar() { asm volatile("bar.sync 1, %0;" ::"n"(FILL_THREADS) : "memory"); }
+
+// Cache refill of one channel block by the 192 fill threads: unique row u, 4-channel group c4 -> 16 bytes of fp32 from global
+// memory -> bf16 hi / lo pairs -> two 8-byte stores at the row's colour-rotated chunk positions.
+__device__ __forceinline__ void fill_cache(const uint8_t* in, const uint8_t* in2, int row_bytes, int row_bytes2, int nkb1, int kb, int ft,
+                                           int U, const int32_t* s_uniq, uint32_t cache_base) {
+  const int c4 = ft & 7, rsub = ft >> 3;             // 8 threads cover one 128-byte row segment; 24 rows per pass
+  const bool second = kb >= nkb1;
+  const int kbl = second ? kb - nkb1 : kb;
+  const int rb = second ? row_bytes2 : row_bytes;
+  const bool col_ok = kbl * ROW_BYTES + c4 * 16 < rb;
+  const uint8_t* src = (second ? in2 : in) + kbl * ROW_BYTES + c4 * 16;
+  constexpr int STEP = FILL_THREADS / 8;
+#pragma unroll 1
+  for (int u0 = rsub; u0 < U; u0 += STEP * FILL_UNROLL) {
+    float4 v[FILL_UNROLL];
+    int32_t e[FILL_UNROLL];
+#pragma unroll
+    for (int j = 0; j < FILL_UNROLL; ++j) {
+      const int u = u0 + j * STEP;
+      e[j] = u < U ? s_uniq[u] : -1;
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e[j] >= 0 && col_ok) v[j] = __ldg(reinterpret_cast<const float4*>(src + size_t(e[j] & 0x0FFFFFFF) * rb));
+    }
+#pragma unroll
+    for (int j = 0; j < FILL_UNROLL; ++j) {
+      if (e[j] < 0) continue;
+      const int u = u0 + j * STEP;
+      const uint32_t g = uint32_t(e[j]) >> 28;
+      uint32_t h0, l0, h1, l1;
+      split2(v[j].x, v[j].y, h0, l0);
+      split2(v[j].z, v[j].w, h1, l1);
+      const uint32_t row = cache_base + uint32_t(u) * ROW_BYTES + uint32_t((c4 & 1) << 3);
+      sts64(row + (((uint32_t(c4 >> 1) + g) & 7u) << 4), h0, h1);
+      sts64(row + (((uint32_t(4 + (c4 >> 1)) + g) & 7u) << 4), l0, l1);
+    }
+  }
 }
 
-__device__ __forceinline__ float4 sel4(bool c, const float4& a, const float4& b) {
-  return make_float4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w);
+// Epilogue of one row warp, out of line so that its register needs (three 32-word arrays for the fused BatchNorm sums) do not
+// spill loop-invariant values of the main loops: TMEM accumulators -> (+ bias) -> output rows at their own positions.
+__device__ __noinline__ void epilogue_rows(uint32_t tmem_lane_base, int n_tile, int ncols, int c_out, int n0, const float* bias,
+                                           float* out, const int32_t* order_s, int rt, int r, bool want_stats, float* s_stats) {
+  const int lane = threadIdx.x & 31;
+  for (int t = 0; t < TM; ++t) {
+    const int32_t o = r < rt ? __ldg(order_s + t * rt + r) : -1;
+    const bool row_ok = o >= 0;
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_lane_base + uint32_t(t * n_tile + c0), v);
+      if (bias) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+          if (c0 + jj < ncols) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __ldg(bias + n0 + c0 + jj));
+      }
+      if (row_ok) {
+        float* orow = out + size_t(o) * c_out + n0 + c0;
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 4) {
+          if (c0 + jj + 3 < ncols) {
+            float4 x;
+            x.x = __uint_as_float(v[jj]);
+            x.y = __uint_as_float(v[jj + 1]);
+            x.z = __uint_as_float(v[jj + 2]);
+            x.w = __uint_as_float(v[jj + 3]);
+            *reinterpret_cast<float4*>(orow + jj) = x;
+          } else {
+            for (int e = jj; e < jj + 4; ++e)
+              if (c0 + e < ncols) orow[e] = __uint_as_float(v[e]);
+          }
+        }
+      }
+      if (want_stats) {
+        // BatchNorm statistics of the output from the accumulator registers (as in conv_bx3.cu): a butterfly over the
+        // warp's 32 rows leaves lane L with the sums of column c0 + L
+        float s1[32], s2[32];
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const float x = row_ok ? __uint_as_float(v[jj]) : 0.f;
+          s1[jj] = x;
+          s2[jj] = x * x;
+        }
+#pragma unroll
+        for (int w2 = 16; w2 >= 1; w2 >>= 1) {
+          const bool upper = (lane & w2) != 0;
+#pragma unroll
+          for (int jj = 0; jj < w2; ++jj) {
+            const float a1 = upper ? s1[jj] : s1[jj + w2], a2 = upper ? s2[jj] : s2[jj + w2];
+            const float k1 = upper ? s1[jj + w2] : s1[jj], k2 = upper ? s2[jj + w2] : s2[jj];
+            s1[jj] = k1 + __shfl_xor_sync(0xffffffffu, a1, w2);
+            s2[jj] = k2 + __shfl_xor_sync(0xffffffffu, a2, w2);
+          }
+        }
+        if (c0 + lane < ncols) {
+          atomicAdd(s_stats + c0 + lane, s1[0]);
+          atomicAdd(s_stats + 256 + c0 + lane, s2[0]);
+        }
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int SB = p.b_stages, TM = p.TM, STA = p.ta_stages, K = p.K, num_kb = p.num_kb, umax = p.umax;
+  const int SB = p.b_stages, K = p.K, num_kb = p.num_kb, umax = p.umax;
+  const int NBUF = p.ta_stages / TM;                                // TMEM A buffers per row tile (tile t owns stages t + TM i)
   const uint32_t b_bytes = uint32_t(p.b_stage_bytes);
   uint8_t* b_ring = smem;                                           // 1024-aligned (SWIZZLE_128B TMA destination)
   uint8_t* cache = b_ring + size_t(SB) * b_bytes;                   // [(umax + 1)][128 B], row umax = zeros
@@ -97,9 +200,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_consta
   uint64_t* b_empty = b_full + MAX_B;
   uint64_t* ta_full = b_empty + MAX_B;
   uint64_t* ta_empty = ta_full + MAX_TA;
-  uint64_t* cache_full = ta_empty + MAX_TA;
-  uint64_t* cache_empty = cache_full + 1;
-  uint64_t* acc_bar = cache_empty + 1;
+  uint64_t* acc_bar = ta_empty + MAX_TA;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -110,15 +211,13 @@ __global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_consta
   if (tid == 0) {
     for (int i = 0; i < MAX_B; ++i) {
       mbar_init(b_full + i, 1);
-      mbar_init(b_empty + i, 1);
+      mbar_init(b_empty + i, TM);                    // one commit per MMA issuer warp
     }
     for (int i = 0; i < MAX_TA; ++i) {
       mbar_init(ta_full + i, 128);
       mbar_init(ta_empty + i, 1);
     }
-    mbar_init(cache_full, FILL_THREADS);
-    mbar_init(cache_empty, 128);
-    mbar_init(acc_bar, 1);
+    mbar_init(acc_bar, TM);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -138,165 +237,109 @@ __global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_consta
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp < 4) {
-    // =================================== splitters: cache row -> bf16 hi / lo -> TMEM ===================================
+    // =================================== row threads: cache row -> TMEM (no arithmetic on the data) ===================
     const int r = warp * 32 + lane;                 // row of the tile = TMEM lane (warp w may touch lanes [32w, 32w + 32))
     const uint32_t lane_addr = uint32_t(warp * 32) << 16;
     const uint32_t cache_base = smem_u32(cache);
-    const int rot = lane & 7;
-    const uint16_t* locb = p.loc + s * int64_t(K) * p.RS;
     const bool row_in_tile = r < p.rt;
-    const int M = K * TM;                           // stages per channel block
-    auto fetch = [&](int m) -> uint32_t {
-      const int ki = m / TM, t = m - ki * TM;
-      const int kk = p.reverse_k ? K - 1 - ki : ki;
-      return row_in_tile ? uint32_t(__ldg(locb + int64_t(kk) * p.RS + t * p.rt + r)) : 0xFFFFu;
-    };
-    uint32_t nx0 = fetch(0), nx1 = fetch(1 % M);
-    int ts = 0;
-    uint32_t pht = 0, phc = 0;
+    const uint32_t none = 0xFFFu | (uint32_t(lane & 7) << 12);
+    // index stream of this row slot: loc[kk][t * rt + r], kk ascending (forward) or descending (dgrad), fetched one offset ahead
+    const int64_t kstride = p.reverse_k ? -int64_t(p.RS) : int64_t(p.RS);
+    const uint16_t* lp0 = p.loc + s * int64_t(K) * p.RS + (p.reverse_k ? int64_t(K - 1) * p.RS : 0) + min(r, p.rt - 1);
+    const int rt = p.rt;
+    int buf = 0;
+    uint32_t pht = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(cache_full, phc);                   // this channel block of every unique row has landed
-      phc ^= 1;
-      for (int m = 0; m < M; ++m) {
-        const uint32_t cur = nx0;
-        nx0 = nx1;
-        int m2 = m + 2;
-        if (m2 >= M) m2 -= M;
-        nx1 = fetch(m2);                            // two stages ahead (the index stream repeats per channel block)
-        const uint32_t j = cur < uint32_t(umax) ? cur : uint32_t(umax);
-        const uint32_t row_addr = cache_base + j * ROW_BYTES;
-        float4 q[8];
+      if (kb > 0) fill_bar();                       // every row thread is done reading the previous channel block
+      fill_cache(p.in, p.in2, p.row_bytes, p.row_bytes2, p.nkb1, kb, tid, U, s_uniq, cache_base);
+      const uint16_t* lp = lp0;
+      uint32_t nx[TM];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) q[i] = lds128(row_addr + (uint32_t(i ^ rot) << 4));
-        // q[i] holds chunk i ^ rot; chunk c = q[c ^ rot]: three conditional butterfly stages
-        float4 a[8], b[8], c[8];
+      for (int t = 0; t < TM; ++t) nx[t] = row_in_tile ? uint32_t(__ldg(lp + t * rt)) : none;
+      fill_bar();                                   // this channel block of every unique row is in the cache
+#pragma unroll 1
+      for (int ki = 0; ki < K; ++ki) {
+        uint32_t cur[TM];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = sel4(rot & 1, q[i ^ 1], q[i]);
+        for (int t = 0; t < TM; ++t) cur[t] = nx[t];
+        if (ki + 1 < K) {
+          lp += kstride;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b[i] = sel4(rot & 2, a[i ^ 2], a[i]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) c[i] = sel4(rot & 4, b[i ^ 4], b[i]);
-        uint32_t w[32];                             // [0,16): hi pairs, [16,32): lo pairs
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          split2(c[i].x, c[i].y, w[2 * i], w[16 + 2 * i]);
-          split2(c[i].z, c[i].w, w[2 * i + 1], w[16 + 2 * i + 1]);
+          for (int t = 0; t < TM; ++t) nx[t] = row_in_tile ? uint32_t(__ldg(lp + t * rt)) : none;
         }
-        mbar_wait(ta_empty + ts, pht ^ 1);          // MMAs that read this TMEM stage last time are done
-        tc_fence_after();
-        tmem_st32(tmem_base + lane_addr + uint32_t(p.ta_col0 + ts * TA_COLS), w);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(ta_full + ts);
-        if (++ts == STA) {
-          ts = 0;
+#pragma unroll
+        for (int t = 0; t < TM; ++t) {
+          const uint32_t j = min(cur[t] & 0xFFFu, uint32_t(umax));
+          const uint32_t g = cur[t] >> 12;
+          const uint32_t row_addr = cache_base + j * ROW_BYTES;
+          uint32_t w[32];                           // [0,16): hi pairs, [16,32): lo pairs
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            lds128(row_addr + (((uint32_t(i) + g) & 7u) << 4), w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+          const int ts = t + buf * TM;
+          mbar_wait(ta_empty + ts, pht ^ 1);        // MMAs that read this TMEM stage last time are done
+          tc_fence_after();
+          tmem_st32(tmem_base + lane_addr + uint32_t(p.ta_col0 + ts * TA_COLS), w);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(ta_full + ts);
+        }
+        if (++buf == NBUF) {
+          buf = 0;
           pht ^= 1;
         }
       }
-      mbar_arrive(cache_empty);                     // every read of this channel block's cache is in registers / TMEM
     }
 
     // =================================== epilogue ===================================
     mbar_wait(acc_bar, 0);
     tc_fence_after();
-    const int ncols = min(p.n_tile, p.c_out - n0);
-    for (int t = 0; t < TM; ++t) {
-      const int32_t o = row_in_tile ? __ldg(p.order + s * p.RS + t * p.rt + r) : -1;
-      const bool row_ok = o >= 0;
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + lane_addr + uint32_t(t * p.n_tile + c0), v);
-        if (p.bias) {
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj)
-            if (c0 + jj < ncols) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __ldg(p.bias + n0 + c0 + jj));
-        }
-        if (row_ok) {
-          float* orow = p.out + size_t(o) * p.c_out + n0 + c0;
-#pragma unroll
-          for (int jj = 0; jj < 32; jj += 4) {
-            if (c0 + jj + 3 < ncols) {
-              float4 x;
-              x.x = __uint_as_float(v[jj]);
-              x.y = __uint_as_float(v[jj + 1]);
-              x.z = __uint_as_float(v[jj + 2]);
-              x.w = __uint_as_float(v[jj + 3]);
-              *reinterpret_cast<float4*>(orow + jj) = x;
-            } else {
-              for (int e = jj; e < jj + 4; ++e)
-                if (c0 + e < ncols) orow[e] = __uint_as_float(v[e]);
-            }
-          }
-        }
-        if (p.stats) {
-          // BatchNorm statistics of the output from the accumulator registers (as in conv_bx3.cu): a butterfly over the
-          // warp's 32 rows leaves lane L with the sums of column c0 + L
-          float s1[32], s2[32];
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const float x = row_ok ? __uint_as_float(v[jj]) : 0.f;
-            s1[jj] = x;
-            s2[jj] = x * x;
-          }
-#pragma unroll
-          for (int w2 = 16; w2 >= 1; w2 >>= 1) {
-            const bool upper = (lane & w2) != 0;
-#pragma unroll
-            for (int jj = 0; jj < w2; ++jj) {
-              const float a1 = upper ? s1[jj] : s1[jj + w2], a2 = upper ? s2[jj] : s2[jj + w2];
-              const float k1 = upper ? s1[jj + w2] : s1[jj], k2 = upper ? s2[jj + w2] : s2[jj];
-              s1[jj] = k1 + __shfl_xor_sync(0xffffffffu, a1, w2);
-              s2[jj] = k2 + __shfl_xor_sync(0xffffffffu, a2, w2);
-            }
-          }
-          if (c0 + lane < ncols) {
-            atomicAdd(s_stats + c0 + lane, s1[0]);
-            atomicAdd(s_stats + 256 + c0 + lane, s2[0]);
-          }
-        }
-      }
-    }
+    epilogue_rows(tmem_base + lane_addr, p.n_tile, min(p.n_tile, p.c_out - n0), p.c_out, n0, p.bias, p.out, p.order + s * p.RS, rt, r,
+                  p.stats != nullptr, s_stats);
     tc_fence_before();
-  } else if (warp == 4) {
-    // =================================== MMA issuer (warp-uniform loop, one elected lane issues) ================
+  } else if (warp == 4 || warp == 6) {
+    // =================================== MMA issuers: warp 4 <-> row tile 0, warp 6 <-> row tile 1 ================
+    // (a single issuing warp needed ~90 dependent instructions per 288-cycle stage and was ~80 % busy: profiles/r2_conv_nb_v2_ncu.txt)
+    const int t = warp == 4 ? 0 : 1;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(p.n_tile >> 3) << 17) | (uint32_t(BM >> 4) << 24);
     const uint32_t desc_hi = uint32_t(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
-    const uint32_t b_ring_base = smem_u32(b_ring);
-    int sb = 0, tsa = 0;
+    const uint32_t b_lo_base = ((smem_u32(b_ring) >> 4) & 0x3FFF) | (1u << 16);
+    const uint32_t b_lo_step = b_bytes >> 4;
+    const uint32_t d_addr = tmem_base + uint32_t(t * p.n_tile);
+    const uint32_t a_base = tmem_base + uint32_t(p.ta_col0 + t * TA_COLS);
+    int sb = 0, buf = 0;
     uint32_t phb = 0, phta = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
       const bool second = kb >= p.nkb1;
       const int valid = min(ROW_BYTES, second ? p.row_bytes2 - (kb - p.nkb1) * ROW_BYTES : p.row_bytes - kb * ROW_BYTES);
-      const int ksteps = (valid + 63) >> 6;          // 16 channels (64 bytes of fp32) per instruction
+      const bool two = valid > 64;                   // 16 channels (64 bytes of fp32) per instruction, 1 or 2 steps
+#pragma unroll 1
       for (int ki = 0; ki < K; ++ki) {
+        const int ts = t + buf * TM;
+        const uint32_t b_lo32 = b_lo_base + uint32_t(sb) * b_lo_step;
+        const uint32_t a_tm = a_base + uint32_t(buf * TM * TA_COLS);
         mbar_wait(b_full + sb, phb);
-        const uint32_t b_base = b_ring_base + uint32_t(sb) * b_bytes;
-        const uint32_t b_lo32 = ((b_base >> 4) & 0x3FFF) | (1u << 16);
-        const uint32_t acc_flag = (ki | kb) ? 1u : 0u;
-        for (int t = 0; t < TM; ++t) {
-          const uint32_t d_addr = tmem_base + uint32_t(t * p.n_tile);
-          mbar_wait(ta_full + tsa, phta);
-          tc_fence_after();
-          const uint32_t a_tm = tmem_base + uint32_t(p.ta_col0 + tsa * TA_COLS);
-          if (elect_one()) {
-#pragma unroll 2
-            for (int j = 0; j < ksteps; ++j) {
-              const uint64_t b_hi = desc_from(b_lo32 + 2 * j, desc_hi);
-              const uint64_t b_lo = desc_from(b_lo32 + 4 + 2 * j, desc_hi);
-              umma_ts_f16(d_addr, a_tm + 8 * j, b_hi, idesc, acc_flag | uint32_t(j));
-              umma_ts_f16(d_addr, a_tm + 16 + 8 * j, b_hi, idesc, 1u);
-              umma_ts_f16(d_addr, a_tm + 8 * j, b_lo, idesc, 1u);
-            }
-            umma_commit(ta_empty + tsa);
+        mbar_wait(ta_full + ts, phta);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t b_hi0 = desc_from(b_lo32, desc_hi), b_lo0 = desc_from(b_lo32 + 4, desc_hi);
+          umma_ts_f16(d_addr, a_tm, b_hi0, idesc, (ki | kb) ? 1u : 0u);
+          umma_ts_f16(d_addr, a_tm + 16, b_hi0, idesc, 1u);
+          umma_ts_f16(d_addr, a_tm, b_lo0, idesc, 1u);
+          if (two) {
+            const uint64_t b_hi1 = desc_from(b_lo32 + 2, desc_hi), b_lo1 = desc_from(b_lo32 + 6, desc_hi);
+            umma_ts_f16(d_addr, a_tm + 8, b_hi1, idesc, 1u);
+            umma_ts_f16(d_addr, a_tm + 24, b_hi1, idesc, 1u);
+            umma_ts_f16(d_addr, a_tm + 8, b_lo1, idesc, 1u);
           }
-          __syncwarp();
-          if (++tsa == STA) {
-            tsa = 0;
-            phta ^= 1;
-          }
+          umma_commit(ta_empty + ts);
+          umma_commit(b_empty + sb);
         }
-        if (elect_one()) umma_commit(b_empty + sb);
         __syncwarp();
+        if (++buf == NBUF) {
+          buf = 0;
+          phta ^= 1;
+        }
         if (++sb == SB) {
           sb = 0;
           phb ^= 1;
@@ -325,26 +368,12 @@ __global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_consta
       }
     }
   } else {
-    // =================================== cache fill (64 threads): unique rows of the supertile, one channel block ==========
-    const int ft = tid - 6 * 32;
-    const int chunk = ft & 7, rsub = ft >> 3;        // 8 lanes cover one 128-byte row segment; 8 rows per pass
+    // =================================== cache fill helper (warp 7; the row threads fill with it) ==========
     const uint32_t cache_base = smem_u32(cache);
-    uint32_t phe = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
-      if (kb > 0) {
-        mbar_wait(cache_empty, phe);                 // the splitters are done with the previous channel block
-        phe ^= 1;
-      }
-      const bool second = kb >= p.nkb1;
-      const int kbl = second ? kb - p.nkb1 : kb;
-      const int rb = second ? p.row_bytes2 : p.row_bytes;
-      const bool col_ok = kbl * ROW_BYTES + chunk * 16 < rb;
-      const uint8_t* src = (second ? p.in2 : p.in) + kbl * ROW_BYTES + chunk * 16;
-      for (int u = rsub; u < U; u += FILL_THREADS / 8) {
-        const int32_t row = s_uniq[u];
-        cp_async16(cache_base + uint32_t(u) * ROW_BYTES + uint32_t(chunk << 4), src + size_t(col_ok ? row : 0) * rb, col_ok ? 16u : 0u);
-      }
-      cp_async_mbar_arrive_noinc(cache_full);
+      if (kb > 0) fill_bar();
+      fill_cache(p.in, p.in2, p.row_bytes, p.row_bytes2, p.nkb1, kb, tid - 96, U, s_uniq, cache_base);
+      fill_bar();
     }
   }
 
@@ -409,7 +438,8 @@ int conv_fwd_nb(const void* in, int c_in, const void* in2, int c_in2, const void
   q.ucount = plan + g.off_ucount;
   q.uniq = plan + g.off_uniq;
   q.loc = reinterpret_cast<const uint16_t*>(plan + g.off_loc);
-  q.RS = g.RS, q.rt = g.rt, q.TM = g.tm, q.umax = g.umax;
+  if (g.tm != TM) return fail(LGS_E_INVALID, "conv_fwd_nb: plan geometry tm %d", g.tm);
+  q.RS = g.RS, q.rt = g.rt, q.umax = g.umax;
   q.reverse_k = reverse_k;
   q.bias = bias;
   q.out = out;
@@ -421,11 +451,11 @@ int conv_fwd_nb(const void* in, int c_in, const void* in2, int c_in2, const void
   q.n_tile = nt;
   q.b_stage_bytes = nt * ROW_BYTES;
   q.ta_col0 = ((g.tm * nt + 31) / 32) * 32;
-  q.ta_stages = std::min(MAX_TA, (256 - q.ta_col0) / TA_COLS);
+  q.ta_stages = std::min(MAX_TA, (256 - q.ta_col0) / TA_COLS) / TM * TM;      // whole buffers per row tile
   int cols = 32;
   while (cols < q.ta_col0 + q.ta_stages * TA_COLS) cols <<= 1;
   q.tmem_cols = cols;
-  const size_t fixed = size_t(g.umax + 1) * ROW_BYTES + size_t(g.umax) * 4 + 2048 + (2 * MAX_B + 2 * MAX_TA + 3) * 8 + 16 + 1024;
+  const size_t fixed = size_t(g.umax + 1) * ROW_BYTES + size_t(g.umax) * 4 + 2048 + (2 * MAX_B + 2 * MAX_TA + 1) * 8 + 16 + 1024;
   int sb = 3;
   while (sb > 2 && fixed + size_t(sb) * q.b_stage_bytes > 113 * 1024) --sb;
   if (fixed + size_t(sb) * q.b_stage_bytes > 113 * 1024) return LGS_E_UNSUPPORTED;

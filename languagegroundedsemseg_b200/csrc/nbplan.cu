@@ -19,9 +19,20 @@
 //   3. nb_scan_kernel     exclusive scan of the 2^18 bin counts (one block)
 //   4. nb_scatter_kernel  order_tmp[bin_start + cursor++] = row;  nb_rank_kernel: rows of a bin sorted by row id, so the
 //                         order (the composition of every supertile) is deterministic
-//   5. nb_plan_kernel     one CTA per supertile: shared-memory hash set of the neighbour rows -> ids by slot order
-//                         (block scan) -> uniq[], loc[][].  The SET of unique rows is deterministic, their local numbering
-//                         is not (linear-probing slots depend on arrival order); nothing downstream depends on it
+//   5. nb_plan_kernel     one CTA per supertile: slots re-ordered by COLOUR (below), shared-memory hash set of the
+//                         neighbour rows -> ids by slot order (block scan) -> uniq[], loc[][].  The SET of unique rows is
+//                         deterministic, their local numbering is not (linear-probing slots depend on arrival order);
+//                         nothing downstream depends on it
+//
+// Colours (bank-conflict-free cache reads without a register permutation).  conv_nb.cu's row threads read 16-byte chunks of
+// ARBITRARY cached rows; eight lanes that read the same chunk index of eight rows with a 128-byte pitch would collide in
+// one bank group.  Every voxel gets a colour g = (x + 3y + 5z) / step mod 8, a cached row stores logical chunk c at position
+// (c + g) mod 8, and the slots of a supertile are ordered so that each aligned group of eight slots (a quarter-warp) holds
+// eight DIFFERENT colours wherever the supertile's colour histogram allows it (rows beyond a colour's share fill the
+// holes and cost a 2-way conflict).  Translation by a kernel offset adds the same constant to all eight colours, so the
+// eight neighbour rows of a quarter-warp are again pairwise different in colour for every offset: lane j reads position
+// (i + g_j) mod 8 in step i and the eight reads fall into eight different bank groups.  Missing neighbours read the zero
+// row at the position their colour WOULD have.  loc = idx | g << 12 (idx 0xFFF = no neighbour), uniq = row | g << 28.
 #include <algorithm>
 #include <string>
 
@@ -174,18 +185,66 @@ __device__ __forceinline__ uint32_t hash_row(int32_t j) {
 }
 
 // One CTA (256 threads) per supertile of RS = tm * rt row slots (slot q = t * rt + i; slots past the map hold order = -1).
-__global__ void __launch_bounds__(256) nb_plan_kernel(const int32_t* __restrict__ table, int K, int64_t n_out,
-                                                      const int32_t* __restrict__ order, int RS, int umax,
+__device__ __forceinline__ int colour_of(int4 c, int step) {
+  return ((c.y / step) + 3 * (c.z / step) + 5 * (c.w / step)) & 7;     // coordinates are exact multiples of the tensor stride
+}
+
+__global__ void __launch_bounds__(256) nb_plan_kernel(const int32_t* __restrict__ coords, int step,
+                                                      const int32_t* __restrict__ table, int K, int64_t n_out,
+                                                      int32_t* __restrict__ order, int RS, int umax,
                                                       int32_t* __restrict__ ucount, int32_t* __restrict__ uniq,
                                                       uint16_t* __restrict__ loc, int32_t* hdr) {
   __shared__ int32_t keys[kHash];
   __shared__ uint16_t ids[kHash];
+  __shared__ uint8_t gcol[kHash];
   __shared__ int32_t warp_sums[8];
   __shared__ int32_t total;
+  __shared__ int32_t ord[256];
+  __shared__ int8_t col_in[256], own_col[256];
+  __shared__ uint8_t taken[256], ovf[256];
   const int s = blockIdx.x, tid = threadIdx.x;
   for (int i = tid; i < kHash; i += 256) keys[i] = -1;
+  // phase 0: slots of the supertile re-ordered by colour: the r-th row of colour c goes to slot 8 r + c while octets last;
+  // the rest (and the padding of the last supertile) fill the free slots in order.  Deterministic.
+  {
+    int32_t o = -1;
+    int c = -1;
+    if (tid < RS) {
+      o = order[int64_t(s) * RS + tid];
+      if (o >= 0) c = colour_of(__ldg(reinterpret_cast<const int4*>(coords) + o), step);
+    }
+    col_in[tid] = int8_t(c);
+    taken[tid] = 0;
+    ord[tid] = -1;
+    own_col[tid] = int8_t(tid & 7);
+    __syncthreads();
+    const int octets = RS >> 3;
+    int rank = 0;
+    if (c >= 0)
+      for (int q = 0; q < tid; ++q) rank += col_in[q] == c ? 1 : 0;
+    const bool primary = c >= 0 && rank < octets;
+    if (primary) {
+      const int slot = 8 * rank + c;
+      ord[slot] = o;
+      own_col[slot] = int8_t(c);
+      taken[slot] = 1;
+    }
+    ovf[tid] = (c >= 0 && !primary) ? 1 : 0;
+    __syncthreads();
+    if (c >= 0 && !primary) {
+      int before = 0;                                   // overflow rows ahead of this one
+      for (int q = 0; q < tid; ++q) before += ovf[q];
+      int slot = 0;
+      for (int seen = -1; slot < RS; ++slot) {
+        if (!taken[slot] && ++seen == before) break;
+      }
+      ord[slot] = o;                                    // distinct `before` -> distinct free slots: no race
+      own_col[slot] = int8_t(c);
+    }
+    __syncthreads();
+    if (tid < RS) order[int64_t(s) * RS + tid] = ord[tid];
+  }
   __syncthreads();
-  const int32_t* ord = order + int64_t(s) * RS;
   const int work = K * RS;
   // phase 1: insert every neighbour row into the hash set
   for (int w = tid; w < work; w += 256) {
@@ -231,8 +290,10 @@ __global__ void __launch_bounds__(256) nb_plan_kernel(const int32_t* __restrict_
   for (int i = 0; i < kHash / 256; ++i) {
     const int32_t key = keys[base + i];
     if (key >= 0) {
+      const int g = colour_of(__ldg(reinterpret_cast<const int4*>(coords) + key), step);
       ids[base + i] = uint16_t(min(id, 0xFFFF));
-      if (id < umax) uniq[int64_t(s) * umax + id] = key;
+      gcol[base + i] = uint8_t(g);
+      if (id < umax) uniq[int64_t(s) * umax + id] = key | (g << 28);
       ++id;
     }
   }
@@ -242,12 +303,14 @@ __global__ void __launch_bounds__(256) nb_plan_kernel(const int32_t* __restrict_
     if (total > umax) atomicOr(hdr + 8, 1);
     atomicMax(hdr + 9, total);
   }
-  // phase 3: the table in local indices (0xFFFF: no neighbour / padded slot / did not fit)
+  // phase 3: the table in local indices: idx | colour << 12; idx 0xFFF = no neighbour / padded slot / did not fit, with the
+  // colour the neighbour would have (own colour + the offset's colour shift), so that the zero-row read is conflict-free too
   uint16_t* lc = loc + int64_t(s) * K * RS;
   for (int w = tid; w < work; w += 256) {
     const int k = w / RS, q = w - k * RS;
     const int32_t o = ord[q];
-    uint16_t v = 0xFFFF;
+    const int dk = (k % 3 - 1) + 3 * ((k / 3) % 3 - 1) + 5 * (k / 9 - 1);                  // x fastest, as in kmap_kernel
+    uint16_t v = uint16_t(0xFFF | (((int(own_col[q]) + dk) & 7) << 12));
     if (o >= 0) {
       const int32_t j = __ldg(table + int64_t(k) * n_out + o);
       if (j >= 0) {
@@ -256,7 +319,7 @@ __global__ void __launch_bounds__(256) nb_plan_kernel(const int32_t* __restrict_
         while (keys[h] != j && probe < kHash) h = (h + 1) & uint32_t(kHash - 1), ++probe;   // bounded: a full set drops rows
         if (probe < kHash) {
           const uint16_t lid = ids[h];
-          if (int(lid) < umax) v = lid;
+          if (int(lid) < umax) v = uint16_t(lid | (uint16_t(gcol[h]) << 12));
         }
       }
     }
@@ -282,7 +345,7 @@ NbGeom nb_geometry(int64_t n_out, int K) {
   NbGeom g;
   g.K = K;
   g.tm = 2;
-  g.umax = g_nb_umax > 0 ? g_nb_umax : 640;
+  g.umax = std::min(4000, g_nb_umax > 0 ? g_nb_umax : 640);
   // rows per tile: whole waves of 296 CTAs (2 resident per SM), tiles as full as the wave count allows
   const int64_t slots = 296;
   const int64_t full = cdiv(n_out, int64_t(g.tm) * 128);
@@ -290,6 +353,7 @@ NbGeom nb_geometry(int64_t n_out, int K) {
   int rt = int(cdiv(cdiv(n_out, waves * slots), int64_t(g.tm)));
   rt = std::min(128, std::max(32, rt));
   if (g_nb_rt > 0) rt = std::min(128, std::max(8, g_nb_rt));
+  rt = std::min(128, (rt + 7) & ~7);                // whole octets of slots per tile (colour groups, see the header comment)
   g.rt = rt;
   g.RS = g.tm * rt;
   g.S = cdiv(n_out, int64_t(g.RS));
@@ -323,16 +387,16 @@ int64_t lgs_nbplan_scratch_bytes(int64_t n_out) {
 }
 
 int lgs_nbplan_supported(int64_t n_out, int32_t K) {
-  return (!nb_disabled() && K == 27 && n_out >= nb_min_rows() && n_out < (int64_t(1) << 31) - 4096) ? 1 : 0;
+  return (!nb_disabled() && K == 27 && n_out >= nb_min_rows() && n_out < (int64_t(1) << 28)) ? 1 : 0;
 }
 
-int lgs_nbplan_build(const int32_t* d_out_coords, int64_t n_out, const int32_t* d_table, int32_t K, void* d_plan, void* d_scratch,
-                     int32_t* h_status, void* stream_) {
-  LGS_TRACE("lgs_nbplan_build %p %lld %p %d %p %p %p", (const void*)d_out_coords, (long long)n_out, (const void*)d_table, (int)K, (const void*)d_plan, (const void*)d_scratch, (const void*)stream_);
+int lgs_nbplan_build(const int32_t* d_out_coords, int64_t n_out, const int32_t* d_table, int32_t K, int32_t step, void* d_plan,
+                     void* d_scratch, int32_t* h_status, void* stream_) {
+  LGS_TRACE("lgs_nbplan_build %p %lld %p %d %d %p %p %p", (const void*)d_out_coords, (long long)n_out, (const void*)d_table, (int)K, (int)step, (const void*)d_plan, (const void*)d_scratch, (const void*)stream_);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!d_out_coords || !d_table || !d_plan || !d_scratch || n_out <= 0 || K < 1 || K > 64)
+  if (!d_out_coords || !d_table || !d_plan || !d_scratch || n_out <= 0 || K != 27 || step < 1)
     return fail(LGS_E_INVALID, "lgs_nbplan_build: bad arguments");
-  if (n_out >= (int64_t(1) << 31) - 4096) return fail(LGS_E_UNSUPPORTED, "lgs_nbplan_build: map too large");
+  if (n_out >= (int64_t(1) << 28)) return fail(LGS_E_UNSUPPORTED, "lgs_nbplan_build: map too large");
   const NbGeom g = nb_geometry(n_out, K);
   int32_t* plan = static_cast<int32_t*>(d_plan);
   int32_t* scr = static_cast<int32_t*>(d_scratch);
@@ -352,7 +416,7 @@ int lgs_nbplan_build(const int32_t* d_out_coords, int64_t n_out, const int32_t* 
   LGS_LAUNCH(nbp::nb_scatter_kernel, rb, 256, 0, stream, bin_of_row, n_out, bins, cursor, order_tmp);
   LGS_LAUNCH(nbp::nb_rank_kernel, unsigned(cdiv(n_pad, 256)), 256, 0, stream, bin_of_row, n_out, n_pad, bins, cursor, order_tmp,
              plan + g.off_order);
-  LGS_LAUNCH(nbp::nb_plan_kernel, unsigned(g.S), 256, 0, stream, d_table, K, n_out, plan + g.off_order, g.RS, g.umax,
+  LGS_LAUNCH(nbp::nb_plan_kernel, unsigned(g.S), 256, 0, stream, d_out_coords, step, d_table, K, n_out, plan + g.off_order, g.RS, g.umax,
              plan + g.off_ucount, plan + g.off_uniq, reinterpret_cast<uint16_t*>(plan + g.off_loc), plan);
   if (h_status) {
     int32_t st[2] = {0, 0};

@@ -391,7 +391,7 @@ class CoordinateManager:
                                       _lib.ptr(table), _lib.ptr(counts), _stream()))
         return table, counts
 
-    def _plan(self, km, cmap):
+    def _plan(self, km, cmap, step):
         """neighbourhood plan of a large same-map 3^3 kernel map: supertiles of spatially close output rows, their unique
         input rows and the table in local indices (csrc/nbplan.cu), consumed by lgs_conv_fwd3.  One host sync (status)."""
         lib = _lib.load()
@@ -401,7 +401,7 @@ class CoordinateManager:
         plan = torch.empty(lib.lgs_nbplan_bytes(km.n_out, km.K) // 4, dtype=torch.int32, device=dev)
         scratch = torch.empty(lib.lgs_nbplan_scratch_bytes(km.n_out) // 4, dtype=torch.int32, device=dev)
         status = (ctypes.c_int32 * 2)()
-        _lib.check(lib.lgs_nbplan_build(_lib.ptr(cmap.coords), km.n_out, _lib.ptr(km.fwd_table), km.K, _lib.ptr(plan),
+        _lib.check(lib.lgs_nbplan_build(_lib.ptr(cmap.coords), km.n_out, _lib.ptr(km.fwd_table), km.K, step, _lib.ptr(plan),
                                         _lib.ptr(scratch), ctypes.cast(status, ctypes.c_void_p), _stream()))
         km.plan_stats = (int(status[0]), int(status[1]))
         if status[0] == 0:
@@ -436,7 +436,7 @@ class CoordinateManager:
             if in_key == out_key and ks % 2 == 1:
                 # C_in[i] = C[o] + off_k  <=>  C[o] = C_in[i] + off_{K-1-k}: dgrad reads the same table mirrored
                 km.bwd_table, km.bwd_reverse = km.fwd_table, True
-                self._plan(km, self._maps[out_key])
+                self._plan(km, self._maps[out_key], _uniform(list(in_key.tensor_stride), "tensor stride") * dil)
             else:
                 km.bwd_table, km.bwd_reverse = self._transpose(km.fwd_table, km.n_in), False
         self._kmaps[ck] = km
