@@ -168,11 +168,13 @@ int lgs_conv_fwd2(const float* d_in, int32_t c_in, const float* d_in2, int32_t c
  * supertile's rows into shared memory once per channel block instead of once per (row, offset) pair.  step = tensor stride x
  * dilation of the map (the spacing of the kernel offsets, as in lgs_kmap_build).
  * Tensor row order is unchanged; results equal lgs_conv_fwd2's (same products, same accumulation order per row).
- *   lgs_nbplan_supported: 1 if a plan is worth building for this map (K == 27, n_out >= 148 * 128 unless tuned).
+ *   lgs_nbplan_supported: 1 if a plan is worth building for this map (K == 27, n_out >= 256 unless tuned).  On maps with fewer
+ *   supertiles than SMs lgs_conv_fwd3 splits the reduction (channel blocks, then kernel offsets) over CTAs; partial sums meet
+ *   through red.global.add on a zeroed output (not when d_bn_sums is given).
  *   lgs_nbplan_build: d_plan lgs_nbplan_bytes() bytes, d_scratch lgs_nbplan_scratch_bytes() bytes (both 16-byte aligned);
  *   h_status (host, may be NULL; synchronises the stream when given): [0] = 1 if some supertile touches more unique rows than
  *   the cache holds (the plan must then NOT be used), [1] = largest unique-row count of a supertile.
- *   lgs_tune keys: "nb_rt" rows per tile, "nb_umax" cache rows, "nb_min_rows", "nb_off".
+ *   lgs_tune keys: "nb_rt" rows per tile, "nb_umax" cache rows, "nb_min_rows", "nb_off", "nb_target_ctas", "nb_no_split".
  * --------------------------------------------------------------------------------------------------------- */
 int lgs_nbplan_supported(int64_t n_out, int32_t K);
 int64_t lgs_nbplan_bytes(int64_t n_out, int32_t K);

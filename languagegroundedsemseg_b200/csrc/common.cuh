@@ -62,6 +62,8 @@ NbGeom nb_geometry(int64_t n_out, int K);
 int nb_tune(const char* key, int value);
 int nb_min_rows();
 int nb_disabled();
+int nb_target_ctas();
+int nb_no_split();
 
 // ---- coordinate keys ---------------------------------------------------------------------------------
 // 64-bit key: batch 10 bit | x 18 bit | y 18 bit | z 18 bit (two's complement fields).

@@ -54,6 +54,7 @@ struct Params {
   const uint16_t* loc;       // [S][K][RS] local index of slot's neighbour at offset k (0xFFF = none) | colour << 12
   int32_t RS, rt, umax;
   int32_t reverse_k;
+  int32_t kb_per_split, kb_splits, k_per_split;   // blockIdx.z = offset split * kb_splits + channel-block split (small maps)
   const float* bias;
   float* out;
   int32_t n_tile, b_stages, ta_stages, ta_col0, tmem_cols, b_stage_bytes;
@@ -126,7 +127,8 @@ __device__ __forceinline__ void fill_cache(const uint8_t* in, const uint8_t* in2
 // Epilogue of one row warp, out of line so that its register needs (three 32-word arrays for the fused BatchNorm sums) do not
 // spill loop-invariant values of the main loops: TMEM accumulators -> (+ bias) -> output rows at their own positions.
 __device__ __noinline__ void epilogue_rows(uint32_t tmem_lane_base, int n_tile, int ncols, int c_out, int n0, const float* bias,
-                                           float* out, const int32_t* order_s, int rt, int r, bool want_stats, float* s_stats) {
+                                           float* out, const int32_t* order_s, int rt, int r, bool want_stats, float* s_stats,
+                                           bool partial) {
   const int lane = threadIdx.x & 31;
   for (int t = 0; t < TM; ++t) {
     const int32_t o = r < rt ? __ldg(order_s + t * rt + r) : -1;
@@ -144,15 +146,22 @@ __device__ __noinline__ void epilogue_rows(uint32_t tmem_lane_base, int n_tile, 
 #pragma unroll
         for (int jj = 0; jj < 32; jj += 4) {
           if (c0 + jj + 3 < ncols) {
-            float4 x;
-            x.x = __uint_as_float(v[jj]);
-            x.y = __uint_as_float(v[jj + 1]);
-            x.z = __uint_as_float(v[jj + 2]);
-            x.w = __uint_as_float(v[jj + 3]);
-            *reinterpret_cast<float4*>(orow + jj) = x;
+            if (partial) {                            // this CTA holds a partial sum over channel blocks / offsets
+              red_add_v4(orow + jj, __uint_as_float(v[jj]), __uint_as_float(v[jj + 1]), __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
+            } else {
+              float4 x;
+              x.x = __uint_as_float(v[jj]);
+              x.y = __uint_as_float(v[jj + 1]);
+              x.z = __uint_as_float(v[jj + 2]);
+              x.w = __uint_as_float(v[jj + 3]);
+              *reinterpret_cast<float4*>(orow + jj) = x;
+            }
           } else {
             for (int e = jj; e < jj + 4; ++e)
-              if (c0 + e < ncols) orow[e] = __uint_as_float(v[e]);
+              if (c0 + e < ncols) {
+                if (partial) atomicAdd(orow + e, __uint_as_float(v[e]));
+                else orow[e] = __uint_as_float(v[e]);
+              }
           }
         }
       }
@@ -189,7 +198,12 @@ __device__ __noinline__ void epilogue_rows(uint32_t tmem_lane_base, int n_tile, 
 __global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int SB = p.b_stages, K = p.K, num_kb = p.num_kb, umax = p.umax;
+  const int SB = p.b_stages, K = p.K, umax = p.umax;
+  // this CTA's share of the reduction: channel blocks [kb0, kb1) x kernel offsets [k0, k1) (everything on large maps)
+  const int zs = blockIdx.z / p.kb_splits, zb = blockIdx.z - zs * p.kb_splits;
+  const int kb0 = zb * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+  const int k0 = zs * p.k_per_split, k1 = min(K, k0 + p.k_per_split);
+  const bool partial = gridDim.z > 1;
   const int NBUF = p.ta_stages / TM;                                // TMEM A buffers per row tile (tile t owns stages t + TM i)
   const uint32_t b_bytes = uint32_t(p.b_stage_bytes);
   uint8_t* b_ring = smem;                                           // 1024-aligned (SWIZZLE_128B TMA destination)
@@ -245,12 +259,12 @@ __global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_consta
     const uint32_t none = 0xFFFu | (uint32_t(lane & 7) << 12);
     // index stream of this row slot: loc[kk][t * rt + r], kk ascending (forward) or descending (dgrad), fetched one offset ahead
     const int64_t kstride = p.reverse_k ? -int64_t(p.RS) : int64_t(p.RS);
-    const uint16_t* lp0 = p.loc + s * int64_t(K) * p.RS + (p.reverse_k ? int64_t(K - 1) * p.RS : 0) + min(r, p.rt - 1);
+    const uint16_t* lp0 = p.loc + s * int64_t(K) * p.RS + (p.reverse_k ? int64_t(K - 1 - k0) : int64_t(k0)) * p.RS + min(r, p.rt - 1);
     const int rt = p.rt;
     int buf = 0;
     uint32_t pht = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      if (kb > 0) fill_bar();                       // every row thread is done reading the previous channel block
+    for (int kb = kb0; kb < kb1; ++kb) {
+      if (kb > kb0) fill_bar();                     // every row thread is done reading the previous channel block
       fill_cache(p.in, p.in2, p.row_bytes, p.row_bytes2, p.nkb1, kb, tid, U, s_uniq, cache_base);
       const uint16_t* lp = lp0;
       uint32_t nx[TM];
@@ -258,11 +272,11 @@ __global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_consta
       for (int t = 0; t < TM; ++t) nx[t] = row_in_tile ? uint32_t(__ldg(lp + t * rt)) : none;
       fill_bar();                                   // this channel block of every unique row is in the cache
 #pragma unroll 1
-      for (int ki = 0; ki < K; ++ki) {
+      for (int ki = k0; ki < k1; ++ki) {
         uint32_t cur[TM];
 #pragma unroll
         for (int t = 0; t < TM; ++t) cur[t] = nx[t];
-        if (ki + 1 < K) {
+        if (ki + 1 < k1) {
           lp += kstride;
 #pragma unroll
           for (int t = 0; t < TM; ++t) nx[t] = row_in_tile ? uint32_t(__ldg(lp + t * rt)) : none;
@@ -294,8 +308,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_consta
     // =================================== epilogue ===================================
     mbar_wait(acc_bar, 0);
     tc_fence_after();
-    epilogue_rows(tmem_base + lane_addr, p.n_tile, min(p.n_tile, p.c_out - n0), p.c_out, n0, p.bias, p.out, p.order + s * p.RS, rt, r,
-                  p.stats != nullptr, s_stats);
+    epilogue_rows(tmem_base + lane_addr, p.n_tile, min(p.n_tile, p.c_out - n0), p.c_out, n0, blockIdx.z == 0 ? p.bias : nullptr, p.out,
+                  p.order + s * p.RS, rt, r, p.stats != nullptr, s_stats, partial);
     tc_fence_before();
   } else if (warp == 4 || warp == 6) {
     // =================================== MMA issuers: warp 4 <-> row tile 0, warp 6 <-> row tile 1 ================
@@ -309,12 +323,12 @@ __global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_consta
     const uint32_t a_base = tmem_base + uint32_t(p.ta_col0 + t * TA_COLS);
     int sb = 0, buf = 0;
     uint32_t phb = 0, phta = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
+    for (int kb = kb0; kb < kb1; ++kb) {
       const bool second = kb >= p.nkb1;
       const int valid = min(ROW_BYTES, second ? p.row_bytes2 - (kb - p.nkb1) * ROW_BYTES : p.row_bytes - kb * ROW_BYTES);
       const bool two = valid > 64;                   // 16 channels (64 bytes of fp32) per instruction, 1 or 2 steps
 #pragma unroll 1
-      for (int ki = 0; ki < K; ++ki) {
+      for (int ki = k0; ki < k1; ++ki) {
         const int ts = t + buf * TM;
         const uint32_t b_lo32 = b_lo_base + uint32_t(sb) * b_lo_step;
         const uint32_t a_tm = a_base + uint32_t(buf * TM * TA_COLS);
@@ -323,7 +337,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_consta
         tc_fence_after();
         if (elect_one()) {
           const uint64_t b_hi0 = desc_from(b_lo32, desc_hi), b_lo0 = desc_from(b_lo32 + 4, desc_hi);
-          umma_ts_f16(d_addr, a_tm, b_hi0, idesc, (ki | kb) ? 1u : 0u);
+          umma_ts_f16(d_addr, a_tm, b_hi0, idesc, (ki > k0 || kb > kb0) ? 1u : 0u);
           umma_ts_f16(d_addr, a_tm + 16, b_hi0, idesc, 1u);
           umma_ts_f16(d_addr, a_tm, b_lo0, idesc, 1u);
           if (two) {
@@ -353,8 +367,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_consta
     const uint32_t b_ring_base = smem_u32(b_ring);
     int sb = 0;
     uint32_t phb = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      for (int ki = 0; ki < K; ++ki) {
+    for (int kb = kb0; kb < kb1; ++kb) {
+      for (int ki = k0; ki < k1; ++ki) {
         mbar_wait(b_empty + sb, phb ^ 1);
         if (elect_one()) {
           mbar_expect_tx(b_full + sb, b_bytes);
@@ -370,8 +384,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_consta
   } else {
     // =================================== cache fill helper (warp 7; the row threads fill with it) ==========
     const uint32_t cache_base = smem_u32(cache);
-    for (int kb = 0; kb < num_kb; ++kb) {
-      if (kb > 0) fill_bar();
+    for (int kb = kb0; kb < kb1; ++kb) {
+      if (kb > kb0) fill_bar();
       fill_cache(p.in, p.in2, p.row_bytes, p.row_bytes2, p.nkb1, kb, tid - 96, U, s_uniq, cache_base);
       fill_bar();
     }
@@ -462,6 +476,36 @@ int conv_fwd_nb(const void* in, int c_in, const void* in2, int c_in2, const void
   q.b_stages = sb;
   const size_t smem = fixed + size_t(sb) * q.b_stage_bytes;
 
+  // Small maps (fewer supertiles than SMs): the reduction over channel blocks and kernel offsets is split over CTAs
+  // (blockIdx.z) until about two CTAs per SM are busy; partial sums meet through red.global.add on a zeroed output.
+  // Channel blocks first (every split fills only its own block of the cache), then offsets.  Never when the BatchNorm
+  // statistics are wanted from the epilogue (they need complete sums).
+  const int n_slices = (c_out + nt - 1) / nt;
+  int kb_splits = 1, k_splits = 1;
+  const int64_t base_ctas = g.S * n_slices;
+  if (!stats && base_ctas < 148 && !nb_no_split()) {
+    // cheapest (waves of nb_target_ctas CTAs) x (fixed cost of a CTA + its stages): a second wave costs a whole CTA time
+    const int64_t slots = nb_target_ctas();
+    double best = 1e30;
+    for (int kbs = 1; kbs <= q.num_kb; ++kbs) {
+      const int kbp = (q.num_kb + kbs - 1) / kbs;
+      if ((q.num_kb + kbp - 1) / kbp != kbs) continue;
+      for (int ks = 1; ks <= 9; ++ks) {
+        const int kp = (K + ks - 1) / ks;
+        if ((K + kp - 1) / kp != ks) continue;
+        const int64_t ctas = base_ctas * kbs * ks;
+        const double cost = double(cdiv(ctas, slots)) * (6000.0 + 3000.0 * kbp + 800.0 * kbp * kp * TM) + 40.0 * kbs * ks;
+        if (cost < best) best = cost, kb_splits = kbs, k_splits = ks;
+      }
+    }
+  }
+  q.kb_per_split = (q.num_kb + kb_splits - 1) / kb_splits;
+  q.kb_splits = (q.num_kb + q.kb_per_split - 1) / q.kb_per_split;
+  q.k_per_split = (K + k_splits - 1) / k_splits;
+  k_splits = (K + q.k_per_split - 1) / q.k_per_split;
+  const unsigned gz = unsigned(q.kb_splits * k_splits);
+  if (gz > 1) LGS_CUDA(cudaMemsetAsync(out, 0, size_t(n_out) * c_out * sizeof(float), stream));
+
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {cuuint64_t(q.num_kb) * 64, cuuint64_t(K) * cuuint64_t(c_out)};
   const cuuint64_t gstride[1] = {cuuint64_t(q.num_kb) * 128};
@@ -471,7 +515,7 @@ int conv_fwd_nb(const void* in, int c_in, const void* in2, int c_in2, const void
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(LGS_E_CUDA, "cuTensorMapEncodeTiled (nb) failed (%d) c_in=%d c_out=%d K=%d", int(cr), c_in + c_in2, c_out, K);
-  const dim3 grid{unsigned(g.S), unsigned((c_out + nt - 1) / nt), 1u};
+  const dim3 grid{unsigned(g.S), unsigned(n_slices), gz};
   LGS_LAUNCH(conv_nb_kernel, grid, THREADS, smem, stream, tmap, q);
   return LGS_OK;
 }

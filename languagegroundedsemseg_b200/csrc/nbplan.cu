@@ -16,7 +16,7 @@
 // Integer work, one pass over the rows per kernel, no sort:
 //   1. nb_extent_kernel   min / max of (b, x, y, z)                                  (atomicMin / atomicMax)
 //   2. nb_bin_kernel      row -> bin = batch bits | Morton(cell), cell = (c - min) >> shift; histogram
-//   3. nb_scan_kernel     exclusive scan of the 2^18 bin counts (one block)
+//   3. nb_scan_*_kernel   exclusive scan of the 2^18 bin counts (block totals, then blocks scan with their offsets)
 //   4. nb_scatter_kernel  order_tmp[bin_start + cursor++] = row;  nb_rank_kernel: rows of a bin sorted by row id, so the
 //                         order (the composition of every supertile) is deterministic
 //   5. nb_plan_kernel     one CTA per supertile: slots re-ordered by COLOUR (below), shared-memory hash set of the
@@ -107,19 +107,12 @@ __global__ void __launch_bounds__(256) nb_bin_kernel(const int32_t* __restrict__
   atomicAdd(bins + b, 1);
 }
 
-// one block of 1024 threads: exclusive scan of kBins counts in place (thread t owns kBins / 1024 consecutive bins)
-__global__ void __launch_bounds__(1024) nb_scan_kernel(int32_t* bins) {
-  constexpr int PER = kBins / 1024;
-  __shared__ int32_t warp_sums[32];
-  int4* mine = reinterpret_cast<int4*>(bins + threadIdx.x * PER);
-  int32_t sum = 0;
-#pragma unroll 8
-  for (int j = 0; j < PER / 4; ++j) {
-    const int4 v = mine[j];
-    sum += v.x + v.y + v.z + v.w;
-  }
+// exclusive scan of the kBins counts in place, two launches of kBins / 1024 blocks x 1024 threads (one bin per thread):
+// block totals, then every block scans the totals of the blocks before it (256 values) and its own 1024 bins
+constexpr int kScanBlocks = kBins / 1024;
+__device__ __forceinline__ int32_t block_inclusive_scan_1024(int32_t v, int32_t* warp_sums) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int32_t inc = sum;
+  int32_t inc = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const int32_t y = __shfl_up_sync(0xffffffffu, inc, d);
@@ -137,14 +130,26 @@ __global__ void __launch_bounds__(1024) nb_scan_kernel(int32_t* bins) {
     warp_sums[lane] = w;
   }
   __syncthreads();
-  int32_t run = (inc - sum) + (warp ? warp_sums[warp - 1] : 0);
-  for (int j = 0; j < PER / 4; ++j) {
-    int4 v = mine[j];
-    const int32_t a = v.x, b = v.y, c = v.z, d = v.w;
-    v.x = run, v.y = run + a, v.z = run + a + b, v.w = run + a + b + c;
-    run += a + b + c + d;
-    mine[j] = v;
-  }
+  return inc + (warp ? warp_sums[warp - 1] : 0);
+}
+__global__ void __launch_bounds__(1024) nb_scan_totals_kernel(const int32_t* __restrict__ bins, int32_t* __restrict__ totals) {
+  __shared__ int32_t warp_sums[32];
+  const int32_t inc = block_inclusive_scan_1024(bins[blockIdx.x * 1024 + threadIdx.x], warp_sums);
+  if (threadIdx.x == 1023) totals[blockIdx.x] = inc;
+}
+__global__ void __launch_bounds__(1024) nb_scan_kernel(int32_t* bins, const int32_t* __restrict__ totals) {
+  __shared__ int32_t warp_sums[32];
+  __shared__ int32_t base;
+  int32_t before = 0;
+  for (int i = threadIdx.x; i < int(blockIdx.x); i += 1024) before += totals[i];     // kScanBlocks <= 1024: one value per thread
+  const int32_t all = block_inclusive_scan_1024(before, warp_sums);
+  if (threadIdx.x == 1023) base = all;
+  __syncthreads();
+  const int32_t off = base;
+  __syncthreads();
+  const int32_t v = bins[blockIdx.x * 1024 + threadIdx.x];
+  const int32_t inc = block_inclusive_scan_1024(v, warp_sums);
+  bins[blockIdx.x * 1024 + threadIdx.x] = off + inc - v;
 }
 
 __global__ void __launch_bounds__(256) nb_scatter_kernel(const int32_t* __restrict__ bin_of_row, int64_t n,
@@ -330,13 +335,15 @@ __global__ void __launch_bounds__(256) nb_plan_kernel(const int32_t* __restrict_
 }  // namespace nbp
 
 // ---- plan geometry: a pure function of (n_out, K) and the knobs, so the builder and the kernels agree without a header ----
-static int g_nb_rt = 0, g_nb_umax = 0, g_nb_min_rows = 0, g_nb_off = 0;
+static int g_nb_rt = 0, g_nb_umax = 0, g_nb_min_rows = 0, g_nb_off = 0, g_nb_target = 0, g_nb_no_split = 0;
 int nb_tune(const char* key, int value) {
   const std::string s(key);
   if (s == "nb_rt") g_nb_rt = value;
   else if (s == "nb_umax") g_nb_umax = value;
   else if (s == "nb_min_rows") g_nb_min_rows = value;
   else if (s == "nb_off") g_nb_off = value;
+  else if (s == "nb_target_ctas") g_nb_target = value;
+  else if (s == "nb_no_split") g_nb_no_split = value;
   else return 0;
   return 1;
 }
@@ -346,12 +353,15 @@ NbGeom nb_geometry(int64_t n_out, int K) {
   g.K = K;
   g.tm = 2;
   g.umax = std::min(4000, g_nb_umax > 0 ? g_nb_umax : 640);
-  // rows per tile: whole waves of 296 CTAs (2 resident per SM), tiles as full as the wave count allows
+  // rows per tile.  Large maps: whole waves of 296 CTAs (2 resident per SM), tiles as full as the wave count allows.
+  // Small maps (fewer than 148 x 128 rows, where the BatchNorm statistics are not fused either): full 128-row tiles — conv_nb.cu finds its parallelism by splitting the
+  // reduction over CTAs instead of by emptying MMA lanes.
   const int64_t slots = 296;
   const int64_t full = cdiv(n_out, int64_t(g.tm) * 128);
   const int64_t waves = std::max<int64_t>(1, cdiv(full, slots));
   int rt = int(cdiv(cdiv(n_out, waves * slots), int64_t(g.tm)));
   rt = std::min(128, std::max(32, rt));
+  if (n_out < 148 * 128) rt = int(std::min<int64_t>(128, std::max<int64_t>(8, cdiv(n_out, int64_t(g.tm)))));
   if (g_nb_rt > 0) rt = std::min(128, std::max(8, g_nb_rt));
   rt = std::min(128, (rt + 7) & ~7);                // whole octets of slots per tile (colour groups, see the header comment)
   g.rt = rt;
@@ -366,7 +376,9 @@ NbGeom nb_geometry(int64_t n_out, int K) {
   return g;
 }
 
-int nb_min_rows() { return g_nb_min_rows > 0 ? g_nb_min_rows : 148 * 128; }
+int nb_min_rows() { return g_nb_min_rows > 0 ? g_nb_min_rows : 256; }
+int nb_target_ctas() { return g_nb_target > 0 ? g_nb_target : 296; }
+int nb_no_split() { return g_nb_no_split; }
 int nb_disabled() { return g_nb_off; }
 
 }  // namespace lgs
@@ -383,7 +395,7 @@ int64_t lgs_nbplan_bytes(int64_t n_out, int32_t K) {
 int64_t lgs_nbplan_scratch_bytes(int64_t n_out) {
   if (n_out <= 0) return 0;
   const int64_t n_pad = n_out + 2 * 128 * 4;       // order_tmp / bin_of_row
-  return (8 + 2 * int64_t(nbp::kBins) + 2 * n_pad) * 4;
+  return (8 + 1024 + 2 * int64_t(nbp::kBins) + 2 * n_pad) * 4;
 }
 
 int lgs_nbplan_supported(int64_t n_out, int32_t K) {
@@ -401,7 +413,8 @@ int lgs_nbplan_build(const int32_t* d_out_coords, int64_t n_out, const int32_t* 
   int32_t* plan = static_cast<int32_t*>(d_plan);
   int32_t* scr = static_cast<int32_t*>(d_scratch);
   int32_t* ext = scr;
-  int32_t* bins = scr + 8;
+  int32_t* totals = scr + 8;
+  int32_t* bins = scr + 8 + 1024;
   int32_t* cursor = bins + nbp::kBins;
   int32_t* bin_of_row = cursor + nbp::kBins;
   int32_t* order_tmp = bin_of_row + (n_out + 1024);
@@ -412,7 +425,8 @@ int lgs_nbplan_build(const int32_t* d_out_coords, int64_t n_out, const int32_t* 
   const unsigned rb = unsigned(cdiv(n_out, 256));
   LGS_LAUNCH(nbp::nb_extent_kernel, std::min(rb, 148u * 8u), 256, 0, stream, d_out_coords, n_out, ext);
   LGS_LAUNCH(nbp::nb_bin_kernel, rb, 256, 0, stream, d_out_coords, n_out, ext, bin_of_row, bins);
-  LGS_LAUNCH(nbp::nb_scan_kernel, 1, 1024, 0, stream, bins);
+  LGS_LAUNCH(nbp::nb_scan_totals_kernel, nbp::kScanBlocks, 1024, 0, stream, bins, totals);
+  LGS_LAUNCH(nbp::nb_scan_kernel, nbp::kScanBlocks, 1024, 0, stream, bins, totals);
   LGS_LAUNCH(nbp::nb_scatter_kernel, rb, 256, 0, stream, bin_of_row, n_out, bins, cursor, order_tmp);
   LGS_LAUNCH(nbp::nb_rank_kernel, unsigned(cdiv(n_pad, 256)), 256, 0, stream, bin_of_row, n_out, n_pad, bins, cursor, order_tmp,
              plan + g.off_order);

@@ -183,6 +183,44 @@ def test_conv_nb_vs_table_driven_and_simt(E, lib, c_in, c_in2, c_out, bias, reve
         lib.lgs_tune(b"nb_min_rows", 0)
 
 
+@pytest.mark.parametrize("n_target,c_in,c_out", [(450, 256, 256), (2200, 256, 256), (2200, 128, 128), (8500, 64, 64), (8500, 192, 128)])
+def test_conv_nb_small_map_split(E, lib, n_target, c_in, c_out):
+    """coarse U-Net levels: fewer supertiles than SMs -> the reduction over channel blocks / offsets is split over CTAs
+    (red.global.add on a zeroed output).  Against the table-driven bx3 kernel and exact SIMT fp32; prints both times."""
+    from languagegroundedsemseg_b200 import _lib
+    coords, km = _scene_map(E, lib, n_target, 11, min_rows=0)
+    assert km.plan is not None, km.plan_stats
+    n, K = km.n_out, 27
+    torch.manual_seed(n_target + c_in)
+    x = torch.randn(n, c_in, device="cuda")
+    w = torch.randn(K, c_in, c_out, device="cuda") / np.sqrt(K * c_in)
+    b = torch.randn(1, c_out, device="cuda")
+    w_fwd, _ = _operands(lib, w)
+    outs, t = {}, {}
+    for name, plan in (("nb", km.plan), ("table", None)):
+        for rev in (0, 1):
+            outs[name, rev] = _conv3(lib, x, None, w_fwd, K, c_out, km, plan, rev, b, None)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o = torch.empty(n, c_out, device="cuda")
+        for _ in range(3):
+            _conv3(lib, x, None, w_fwd, K, c_out, km, plan, 0, b, None, o)
+        e0.record()
+        for _ in range(20):
+            _conv3(lib, x, None, w_fwd, K, c_out, km, plan, 0, b, None, o)
+        e1.record()
+        torch.cuda.synchronize()
+        t[name] = e0.elapsed_time(e1) / 20 * 1e3
+    y_ref = torch.empty(n, c_out, device="cuda")
+    _lib.check(lib.lgs_conv_fwd(_lib.ptr(x), n, c_in, _lib.ptr(w), _lib.W_KCN, K, c_out, _lib.ptr(km.fwd_table), n,
+                                0, _lib.ptr(b), _lib.ptr(y_ref), _lib.F32, _lib.ALGO_SIMT, _stream()))
+    e_tb = max(rel_err(outs["nb", r], outs["table", r]) for r in (0, 1))
+    e_ref = rel_err(outs["nb", 0], y_ref)
+    print(f"[small map {n} rows {c_in}->{c_out}] nb {t['nb']:.1f} us, table-driven {t['table']:.1f} us; vs table-driven {e_tb:.1e}, vs SIMT {e_ref:.1e}; "
+          f"unique rows max {km.plan_stats[1]}")
+    assert not torch.isnan(outs["nb", 0]).any()
+    assert e_tb < 3e-5 and e_ref < 1e-4
+
+
 def test_facade_layers_with_plan_vs_oracle(E, lib):
     """two stacked 3^3 convolutions fwd + bwd through the facade with plans on (small-map threshold lowered) vs the oracle"""
     from oracle import me_cpu
