@@ -120,6 +120,11 @@ def load():
                 for name in SIGNATURES:
                     if hasattr(_fast, name):
                         setattr(ns, name, getattr(_fast, name))
+        # LGS_TUNE="key=value,key=value": lgs_tune knobs for experiments (e.g. pdl=0, nb_off=1); unknown keys raise
+        for kv in filter(None, os.environ.get("LGS_TUNE", "").split(",")):
+            key, _, val = kv.partition("=")
+            if lib.lgs_tune(key.strip().encode(), int(val)) != 0:
+                raise RuntimeError(f"LGS_TUNE: unknown knob {key!r}")
         _lib = ns
     return _lib
 

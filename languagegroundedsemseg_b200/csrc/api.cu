@@ -1,4 +1,6 @@
 // C-ABI dispatch for the convolution entry points (include/lgs_b200.h).
+#include <string>
+
 #include "common.cuh"
 
 namespace lgs {
@@ -38,6 +40,10 @@ int lgs_has_tc(void) { return tc_built() ? 1 : 0; }
 
 int lgs_tune(const char* key, int32_t value) {
   if (!key) return fail(LGS_E_INVALID, "lgs_tune: null key");
+  if (std::string(key) == "pdl") {
+    g_pdl.store(value ? 1 : 0);
+    return LGS_OK;
+  }
   if (bx3_tune(key, value)) return LGS_OK;
   if (nb_tune(key, value)) return LGS_OK;
   return fail(LGS_E_INVALID, "lgs_tune: unknown key %s", key);

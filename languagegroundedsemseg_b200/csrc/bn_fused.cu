@@ -42,6 +42,7 @@ __device__ __forceinline__ void bn_block_reduce(float a, float b, int ch, int c,
 template <int U>
 __global__ void __launch_bounds__(BN_TX * BN_TY)
 bn_stats_kernel(const float* __restrict__ x, int64_t n, int c, double* __restrict__ sums /*[BN_COPIES][2c]*/) {
+  pdl_grid_sync();
   const int ch = blockIdx.x * BN_TX + threadIdx.x;
   const int64_t r0 = int64_t(blockIdx.y) * BN_ROWS + threadIdx.y;
   const int64_t r1 = min(n, int64_t(blockIdx.y + 1) * BN_ROWS);
@@ -92,6 +93,7 @@ __device__ __forceinline__ void bn_vec_reduce(const float (&a)[4], const float (
 template <int U>
 __global__ void __launch_bounds__(BN_VTHREADS)
 bn_stats_vec_kernel(const float4* __restrict__ x, int64_t n, int c, int T, double* __restrict__ sums /*[BN_COPIES][2c]*/) {
+  pdl_grid_sync();
   const int c4 = c >> 2;
   const int64_t i0 = int64_t(blockIdx.x) * BN_VROWS * c4;
   const int64_t i1 = min(n, int64_t(blockIdx.x + 1) * BN_VROWS) * c4;
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(BN_VTHREADS)
 bn_bwd_stats_vec_kernel(const float4* __restrict__ x, const float4* __restrict__ z, const float4* __restrict__ dz, int64_t n,
                         int c, int T, const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
                         double* __restrict__ sums /*[BN_COPIES][2c]: sum dy, sum dy*xhat*/) {
+  pdl_grid_sync();
   const int c4 = c >> 2;
   const int64_t i0 = int64_t(blockIdx.x) * BN_VROWS * c4;
   const int64_t i1 = min(n, int64_t(blockIdx.x + 1) * BN_VROWS) * c4;
@@ -157,6 +160,7 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, int6
                 float eps, int relu, float* __restrict__ z, float* __restrict__ save_mean, float* __restrict__ save_invstd,
                 float* running_mean, float* running_var, float momentum, long long* num_batches_tracked,
                 double* __restrict__ zero_next) {
+  pdl_grid_sync();
   extern __shared__ float sh[];   // scale[c], shift[c]
   float* scale = sh;
   float* shift = sh + c;
@@ -215,6 +219,7 @@ __global__ void __launch_bounds__(BN_TX * BN_TY)
 bn_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ z, const float* __restrict__ dz, int64_t n, int c,
                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
                     double* __restrict__ sums /*[BN_COPIES][2c]: sum dy, sum dy*xhat*/) {
+  pdl_grid_sync();
   const int ch = blockIdx.x * BN_TX + threadIdx.x;
   const int64_t r0 = int64_t(blockIdx.y) * BN_ROWS + threadIdx.y;
   const int64_t r1 = min(n, int64_t(blockIdx.y + 1) * BN_ROWS);
@@ -247,6 +252,7 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ z, co
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const double* __restrict__ sums, int relu, float* __restrict__ dx, float* __restrict__ dres,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, double* __restrict__ zero_next) {
+  pdl_grid_sync();
   extern __shared__ float sh[];   // k1[c] = gamma*invstd, k2[c] = mean(dy), k3[c] = mean(dy*xhat), m[c], is[c]
   float* k1 = sh;
   float* k2 = sh + c;
@@ -339,18 +345,18 @@ int lgs_bn_fwd2(const float* d_x, const float* d_residual, int64_t n, int32_t c,
   if (stats_ready) {
     // the column sums were accumulated by the producing convolution's epilogue (lgs_conv_fwd2, d_bn_sums): no statistics pass
   } else if (bn_use_vec(d_x, nullptr, nullptr, c)) {
-    LGS_LAUNCH(bn_stats_vec_kernel<4>, unsigned(cdiv(n, BN_VROWS)), BN_VTHREADS, 0, stream,
+    LGS_LAUNCH_PDL(bn_stats_vec_kernel<4>, unsigned(cdiv(n, BN_VROWS)), BN_VTHREADS, 0, stream,
                reinterpret_cast<const float4*>(d_x), n, c, bn_vec_threads(c), d_scratch);
   } else if (unroll == 1) {
-    LGS_LAUNCH(bn_stats_kernel<1>, grid, block, 0, stream, d_x, n, c, d_scratch);
+    LGS_LAUNCH_PDL(bn_stats_kernel<1>, grid, block, 0, stream, d_x, n, c, d_scratch);
   } else {
-    LGS_LAUNCH(bn_stats_kernel<4>, grid, block, 0, stream, d_x, n, c, d_scratch);
+    LGS_LAUNCH_PDL(bn_stats_kernel<4>, grid, block, 0, stream, d_x, n, c, d_scratch);
   }
   const int64_t total4 = n * c / 4;
   int blocks = int(cdiv(total4, 256 * 4));
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  LGS_LAUNCH(bn_apply_kernel, blocks, 256, size_t(2 * c) * sizeof(float), stream, d_x, d_residual, n, c, d_scratch, d_gamma, d_beta,
+  LGS_LAUNCH_PDL(bn_apply_kernel, blocks, 256, size_t(2 * c) * sizeof(float), stream, d_x, d_residual, n, c, d_scratch, d_gamma, d_beta,
              eps, relu, d_z, d_save_mean, d_save_invstd, d_running_mean, d_running_var, momentum,
              reinterpret_cast<long long*>(d_num_batches_tracked), d_scratch_next);
   return LGS_OK;
@@ -370,19 +376,19 @@ int lgs_bn_bwd(const float* d_x, const float* d_z, const float* d_dz, int64_t n,
   static const int unroll = getenv("LGS_BN_UNROLL") ? atoi(getenv("LGS_BN_UNROLL")) : 4;
   if (bn_use_vec(d_x, relu ? d_z : nullptr, d_dz, c) && !(reinterpret_cast<uintptr_t>(d_save_mean) & 15) &&
       !(reinterpret_cast<uintptr_t>(d_save_invstd) & 15)) {
-    LGS_LAUNCH(bn_bwd_stats_vec_kernel<2>, unsigned(cdiv(n, BN_VROWS)), BN_VTHREADS, 0, stream,
+    LGS_LAUNCH_PDL(bn_bwd_stats_vec_kernel<2>, unsigned(cdiv(n, BN_VROWS)), BN_VTHREADS, 0, stream,
                reinterpret_cast<const float4*>(d_x), reinterpret_cast<const float4*>(d_z),
                reinterpret_cast<const float4*>(d_dz), n, c, bn_vec_threads(c), d_save_mean, d_save_invstd, relu, d_scratch);
   } else if (unroll == 1) {
-    LGS_LAUNCH(bn_bwd_stats_kernel<1>, grid, block, 0, stream, d_x, d_z, d_dz, n, c, d_save_mean, d_save_invstd, relu, d_scratch);
+    LGS_LAUNCH_PDL(bn_bwd_stats_kernel<1>, grid, block, 0, stream, d_x, d_z, d_dz, n, c, d_save_mean, d_save_invstd, relu, d_scratch);
   } else {
-    LGS_LAUNCH(bn_bwd_stats_kernel<4>, grid, block, 0, stream, d_x, d_z, d_dz, n, c, d_save_mean, d_save_invstd, relu, d_scratch);
+    LGS_LAUNCH_PDL(bn_bwd_stats_kernel<4>, grid, block, 0, stream, d_x, d_z, d_dz, n, c, d_save_mean, d_save_invstd, relu, d_scratch);
   }
   const int64_t total4 = n * c / 4;
   int blocks = int(cdiv(total4, 256 * 4));
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  LGS_LAUNCH(bn_bwd_apply_kernel, blocks, 256, size_t(5 * c) * sizeof(float), stream, d_x, d_z, d_dz, n, c, d_save_mean,
+  LGS_LAUNCH_PDL(bn_bwd_apply_kernel, blocks, 256, size_t(5 * c) * sizeof(float), stream, d_x, d_z, d_dz, n, c, d_save_mean,
              d_save_invstd, d_gamma, d_scratch, relu, d_dx, d_dresidual, d_dgamma, d_dbeta, d_scratch_next);
   return LGS_OK;
 }

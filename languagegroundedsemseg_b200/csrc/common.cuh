@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdarg>
+#include <utility>
 
 #include "../../include/lgs_b200.h"
 
@@ -36,6 +37,39 @@ inline int fail(int code, const char* fmt, ...) {
     ::lgs::g_launches.fetch_add(1, std::memory_order_relaxed);                                      \
     LGS_CUDA(cudaGetLastError());                                                                   \
   } while (0)
+
+// ---- programmatic dependent launch --------------------------------------------------------------------
+// A kernel launched with LGS_LAUNCH_PDL may be scheduled while the previous kernel of its stream is still running (its
+// CTAs become resident as the predecessor's drain) — the launch latency and the drain / fill gap between two dependent
+// kernels (2-3 us, ~500 launches per training step) overlap.  Contract: such a kernel calls pdl_grid_sync() before it
+// touches global memory (griddepcontrol.wait returns when the predecessor grid has completed and its writes are
+// visible), which also lets ITS successor launch early.  lgs_tune("pdl", 0) switches to plain launches.
+extern std::atomic<int> g_pdl;
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl.load(std::memory_order_relaxed) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#define LGS_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                                      \
+  do {                                                                                              \
+    LGS_CUDA(::lgs::launch_pdl(kernel, dim3(grid), dim3(block), size_t(smem), (stream), __VA_ARGS__)); \
+    ::lgs::g_launches.fetch_add(1, std::memory_order_relaxed);                                      \
+  } while (0)
+#endif
 
 // ---- call recorder (lgs_trace_begin / lgs_trace_end) --------------------------------------------------
 // While recording, a traced entry point appends one line "name arg arg ..." and returns LGS_OK WITHOUT touching the

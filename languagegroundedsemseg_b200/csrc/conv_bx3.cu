@@ -86,6 +86,7 @@ __device__ __forceinline__ void split2(float e0, float e1, uint32_t& hi, uint32_
 // read in front of every cp.async).  A warp-level cp.async costs ~16-18 cycles whether its lanes copy, zero-fill or are
 // predicated off, so the gather stream is bounded by (row, offset) SLOTS, not by bytes: ~500 cycles per 16 KB stage alone.
 __global__ void __launch_bounds__(THREADS, 1) conv_bx3_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
+  pdl_grid_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int SA = p.a_stages, SB = p.b_stages, TM = p.TM, STA = p.ta_stages;
@@ -450,6 +451,7 @@ __device__ __forceinline__ void weight_prep_bx3_tile(const float* __restrict__ w
 }
 
 __global__ void __launch_bounds__(256) weight_prep_bx3_batch_kernel(const int64_t* __restrict__ desc, int n_layers) {
+  pdl_grid_sync();
   const int64_t b = blockIdx.x;
   int lo = 0, hi = n_layers - 1;
   while (lo < hi) {
@@ -471,7 +473,7 @@ __global__ void __launch_bounds__(256) weight_prep_bx3_kernel(const float* __res
 int weight_prep_bx3_batch(const int64_t* desc, int n_layers, int64_t total_tiles, cudaStream_t stream) {
   if (n_layers == 0 || total_tiles == 0) return LGS_OK;
   const dim3 block{32u, 8u, 1u};
-  LGS_LAUNCH(bx3::weight_prep_bx3_batch_kernel, unsigned(total_tiles), block, 0, stream, desc, n_layers);
+  LGS_LAUNCH_PDL(bx3::weight_prep_bx3_batch_kernel, unsigned(total_tiles), block, 0, stream, desc, n_layers);
   return LGS_OK;
 }
 
@@ -648,7 +650,7 @@ int conv_fwd_bx3(const void* in, int c_in, const void* in2, int c_in2, const voi
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(LGS_E_CUDA, "cuTensorMapEncodeTiled (bx3) failed (%d) c_in=%d c_out=%d K=%d", int(cr), c_in + c_in2, c_out, K);
   const dim3 grid{unsigned(bGX), unsigned(bNS), unsigned(q.k_splits)};
-  LGS_LAUNCH(conv_bx3_kernel, grid, THREADS, smem, stream, tmap, q);
+  LGS_LAUNCH_PDL(conv_bx3_kernel, grid, THREADS, smem, stream, tmap, q);
   return LGS_OK;
 }
 

@@ -196,6 +196,7 @@ __device__ __noinline__ void epilogue_rows(uint32_t tmem_lane_base, int n_tile, 
 }
 
 __global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_constant__ CUtensorMap tmap_w, const Params p) {
+  pdl_grid_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int SB = p.b_stages, K = p.K, umax = p.umax;
@@ -516,7 +517,7 @@ int conv_fwd_nb(const void* in, int c_in, const void* in2, int c_in2, const void
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(LGS_E_CUDA, "cuTensorMapEncodeTiled (nb) failed (%d) c_in=%d c_out=%d K=%d", int(cr), c_in + c_in2, c_out, K);
   const dim3 grid{unsigned(g.S), unsigned(n_slices), gz};
-  LGS_LAUNCH(conv_nb_kernel, grid, THREADS, smem, stream, tmap, q);
+  LGS_LAUNCH_PDL(conv_nb_kernel, grid, THREADS, smem, stream, tmap, q);
   return LGS_OK;
 }
 

@@ -1140,6 +1140,7 @@ __device__ __forceinline__ uint32_t mn_chunk_pos(uint32_t c, uint32_t r) {
 template <bool BF16>
 __global__ void __launch_bounds__(THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
+  pdl_grid_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int blk_bytes = p.R * KBLOCK_BYTES;             // one channel block of one tile
@@ -1504,9 +1505,9 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
 
   const dim3 grid{unsigned(chunks), unsigned(groups), unsigned(n_splits * m_slices)};
   if (dtype == LGS_BF16) {
-    LGS_LAUNCH(wgrad_tc_kernel<true>, grid, THREADS, smem_bytes, stream, tmap, q);
+    LGS_LAUNCH_PDL(wgrad_tc_kernel<true>, grid, THREADS, smem_bytes, stream, tmap, q);
   } else {
-    LGS_LAUNCH(wgrad_tc_kernel<false>, grid, THREADS, smem_bytes, stream, tmap, q);
+    LGS_LAUNCH_PDL(wgrad_tc_kernel<false>, grid, THREADS, smem_bytes, stream, tmap, q);
   }
   return LGS_OK;
 }

@@ -15,6 +15,7 @@ namespace lgs {
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_trace_on{0};
+std::atomic<int> g_pdl{1};
 static std::mutex g_trace_mu;
 static std::string g_trace_buf;
 

@@ -27,6 +27,7 @@ namespace lgs {
 // `cat` (models/res16unet.py:237,247,257,267), its backward column split, c_in 3 -> 4 padding, gradient slicing
 __global__ void __launch_bounds__(256) copy2d_kernel(const float* __restrict__ src, int64_t src_ld, const float* dummy,
                                                      float* __restrict__ dst, int64_t dst_ld, int64_t rows, int cols) {
+  pdl_grid_sync();
   (void)dummy;
   const int64_t total = rows * cols;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) copy2d_kernel(const float* __restrict__ s
 }
 __global__ void __launch_bounds__(256) copy2d_v4_kernel(const float4* __restrict__ src, int64_t src_ld4, float4* __restrict__ dst,
                                                         int64_t dst_ld4, int64_t rows, int cols4) {
+  pdl_grid_sync();
   const int64_t total = rows * cols4;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
     const int64_t r = i / cols4;
@@ -47,6 +49,7 @@ __global__ void __launch_bounds__(256) copy2d_v4_kernel(const float4* __restrict
 // out = a + b (float4 stream): gradient accumulation where two consumers meet (residual branches, skip connections)
 __global__ void __launch_bounds__(256) add_v4_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out,
                                                      int64_t n4) {
+  pdl_grid_sync();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
     const float4 x = __ldg(a + i), y = __ldg(b + i);
     out[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
@@ -54,6 +57,7 @@ __global__ void __launch_bounds__(256) add_v4_kernel(const float4* __restrict__ 
 }
 // out[c] = sum_r g[r, c]  (bias gradient of the classifier, models/res16unet.py:193): block = 32 x 8, fp32 partials, atomics
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g, int64_t rows, int c, float* __restrict__ out) {
+  pdl_grid_sync();
   __shared__ float sh[8][33];
   const int ch = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
@@ -85,10 +89,10 @@ int lgs_copy2d(const float* d_src, int64_t src_ld, float* d_dst, int64_t dst_ld,
   const int64_t work = v4 ? rows * (cols / 4) : rows * cols;
   const unsigned blocks = unsigned(std::min<int64_t>(cdiv(work, 256 * 4), 148 * 8));
   if (v4) {
-    LGS_LAUNCH(copy2d_v4_kernel, std::max(1u, blocks), 256, 0, stream, reinterpret_cast<const float4*>(d_src), src_ld / 4,
+    LGS_LAUNCH_PDL(copy2d_v4_kernel, std::max(1u, blocks), 256, 0, stream, reinterpret_cast<const float4*>(d_src), src_ld / 4,
                reinterpret_cast<float4*>(d_dst), dst_ld / 4, rows, cols / 4);
   } else {
-    LGS_LAUNCH(copy2d_kernel, std::max(1u, blocks), 256, 0, stream, d_src, src_ld, nullptr, d_dst, dst_ld, rows, cols);
+    LGS_LAUNCH_PDL(copy2d_kernel, std::max(1u, blocks), 256, 0, stream, d_src, src_ld, nullptr, d_dst, dst_ld, rows, cols);
   }
   return LGS_OK;
 }
@@ -101,7 +105,7 @@ int lgs_add(const float* d_a, const float* d_b, float* d_out, int64_t n, void* s
   if (!d_a || !d_b || !d_out || ((reinterpret_cast<uintptr_t>(d_a) | reinterpret_cast<uintptr_t>(d_b) | reinterpret_cast<uintptr_t>(d_out)) & 15))
     return fail(LGS_E_INVALID, "lgs_add: null or unaligned pointer");
   const unsigned blocks = unsigned(std::min<int64_t>(cdiv(n / 4, 256 * 4), 148 * 8));
-  LGS_LAUNCH(add_v4_kernel, std::max(1u, blocks), 256, 0, stream, reinterpret_cast<const float4*>(d_a), reinterpret_cast<const float4*>(d_b),
+  LGS_LAUNCH_PDL(add_v4_kernel, std::max(1u, blocks), 256, 0, stream, reinterpret_cast<const float4*>(d_a), reinterpret_cast<const float4*>(d_b),
              reinterpret_cast<float4*>(d_out), n / 4);
   return LGS_OK;
 }
@@ -113,7 +117,7 @@ int lgs_colsum(const float* d_g, int64_t rows, int32_t c, float* d_out, void* st
   LGS_CUDA(cudaMemsetAsync(d_out, 0, size_t(c) * sizeof(float), stream));
   if (rows == 0) return LGS_OK;
   const dim3 grid{unsigned((c + 31) / 32), unsigned(std::min<int64_t>(cdiv(rows, 8 * 16), 148 * 4)), 1u}, block{32u, 8u, 1u};
-  LGS_LAUNCH(colsum_kernel, grid, block, 0, stream, d_g, rows, c, d_out);
+  LGS_LAUNCH_PDL(colsum_kernel, grid, block, 0, stream, d_g, rows, c, d_out);
   return LGS_OK;
 }
 

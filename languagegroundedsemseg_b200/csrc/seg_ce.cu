@@ -16,6 +16,7 @@ constexpr int SCE_MAXV = 8;               // float4 per lane: C <= 1024
 
 __global__ void __launch_bounds__(1024)
 seg_ce_count_kernel(const int64_t* __restrict__ labels, int64_t n, int c, int64_t ignore, double* __restrict__ ws) {
+  pdl_grid_sync();
   __shared__ int part[32];
   int cnt = 0;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
@@ -37,6 +38,7 @@ seg_ce_count_kernel(const int64_t* __restrict__ labels, int64_t n, int c, int64_
 __global__ void __launch_bounds__(SCE_THREADS)
 seg_ce_kernel(const float* __restrict__ logits, int64_t n, int c, const int64_t* __restrict__ labels, int64_t ignore,
               double* __restrict__ ws, float* __restrict__ loss_out, float* __restrict__ dlogits) {
+  pdl_grid_sync();
   __shared__ float wsum[SCE_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = int64_t(blockIdx.x) * (SCE_THREADS / 32) + warp;
@@ -131,8 +133,8 @@ int lgs_seg_ce(const float* d_logits, int64_t n, int32_t c, const int64_t* d_lab
   if (!d_logits || !d_labels || !d_ws || !d_loss) return fail(LGS_E_INVALID, "lgs_seg_ce: null pointer");
   if ((reinterpret_cast<uintptr_t>(d_logits) & 15) || (reinterpret_cast<uintptr_t>(d_grad_logits) & 15))
     return fail(LGS_E_UNSUPPORTED, "lgs_seg_ce: logits / gradient rows must be 16-byte aligned");
-  LGS_LAUNCH(seg_ce_count_kernel, 1, 1024, 0, stream, d_labels, n, c, ignore_label, d_ws);
-  LGS_LAUNCH(seg_ce_kernel, unsigned(cdiv(n, SCE_THREADS / 32)), SCE_THREADS, 0, stream, d_logits, n, c, d_labels,
+  LGS_LAUNCH_PDL(seg_ce_count_kernel, 1, 1024, 0, stream, d_labels, n, c, ignore_label, d_ws);
+  LGS_LAUNCH_PDL(seg_ce_kernel, unsigned(cdiv(n, SCE_THREADS / 32)), SCE_THREADS, 0, stream, d_logits, n, c, d_labels,
              ignore_label, d_ws, d_loss, d_grad_logits);
   return LGS_OK;
 }
