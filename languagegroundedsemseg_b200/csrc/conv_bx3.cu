@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_bx3_kernel(const __grid_const
           for (int i = 0; i < 4; ++i) {
             const int r = rbase + 32 * i;
             const int64_t o = m0 + int64_t(t) * p.rt + r;
-            v[t][i] = (t < TM && r < p.rt && o < p.n_out) ? (trow ? __ldg(trow + o) : int32_t(o)) : -1;
+            v[t][i] = (t < TM && r < p.rt && o < p.n_out) ? (trow ? ldg_nc_ordered(trow + o) : int32_t(o)) : -1;
           }
         }
       };

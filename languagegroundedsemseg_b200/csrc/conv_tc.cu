@@ -1217,7 +1217,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int64_t o = row0 + 16 * i;
-        v[i] = (i < passes && o < r_end) ? (trow ? __ldg(trow + o) : int32_t(o)) : -1;
+        v[i] = (i < passes && o < r_end) ? (trow ? ldg_nc_ordered(trow + o) : int32_t(o)) : -1;
       }
     };
     int32_t cur[8], nxt[8];

@@ -167,6 +167,13 @@ __device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) {
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
+// table entry read that keeps its place in program order (asm volatile): a plain __ldg of read-only data may be sunk by the
+// compiler past the cp.async / mbarrier code it is meant to run ahead of, which exposes its L2 latency at the next stage
+__device__ __forceinline__ int32_t ldg_nc_ordered(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ---- host side: driver entry point of cuTensorMapEncodeTiled (no -lcuda link dependency on the symbol) ----
