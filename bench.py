@@ -52,7 +52,8 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled while the timed regions run: NVML in-process every 100 ms (nvidia-smi -lms 200 as
+    the fallback); rows = [host time, sm MHz, max sm MHz, power, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap]."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -60,7 +61,39 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
         self.window = None          # (t0, t1) host times of the timed region: only samples inside it are reported
 
+    def _nvml_loop(self, nv, h):
+        names = {0x8: 3, 0x40: 4, 0x20: 5, 0x4: 6}          # HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap -> row column
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self._stop.is_set():
+            try:
+                row = [time.time(), str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), "", "Not Active", "Not Active", "Not Active", "Not Active"]
+                mask = get_reasons(h)
+                for bit, col in names.items():
+                    if mask & bit:
+                        row[col + 1] = "Active"
+                self.rows.append(row)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
     def __enter__(self):
+        # in-process NVML (nvidia_ml_py) first: one clock + one reasons query per 100 ms from a thread.  The nvidia-smi child
+        # process it replaces stalled the CUDA launch path for 50-80 ms in one timed region out of three (one step of 87 ms
+        # among 11 ms steps, profiles/r2_bench_stalls.txt); nvidia-smi stays as the fallback
+        try:
+            if self.index < 0:
+                raise RuntimeError('disabled')
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self._stop = threading.Event()
+            self.t = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.t.start()
+            self.nvml = True
+            return self
+        except Exception:
+            self.nvml = False
         try:
             if self.index < 0:
                 raise RuntimeError('disabled')
@@ -81,6 +114,10 @@ class ClockSampler:
     def wait_first_sample(self, timeout=15.0):
         """block until the poller has printed its first row, i.e. its NVML start-up (1-3 s on an 8-GPU box) is over"""
         t0 = time.time()
+        if getattr(self, "nvml", False):
+            while not self.rows and time.time() - t0 < timeout:
+                time.sleep(0.02)
+            return
         while self.proc is not None and self.proc.poll() is None and not self.rows and time.time() - t0 < timeout:
             time.sleep(0.05)
 
@@ -89,6 +126,10 @@ class ClockSampler:
             self.proc.terminate()
 
     def __exit__(self, *a):
+        if getattr(self, "nvml", False):
+            self._stop.set()
+            self.t.join(timeout=2)
+            return
         if self.proc and self.proc.poll() is None:
             time.sleep(0.25)
             self.proc.terminate()
@@ -429,12 +470,16 @@ def run_engine(args, rank, world, local_rank):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_w0 = time.time()
     ev0.record()
+    marks = []
     for _ in range(args.steps):
         loss = resident_step()
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record()
     ev1.record()
     barrier()
     clocks_value = clk.summary((t_w0, time.time()))
     ms = ev0.elapsed_time(ev1)
+    per_step = [a.elapsed_time(b) for a, b in zip([ev0] + marks[:-1], marks)]      # diagnostics only: the value is ms / steps
     launches = _lib.launch_count() - l0
     loss_val = float(loss.item())
     if args.profile_run:
@@ -518,7 +563,8 @@ def run_engine(args, rank, world, local_rank):
     h2d = h_coords.numel() * 4 + h_feats.numel() * 4 + h_labels.numel() * 8
     res = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "warmup_done": warm_done, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "warmup_done": warm_done, "ms_per_step": round(ms / args.steps, 3),
+        "step_ms": {"median": round(statistics.median(per_step), 3), "min": round(min(per_step), 3), "max": round(max(per_step), 3)}, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.dtype == "f32" else "bf16", "data": "synthetic",
         "config": {"workload": workload_string(args.model, n_vox, args.voxel_size, args.voxels, args.config), "voxels_per_gpu": n_vox, "algo": args.algo,
                    "binding": _lib.binding() + " (Python -> C ABI)",

@@ -279,14 +279,44 @@ class _CoordMap:
     __slots__ = ("coords", "tkeys", "tvals", "n", "capacity")
 
 
+_PLAN_STATUS = {"buf": None, "next": 0}          # pinned ring of plan-builder status words (cudaHostAlloc once, not per plan)
+
+
+def _plan_status_slot():
+    if _PLAN_STATUS["buf"] is None:
+        _PLAN_STATUS["buf"] = torch.empty(256, 2, dtype=torch.int32).pin_memory()
+    i = _PLAN_STATUS["next"]
+    _PLAN_STATUS["next"] = (i + 1) % 256
+    return _PLAN_STATUS["buf"][i]
+
+
 class KernelMap:
     """Output-stationary neighbour tables of one (in map, out map, kernel) triple.
     fwd_table [K, n_out] rows of the input map; bwd_table [K, n_in] rows of the output map (dgrad)."""
-    __slots__ = ("K", "n_in", "n_out", "fwd_table", "bwd_table", "bwd_reverse", "counts", "plan", "plan_stats")
-    # plan: neighbourhood plan of a large same-map 3^3 table (lgs_nbplan_build; None when not built / not usable)
+    __slots__ = ("K", "n_in", "n_out", "fwd_table", "bwd_table", "bwd_reverse", "counts", "_plan", "_plan_status", "_plan_event",
+                 "_plan_builder", "plan_stats")
+    # plan: neighbourhood plan of a same-map 3^3 table (lgs_nbplan_build; None when not built / not usable).  Built with the
+    # kernel map (on the staging stream, a step ahead) once some convolution has asked for one, lazily at the first request
+    # before that (bf16 / 'tc' / 'simt' runs never ask and never pay for plans).  The builder's status (did a supertile overflow
+    # the cache?) comes back through pinned memory behind an event and is only waited for at the first use of the plan —
+    # normally a step later, so building plans never blocks the host.
 
     def __init__(self):
-        self.plan = self.plan_stats = None
+        self._plan = self._plan_status = self._plan_event = self._plan_builder = self.plan_stats = None
+
+    @property
+    def plan(self):
+        if self._plan_builder is not None:
+            build, self._plan_builder = self._plan_builder, None
+            _state["plans_wanted"] = True
+            build()
+        if self._plan_event is not None:
+            self._plan_event.synchronize()
+            self._plan_event = None
+            self.plan_stats = (int(self._plan_status[0]), int(self._plan_status[1]))
+            if self.plan_stats[0] != 0:
+                self._plan = None                 # a supertile touches more unique rows than the cache holds: table-driven kernel
+        return self._plan
 
 
 def _build_coordmap(coords: torch.Tensor, quant: int, want_maps: bool):
@@ -392,20 +422,21 @@ class CoordinateManager:
         return table, counts
 
     def _plan(self, km, cmap, step):
-        """neighbourhood plan of a large same-map 3^3 kernel map: supertiles of spatially close output rows, their unique
-        input rows and the table in local indices (csrc/nbplan.cu), consumed by lgs_conv_fwd3.  One host sync (status)."""
+        """neighbourhood plan of a same-map 3^3 kernel map: supertiles of spatially close output rows, their unique input
+        rows and the table in local indices (csrc/nbplan.cu), consumed by lgs_conv_fwd3.  No host sync: see KernelMap.plan."""
         lib = _lib.load()
         if not _state.get("nbplan", True) or not lib.lgs_nbplan_supported(km.n_out, km.K):
             return
         dev = km.fwd_table.device
         plan = torch.empty(lib.lgs_nbplan_bytes(km.n_out, km.K) // 4, dtype=torch.int32, device=dev)
         scratch = torch.empty(lib.lgs_nbplan_scratch_bytes(km.n_out) // 4, dtype=torch.int32, device=dev)
-        status = (ctypes.c_int32 * 2)()
         _lib.check(lib.lgs_nbplan_build(_lib.ptr(cmap.coords), km.n_out, _lib.ptr(km.fwd_table), km.K, step, _lib.ptr(plan),
-                                        _lib.ptr(scratch), ctypes.cast(status, ctypes.c_void_p), _stream()))
-        km.plan_stats = (int(status[0]), int(status[1]))
-        if status[0] == 0:
-            km.plan = plan
+                                        _lib.ptr(scratch), None, _stream()))
+        km._plan_status = _plan_status_slot()
+        km._plan_status.copy_(plan[8:10], non_blocking=True)          # header words 8, 9: overflow flag, largest unique-row count
+        km._plan_event = torch.cuda.Event()
+        km._plan_event.record(torch.cuda.current_stream())
+        km._plan = plan
 
     def _transpose(self, table, n_in):
         lib = _lib.load()
@@ -436,7 +467,11 @@ class CoordinateManager:
             if in_key == out_key and ks % 2 == 1:
                 # C_in[i] = C[o] + off_k  <=>  C[o] = C_in[i] + off_{K-1-k}: dgrad reads the same table mirrored
                 km.bwd_table, km.bwd_reverse = km.fwd_table, True
-                self._plan(km, self._maps[out_key], _uniform(list(in_key.tensor_stride), "tensor stride") * dil)
+                cmap, step = self._maps[out_key], _uniform(list(in_key.tensor_stride), "tensor stride") * dil
+                if _state.get("plans_wanted"):
+                    self._plan(km, cmap, step)
+                else:
+                    km._plan_builder = lambda km=km, cmap=cmap, step=step: self._plan(km, cmap, step)
             else:
                 km.bwd_table, km.bwd_reverse = self._transpose(km.fwd_table, km.n_in), False
         self._kmaps[ck] = km
@@ -451,7 +486,7 @@ class CoordinateManager:
                     seen.add(id(t))
                     yield t
         for km in self._kmaps.values():
-            for t in (km.fwd_table, km.bwd_table, km.counts, km.plan):
+            for t in (km.fwd_table, km.bwd_table, km.counts, km._plan):
                 if t is not None and id(t) not in seen:
                     seen.add(id(t))
                     yield t
@@ -889,7 +924,7 @@ def _conv_fwd_impl(feats, weight, bias, km, algo, need_dgrad, module=None):
         w32 = weights32() if w32 is None else w32
         wf, layout, a = w32.to(feats.dtype), _lib.W_KCN, _lib.ALGO_SIMT
     with _Timed("fwd", K, c_in, c_out, n_in, n_out, km, feats.dtype):
-        if a == _lib.ALGO_BX3 and km is not None and km.plan is not None and dt == _lib.F32:
+        if a == _lib.ALGO_BX3 and dt == _lib.F32 and km is not None and km.plan is not None:
             # large same-map 3^3 map: neighbourhood-cache kernel (same products and per-row accumulation order)
             _lib.check(lib.lgs_conv_fwd3(_lib.ptr(feats), c_in, None, 0, n_in, _lib.ptr(wf), K, c_out, _lib.ptr(km.fwd_table),
                                          _lib.ptr(km.plan), n_out, 0, _lib.ptr(b32), _lib.ptr(out), None, _stream()))
@@ -937,7 +972,7 @@ def _conv_bwd_impl(m, feats, w_bwd, gout, need_gin, need_gw, need_gb):
         gin = torch.empty((n_in, c_in), dtype=feats.dtype, device=feats.device)
         layout, a = (m.tc_layout, algo) if m.bwd_tc else (_lib.W_KNC, _lib.ALGO_SIMT)
         with _Timed("dgrad", K, c_out, c_in, n_out, n_in, km, feats.dtype):
-            if a == _lib.ALGO_BX3 and km is not None and km.plan is not None and km.bwd_reverse and dt == _lib.F32:
+            if a == _lib.ALGO_BX3 and dt == _lib.F32 and km is not None and km.bwd_reverse and km.plan is not None:
                 _lib.check(lib.lgs_conv_fwd3(_lib.ptr(gout), c_out, None, 0, n_out, _lib.ptr(w_bwd), K, c_in, _lib.ptr(km.bwd_table),
                                              _lib.ptr(km.plan), n_in, 1, None, _lib.ptr(gin), None, _stream()))
             else:
