@@ -1220,12 +1220,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
         v[i] = (i < passes && o < r_end) ? (trow ? ldg_nc_ordered(trow + o) : int32_t(o)) : -1;
       }
     };
-    int32_t cur[8], nxt[8];
-    if (n_tiles > 0) load_rows(0, 0, cur);
+    // table entries are read TWO steps ahead: a load issued behind a stage's 24 cp.async per thread drains through the same
+    // LSU queue and came back only after the next stage had started (25 % of the producers' samples, profiles/r2_wgrad_L0_96_ncu.txt)
+    int32_t cur[8], nxt[8], nx2[8];
+    const int total_steps = n_tiles * g_count;
+    auto load_step = [&](int step, int32_t (&v)[8]) {
+      if (step < total_steps) load_rows(step / g_count, step % g_count, v);
+    };
+    load_step(0, cur);
+    load_step(1, nxt);
+    int step = 0;
     for (int t = 0; t < n_tiles; ++t) {
-      for (int g = 0; g < g_count; ++g) {
-        const bool last = (g + 1 == g_count) && (t + 1 == n_tiles);
-        if (!last) load_rows(g + 1 == g_count ? t + 1 : t, g + 1 == g_count ? 0 : g + 1, nxt);
+      for (int g = 0; g < g_count; ++g, ++step) {
+        load_step(step + 2, nx2);
         mbar_wait(aempty + s, ph ^ 1);
         uint32_t a_base = a_smem_base + uint32_t(s) * uint32_t(a_stage_bytes);
         int col = chunk * 16;
@@ -1245,7 +1252,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_gy, const WParams p) {
           ph ^= 1;
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+        for (int i = 0; i < 8; ++i) cur[i] = nxt[i], nxt[i] = nx2[i];
       }
     }
     // =================================== epilogue: TMEM -> red.add into dW ===================================
