@@ -26,6 +26,8 @@ int conv_fwd_bx3(const void* in, int c_in, const void* in2, int c_in2, const voi
 int bx3_tune(const char* key, int value);
 int weight_prep_bx3(const float* w, int K, int c_in, int c_out, void* fwd, void* bwd, cudaStream_t stream);
 int weight_prep_bx3_batch(const int64_t* desc, int n_layers, int64_t total_tiles, cudaStream_t stream);
+int conv_wgrad_stem(const void* in, int c_in, const void* gout, int64_t n_out, int c_out, const int32_t* table, int K, float* gw,
+                    int dtype, cudaStream_t stream);
 // neighbourhood-cache path (conv_nb.cu, nbplan.cu)
 int conv_nb_shape_ok(int c_in, int c_in2, int c_out, int K);
 int conv_fwd_nb(const void* in, int c_in, const void* in2, int c_in2, const void* w, int K, int c_out, const void* d_plan,
@@ -144,6 +146,9 @@ int lgs_conv_wgrad(const void* d_in, int64_t n_in, int32_t c_in, const void* d_g
     const int rc = conv_wgrad_tc(d_in, n_in, c_in, d_grad_out, n_out, c_out, d_table, K, d_grad_w, dtype, stream);
     if (rc != LGS_E_UNSUPPORTED) return rc;
   } else if (algo == LGS_ALGO_TC3 || algo == LGS_ALGO_BX3) {
+    // the stem (c_in 4, c_out 32, K 27): exact fp32 SIMT kernel, 4x faster than 128 MMA lanes for 4 channels
+    const int rs = conv_wgrad_stem(d_in, c_in, d_grad_out, n_out, c_out, d_table, K, d_grad_w, dtype, stream);
+    if (rs != LGS_E_UNSUPPORTED) return rs;
     // weight gradients: single-pass TF32 products with fp32 accumulation (sums over ~1e5 rows)
     const int rc = conv_wgrad_tc(d_in, n_in, c_in, d_grad_out, n_out, c_out, d_table, K, d_grad_w, dtype, stream);
     if (rc != LGS_E_UNSUPPORTED) return rc;

@@ -5,6 +5,8 @@
 // rows through the kernel-map table into shared memory and accumulate in registers; one store per output element.
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace lgs {
@@ -219,6 +221,76 @@ int conv_fwd_simt(const void* in, int64_t n_in, int c_in, const void* w, int w_l
   if (dtype == LGS_F32)
     return launch_conv_simt<float>(in, c_in, w, w_layout, K, c_out, table, n_out, reverse_k, bias, out, stream);
   return launch_conv_simt<__nv_bfloat16>(in, c_in, w, w_layout, K, c_out, table, n_out, reverse_k, bias, out, stream);
+}
+
+// ---- wgrad of the stem: c_in = 4 (3 colour channels + pad), c_out = 32, K = 27 (res16unet.py:38 conv0p1s1) ------------------
+// 149 K rows x 27 offsets x 4 x 32 = 0.5 GMAC of exact fp32 FMAs: the tensor-core wgrad spends 230 us on it (128 MMA lanes for
+// 4 input channels, one 16-byte cp.async per (row, offset)); here a block stages 64 output rows — their 27 neighbour rows of X
+// (one float4 each) and their dY rows — in shared memory with coalesced loads and thread (co, offset group) keeps its
+// 4 offsets x 4 channels of dW in registers over all of the block's tiles; one atomicAdd per dW element and block at the end.
+constexpr int WS_TILE = 64, WS_K = 27;
+__global__ void __launch_bounds__(256) wgrad_stem_kernel(const float4* __restrict__ x, const float* __restrict__ gy,
+                                                         const int32_t* __restrict__ table, int64_t n_out,
+                                                         float* __restrict__ gw /*[27][4][32]*/) {
+  __shared__ float4 xs[WS_K][WS_TILE];
+  __shared__ float dys[WS_TILE][32];
+  const int tid = threadIdx.x, co = tid & 31, kg = tid >> 5;      // offsets kg, kg + 8, kg + 16, kg + 24 (< 27)
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  const int64_t tiles = (n_out + WS_TILE - 1) / WS_TILE;
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int64_t o0 = t * WS_TILE;
+    __syncthreads();                                              // the previous tile's reads are done
+    for (int i = tid; i < WS_K * WS_TILE; i += 256) {
+      const int k = i / WS_TILE, r = i - k * WS_TILE;
+      const int64_t o = o0 + r;
+      const int32_t j = o < n_out ? __ldg(table + int64_t(k) * n_out + o) : -1;
+      xs[k][r] = j >= 0 ? __ldg(x + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = tid; i < WS_TILE * 32; i += 256) {
+      const int r = i >> 5;
+      dys[r][i & 31] = o0 + r < n_out ? __ldg(gy + (o0 + r) * 32 + (i & 31)) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < WS_TILE; ++r) {
+      const float d = dys[r][co];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int k = kg + 8 * a;
+        if (k < WS_K) {
+          const float4 v = xs[k][r];                              // same address for the whole warp: broadcast
+          acc[a][0] = fmaf(v.x, d, acc[a][0]);
+          acc[a][1] = fmaf(v.y, d, acc[a][1]);
+          acc[a][2] = fmaf(v.z, d, acc[a][2]);
+          acc[a][3] = fmaf(v.w, d, acc[a][3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int k = kg + 8 * a;
+    if (k < WS_K)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) atomicAdd(gw + (k * 4 + b) * 32 + co, acc[a][b]);
+  }
+}
+
+// 1 if conv_wgrad_stem takes this layer (fp32, K = 27, c_in = 4, c_out = 32, 16-byte aligned rows)
+int conv_wgrad_stem(const void* in, int c_in, const void* gout, int64_t n_out, int c_out, const int32_t* table, int K, float* gw,
+                    int dtype, cudaStream_t stream) {
+  if (dtype != LGS_F32 || K != WS_K || c_in != 4 || c_out != 32 || !table || (reinterpret_cast<uintptr_t>(in) & 15))
+    return LGS_E_UNSUPPORTED;
+  LGS_CUDA(cudaMemsetAsync(gw, 0, size_t(K) * c_in * c_out * sizeof(float), stream));
+  if (n_out == 0) return LGS_OK;
+  const int64_t tiles = cdiv(n_out, WS_TILE);
+  const unsigned grid = unsigned(std::min<int64_t>(tiles, 148 * 4));
+  LGS_LAUNCH(wgrad_stem_kernel, grid, 256, 0, stream, static_cast<const float4*>(in), static_cast<const float*>(gout), table, n_out, gw);
+  return LGS_OK;
 }
 
 int conv_wgrad_simt(const void* in, int c_in, const void* gout, int64_t n_out, int c_out, const int32_t* table, int K,

@@ -56,6 +56,10 @@ for sid, es in sorted(streams.items(), key=lambda kv: -len(kv[1])):
     small = [g for g in gaps if 0 <= g < 50]
     print(f"stream {sid}: {len(es)} kernels, {1e-3 * tot:.3f} ms of kernels; gaps to the next kernel of the same stream: "
           f"median {sorted(gaps)[len(gaps) // 2] if gaps else 0:.1f} us, sum of gaps < 50 us {1e-3 * sum(small):.3f} ms ({len(small)} gaps)", file=out)
+if len(sys.argv) > 2:
+    with open(sys.argv[2], "w") as tr:        # compact trace of the step: start us, duration us, stream, grid, kernel
+        for e in step:
+            tr.write(f"{e['ts'] - t0:10.1f} {e['dur']:8.1f} {e['args'].get('stream')} {e['args'].get('grid')} {e['name'].split('(')[0].replace('void ', '')[:60]}\n")
 agg = {}
 for e in step:
     n = e["name"].split("(")[0].replace("void ", "")
