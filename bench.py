@@ -319,6 +319,9 @@ def run_engine(args, rank, world, local_rank):
     _lib.load()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if os.environ.get("LGS_MAIN_PRIORITY", "0") != "0":
+        # experiment: training stream = a high-priority stream, so its (critical-path) kernels get SMs ahead of the wgrad side stream
+        torch.cuda.set_stream(torch.cuda.Stream(dev, priority=-1))
     # ONE nvidia-smi poller (rank 0 only: concurrent pollers slow the driver), started now — seconds before the first timed
     # region — because its NVML start-up stalls CUDA calls for a few hundred ms; it then polls every 200 ms through both
     # timed regions and each region reports the samples that fall inside it.

@@ -26,6 +26,8 @@ import ctypes
 import struct
 
 import numpy as np
+import os
+
 import torch
 
 from . import _lib
@@ -373,7 +375,8 @@ class NativeStep:
         self._desc_slot = self._ext_dynamic.pop("desc")
         self._desc_t = None
         self._scratch = torch.zeros(2 * 16384, dtype=torch.float64, device=dev)
-        self._side = torch.cuda.Stream(dev) if not self._dry else None
+        # LGS_SIDE_PRIORITY=1: wgrad side stream at high priority (experiment knob, profiles/r2_stream_priority.txt)
+        self._side = torch.cuda.Stream(dev, priority=-1 if os.environ.get("LGS_SIDE_PRIORITY", "0") != "0" else 0) if not self._dry else None
         ops = np.asarray(self._ops, dtype=np.int64)
         bufs = np.asarray(self._bufs, dtype=np.int64)
         self.n_ops = ops.shape[0]
