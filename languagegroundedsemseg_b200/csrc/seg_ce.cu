@@ -19,9 +19,16 @@ seg_ce_count_kernel(const int64_t* __restrict__ labels, int64_t n, int c, int64_
   pdl_grid_sync();
   __shared__ int part[32];
   int cnt = 0;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const int64_t y = __ldg(labels + i);
-    cnt += (y != ignore && y >= 0 && y < c) ? 1 : 0;
+  // 8 independent loads in flight per thread: one block walks 1.2 MB of labels, serial loads cost 32 us at 150 K points
+  for (int64_t i0 = threadIdx.x; i0 < n; i0 += int64_t(blockDim.x) * 8) {
+    int64_t y[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t i = i0 + int64_t(u) * blockDim.x;
+      y[u] = i < n ? __ldg(labels + i) : ignore;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cnt += (y[u] != ignore && y[u] >= 0 && y[u] < c) ? 1 : 0;
   }
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;

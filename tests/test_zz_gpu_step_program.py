@@ -50,7 +50,11 @@ def _check_against_exact(name, cand, facades, exact):
     n = len(e_c)
     med_f, worst_f = max(e[n // 2] for e in e_f), max(e[-1] for e in e_f)
     print(f"[{name}] vs exact fp32: facade median {med_f:.2e} worst {worst_f:.2e};  candidate median {e_c[n // 2]:.2e} worst {e_c[-1]:.2e}")
-    assert e_c[n // 2] < 2 * med_f + 1e-6 and e_c[-1] < 2 * worst_f + 1e-5, (e_c[n // 2], e_c[-1], med_f, worst_f)
+    # The noise is bimodal: identical runs of ONE driver land at a median of either ~4.4e-3 or ~9.8e-3 ('tc') depending on how a
+    # handful of arrival-order-dependent sums round (3 x 6 repetitions in profiles/r2_noise_gate_runs.txt: the facade itself
+    # measured 4.56e-3, 4.45e-3 and 9.79e-3).  Two facade samples can both fall into the low mode, so the gate also admits the
+    # high mode's level; a driver that issues a wrong, missing or misordered kernel is off by O(1), not by 1e-2.
+    assert e_c[n // 2] < max(2 * med_f, 3e-2) and e_c[-1] < max(2 * worst_f, 6e-2), (e_c[n // 2], e_c[-1], med_f, worst_f)
     a = facades[0]
     assert abs(a[0] - cand[0]) < 1e-4 * abs(a[0]), (a[0], cand[0])
     assert rel_err(cand[1], a[1]) < 1e-4
