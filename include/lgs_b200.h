@@ -189,6 +189,13 @@ int lgs_nbplan_geometry(int64_t n_out, int32_t K, int64_t* out);
 int lgs_conv_fwd3(const float* d_in, int32_t c_in, const float* d_in2, int32_t c_in2, int64_t n_in, const void* d_weight,
                   int32_t K, int32_t c_out, const int32_t* d_table, const void* d_plan, int64_t n_out, int32_t reverse_k,
                   const float* d_bias, float* d_out, double* d_bn_sums, void* stream);
+/* lgs_conv_fwd3 + d_addend: out = conv(in) (+ bias) + addend, addend fp32 [n_out, c_out] or NULL — the dgrad of a residual
+ * block's first convolution plus the gradient of the identity path (models/modules/resnet_block.py:41-57 backward) without a
+ * separate add pass.  Fused into the neighbourhood-cache kernel's epilogue; any other path runs lgs_conv_fwd2 + lgs_add in
+ * place.  d_bn_sums and d_addend exclude each other. */
+int lgs_conv_fwd4(const float* d_in, int32_t c_in, const float* d_in2, int32_t c_in2, int64_t n_in, const void* d_weight,
+                  int32_t K, int32_t c_out, const int32_t* d_table, const void* d_plan, int64_t n_out, int32_t reverse_k,
+                  const float* d_bias, const float* d_addend, float* d_out, double* d_bn_sums, void* stream);
 
 /* grad_w[k] = sum_o in[table[k][o], :]^T (outer) grad_out[o, :]   -> fp32 [K,c_in,c_out], overwritten. */
 int lgs_conv_wgrad(const void* d_in, int64_t n_in, int32_t c_in,
@@ -295,7 +302,7 @@ int lgs_colsum(const float* d_g, int64_t rows, int32_t c, float* d_out, void* st
  *   level_rows [n_levels] voxels per U-Net level of THIS batch;  d_arena: lgs_program_arena_bytes() bytes of scratch;
  *   d_bn_scratch: 2 x 16384 doubles, all zero before the first run (the program alternates the halves like the facade).
  * --------------------------------------------------------------------------------------------------------- */
-#define LGS_PROGRAM_OP_WORDS 16
+#define LGS_PROGRAM_OP_WORDS 18
 #define LGS_OP_WEIGHT_PREP 1
 #define LGS_OP_CONV 2
 #define LGS_OP_WGRAD 3

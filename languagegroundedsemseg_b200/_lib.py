@@ -34,6 +34,7 @@ SIGNATURES = {
     "lgs_conv_fwd": (C.c_int, [_p, _i64, _i32, _p, _i32, _i32, _i32, _p, _i64, _i32, _p, _p, _i32, _i32, _p]),
     "lgs_conv_fwd2": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _i32, _p, _i64, _i32, _p, _p, _p, _p]),
     "lgs_conv_fwd3": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _i32, _p, _p, _i64, _i32, _p, _p, _p, _p]),
+    "lgs_conv_fwd4": (C.c_int, [_p, _i32, _p, _i32, _i64, _p, _i32, _i32, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     "lgs_nbplan_supported": (C.c_int, [_i64, _i32]),
     "lgs_nbplan_bytes": (_i64, [_i64, _i32]),
     "lgs_nbplan_scratch_bytes": (_i64, [_i64]),

@@ -31,7 +31,7 @@ int conv_wgrad_stem(const void* in, int c_in, const void* gout, int64_t n_out, i
 // neighbourhood-cache path (conv_nb.cu, nbplan.cu)
 int conv_nb_shape_ok(int c_in, int c_in2, int c_out, int K);
 int conv_fwd_nb(const void* in, int c_in, const void* in2, int c_in2, const void* w, int K, int c_out, const void* d_plan,
-                int64_t n_out, int reverse_k, const float* bias, float* out, double* stats, cudaStream_t stream);
+                int64_t n_out, int reverse_k, const float* bias, const float* addend, float* out, double* stats, cudaStream_t stream);
 }  // namespace lgs
 
 using namespace lgs;
@@ -178,14 +178,28 @@ int lgs_conv_fwd2(const float* d_in, int32_t c_in, const float* d_in2, int32_t c
 int lgs_conv_fwd3(const float* d_in, int32_t c_in, const float* d_in2, int32_t c_in2, int64_t n_in, const void* d_weight,
                   int32_t K, int32_t c_out, const int32_t* d_table, const void* d_plan, int64_t n_out, int32_t reverse_k,
                   const float* d_bias, float* d_out, double* d_bn_sums, void* stream_) {
-  if (!d_plan || !lgs_nbplan_supported(n_out, K) || n_in != n_out || !conv_nb_shape_ok(c_in, c_in2, c_out, K))
-    return lgs_conv_fwd2(d_in, c_in, d_in2, c_in2, n_in, d_weight, K, c_out, d_table, n_out, reverse_k, d_bias, d_out, d_bn_sums, stream_);
-  LGS_TRACE("lgs_conv_fwd3 %p %d %p %d %lld %p %d %d %p %p %lld %d %p %p %p %p", (const void*)d_in, (int)c_in, (const void*)d_in2, (int)c_in2, (long long)n_in, (const void*)d_weight, (int)K, (int)c_out, (const void*)d_table, (const void*)d_plan, (long long)n_out, (int)reverse_k, (const void*)d_bias, (const void*)d_out, (const void*)d_bn_sums, (const void*)stream_);
-  if (!d_in || (c_in2 > 0 && !d_in2) || !d_weight || !d_out) return fail(LGS_E_INVALID, "lgs_conv_fwd3: null pointer");
-  const int rc = conv_fwd_nb(d_in, c_in, c_in2 > 0 ? d_in2 : nullptr, c_in2, d_weight, K, c_out, d_plan, n_out, reverse_k, d_bias,
+  return lgs_conv_fwd4(d_in, c_in, d_in2, c_in2, n_in, d_weight, K, c_out, d_table, d_plan, n_out, reverse_k, d_bias, nullptr, d_out,
+                       d_bn_sums, stream_);
+}
+
+int lgs_conv_fwd4(const float* d_in, int32_t c_in, const float* d_in2, int32_t c_in2, int64_t n_in, const void* d_weight,
+                  int32_t K, int32_t c_out, const int32_t* d_table, const void* d_plan, int64_t n_out, int32_t reverse_k,
+                  const float* d_bias, const float* d_addend, float* d_out, double* d_bn_sums, void* stream_) {
+  if (d_addend && d_bn_sums) return fail(LGS_E_INVALID, "lgs_conv_fwd4: BatchNorm sums are those of the convolution alone (no addend)");
+  if (!d_plan || !lgs_nbplan_supported(n_out, K) || n_in != n_out || !conv_nb_shape_ok(c_in, c_in2, c_out, K)) {
+    const int rc = lgs_conv_fwd2(d_in, c_in, d_in2, c_in2, n_in, d_weight, K, c_out, d_table, n_out, reverse_k, d_bias, d_out, d_bn_sums, stream_);
+    if (rc != LGS_OK || !d_addend) return rc;
+    return lgs_add(d_out, d_addend, d_out, n_out * int64_t(c_out), stream_);
+  }
+  LGS_TRACE("lgs_conv_fwd4 %p %d %p %d %lld %p %d %d %p %p %lld %d %p %p %p %p %p", (const void*)d_in, (int)c_in, (const void*)d_in2, (int)c_in2, (long long)n_in, (const void*)d_weight, (int)K, (int)c_out, (const void*)d_table, (const void*)d_plan, (long long)n_out, (int)reverse_k, (const void*)d_bias, (const void*)d_addend, (const void*)d_out, (const void*)d_bn_sums, (const void*)stream_);
+  if (!d_in || (c_in2 > 0 && !d_in2) || !d_weight || !d_out) return fail(LGS_E_INVALID, "lgs_conv_fwd4: null pointer");
+  const int rc = conv_fwd_nb(d_in, c_in, c_in2 > 0 ? d_in2 : nullptr, c_in2, d_weight, K, c_out, d_plan, n_out, reverse_k, d_bias, d_addend,
                              d_out, d_bn_sums, static_cast<cudaStream_t>(stream_));
-  if (rc == LGS_E_UNSUPPORTED)
-    return lgs_conv_fwd2(d_in, c_in, d_in2, c_in2, n_in, d_weight, K, c_out, d_table, n_out, reverse_k, d_bias, d_out, d_bn_sums, stream_);
+  if (rc == LGS_E_UNSUPPORTED) {
+    const int r2 = lgs_conv_fwd2(d_in, c_in, d_in2, c_in2, n_in, d_weight, K, c_out, d_table, n_out, reverse_k, d_bias, d_out, d_bn_sums, stream_);
+    if (r2 != LGS_OK || !d_addend) return r2;
+    return lgs_add(d_out, d_addend, d_out, n_out * int64_t(c_out), stream_);
+  }
   return rc;
 }
 

@@ -56,6 +56,7 @@ struct Params {
   int32_t reverse_k;
   int32_t kb_per_split, kb_splits, k_per_split;   // blockIdx.z = offset split * kb_splits + channel-block split (small maps)
   const float* bias;
+  const float* addend;       // [n_out][c_out] added to the result (dgrad + residual-path gradient), or NULL
   float* out;
   int32_t n_tile, b_stages, ta_stages, ta_col0, tmem_cols, b_stage_bytes;
   double* stats;
@@ -127,8 +128,8 @@ __device__ __forceinline__ void fill_cache(const uint8_t* in, const uint8_t* in2
 // Epilogue of one row warp, out of line so that its register needs (three 32-word arrays for the fused BatchNorm sums) do not
 // spill loop-invariant values of the main loops: TMEM accumulators -> (+ bias) -> output rows at their own positions.
 __device__ __noinline__ void epilogue_rows(uint32_t tmem_lane_base, int n_tile, int ncols, int c_out, int n0, const float* bias,
-                                           float* out, const int32_t* order_s, int rt, int r, bool want_stats, float* s_stats,
-                                           bool partial) {
+                                           const float* addend, float* out, const int32_t* order_s, int rt, int r, bool want_stats,
+                                           float* s_stats, bool partial) {
   const int lane = threadIdx.x & 31;
   for (int t = 0; t < TM; ++t) {
     const int32_t o = r < rt ? __ldg(order_s + t * rt + r) : -1;
@@ -140,6 +141,22 @@ __device__ __noinline__ void epilogue_rows(uint32_t tmem_lane_base, int n_tile, 
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj)
           if (c0 + jj < ncols) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __ldg(bias + n0 + c0 + jj));
+      }
+      if (addend && row_ok) {                       // out = conv + addend (this CTA is the one that adds it: blockIdx.z == 0)
+        const float* arow = addend + size_t(o) * c_out + n0 + c0;
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 4) {
+          if (c0 + jj + 3 < ncols) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(arow + jj));
+            v[jj] = __float_as_uint(__uint_as_float(v[jj]) + a.x);
+            v[jj + 1] = __float_as_uint(__uint_as_float(v[jj + 1]) + a.y);
+            v[jj + 2] = __float_as_uint(__uint_as_float(v[jj + 2]) + a.z);
+            v[jj + 3] = __float_as_uint(__uint_as_float(v[jj + 3]) + a.w);
+          } else {
+            for (int e = jj; e < jj + 4; ++e)
+              if (c0 + e < ncols) v[e] = __float_as_uint(__uint_as_float(v[e]) + __ldg(arow + e));
+          }
+        }
       }
       if (row_ok) {
         float* orow = out + size_t(o) * c_out + n0 + c0;
@@ -309,8 +326,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv_nb_kernel(const __grid_consta
     // =================================== epilogue ===================================
     mbar_wait(acc_bar, 0);
     tc_fence_after();
-    epilogue_rows(tmem_base + lane_addr, p.n_tile, min(p.n_tile, p.c_out - n0), p.c_out, n0, blockIdx.z == 0 ? p.bias : nullptr, p.out,
-                  p.order + s * p.RS, rt, r, p.stats != nullptr, s_stats, partial);
+    epilogue_rows(tmem_base + lane_addr, p.n_tile, min(p.n_tile, p.c_out - n0), p.c_out, n0, blockIdx.z == 0 ? p.bias : nullptr,
+                  blockIdx.z == 0 ? p.addend : nullptr, p.out, p.order + s * p.RS, rt, r, p.stats != nullptr, s_stats, partial);
     tc_fence_before();
   } else if (warp == 4 || warp == 6) {
     // =================================== MMA issuers: warp 4 <-> row tile 0, warp 6 <-> row tile 1 ================
@@ -416,17 +433,17 @@ int conv_bx3_shape_ok(int c_in, int c_out);
 int conv_nb_shape_ok(int c_in, int c_in2, int c_out, int K) {
   if (K != 27 || !conv_bx3_shape_ok(c_in, c_out)) return 0;
   if (c_in2 && (c_in % 32 != 0 || c_in2 % 4 != 0 || c_in2 < 4)) return 0;
-  if (c_out % 16 != 0 || c_out > 384) return 0;
+  if (c_out % 16 != 0 || c_out > 1024) return 0;      // 1024: the BatchNorm accumulator scratch holds 8 x 2 x 1024 doubles
   return 1;
 }
 
 // in2 / c_in2: optional second gather source as in conv_fwd_bx3.  d_plan: lgs_nbplan_build output for (n_out, K).
 int conv_fwd_nb(const void* in, int c_in, const void* in2, int c_in2, const void* w, int K, int c_out, const void* d_plan,
-                int64_t n_out, int reverse_k, const float* bias, float* out, double* stats, cudaStream_t stream) {
+                int64_t n_out, int reverse_k, const float* bias, const float* addend, float* out, double* stats, cudaStream_t stream) {
   using namespace nb;
   if (!conv_nb_shape_ok(c_in, in2 ? c_in2 : 0, c_out, K)) return LGS_E_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(in2) & 15) || (reinterpret_cast<uintptr_t>(w) & 15) ||
-      (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(d_plan) & 15))
+      (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(d_plan) & 15) || (reinterpret_cast<uintptr_t>(addend) & 15))
     return LGS_E_UNSUPPORTED;
   if (n_out == 0) return LGS_OK;
   EncodeTiledFn encode = get_encode();
@@ -457,6 +474,7 @@ int conv_fwd_nb(const void* in, int c_in, const void* in2, int c_in2, const void
   q.RS = g.RS, q.rt = g.rt, q.umax = g.umax;
   q.reverse_k = reverse_k;
   q.bias = bias;
+  q.addend = addend;
   q.out = out;
   q.stats = stats;
   // output channels per CTA: TM accumulators + >= 2 split-A stages within 256 TMEM columns (two CTAs share an SM's 512)

@@ -47,11 +47,12 @@ __global__ void __launch_bounds__(256) copy2d_v4_kernel(const float4* __restrict
   }
 }
 // out = a + b (float4 stream): gradient accumulation where two consumers meet (residual branches, skip connections)
-__global__ void __launch_bounds__(256) add_v4_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out,
+__global__ void __launch_bounds__(256) add_v4_kernel(const float4* a, const float4* __restrict__ b, float4* out,   // a may alias out
+
                                                      int64_t n4) {
   pdl_grid_sync();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
-    const float4 x = __ldg(a + i), y = __ldg(b + i);
+    const float4 x = a[i], y = __ldg(b + i);
     out[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
   }
 }
@@ -214,11 +215,11 @@ int lgs_program_run(lgs_program* p, int32_t op_begin, int32_t op_end, const int6
       case LGS_OP_WEIGHT_PREP:   // 1 desc, 2 n_layers, 3 total_tiles, 4 nsplit
         rc = lgs_weight_prep_batch(static_cast<const int64_t*>(P(o[1])), int32_t(o[2]), o[3], int32_t(o[4]), LGS_F32, stream);
         break;
-      case LGS_OP_CONV: {        // 1 in, 2 c_in, 3 in2, 4 c_in2, 5 lvl_in, 6 weight, 7 K, 8 c_out, 9 table, 10 lvl_out, 11 reverse_k, 12 bias, 13 out, 14 stats flag, 15 plan
+      case LGS_OP_CONV: {        // 1 in, 2 c_in, 3 in2, 4 c_in2, 5 lvl_in, 6 weight, 7 K, 8 c_out, 9 table, 10 lvl_out, 11 reverse_k, 12 bias, 13 out, 14 stats flag, 15 plan, 16 addend
         double* sums = (o[14] && rows_of(o[10]) >= kFuseStatsMinRows) ? half(p->bn_half) : nullptr;
-        rc = lgs_conv_fwd3(static_cast<const float*>(P(o[1])), int32_t(o[2]), static_cast<const float*>(P(o[3])), int32_t(o[4]), rows_of(o[5]),
+        rc = lgs_conv_fwd4(static_cast<const float*>(P(o[1])), int32_t(o[2]), static_cast<const float*>(P(o[3])), int32_t(o[4]), rows_of(o[5]),
                            P(o[6]), int32_t(o[7]), int32_t(o[8]), static_cast<const int32_t*>(P(o[9])), P(o[15]), rows_of(o[10]), int32_t(o[11]),
-                           static_cast<const float*>(P(o[12])), static_cast<float*>(P(o[13])), sums, stream);
+                           static_cast<const float*>(P(o[12])), static_cast<const float*>(P(o[16])), static_cast<float*>(P(o[13])), sums, stream);
         break;
       }
       case LGS_OP_WGRAD: {       // 1 in, 2 c_in, 3 lvl_in, 4 gout, 5 c_out, 6 lvl_out, 7 table, 8 K, 9 gw, 10 algo, 11 on side stream

@@ -34,7 +34,7 @@ from . import _lib
 from . import minkowski as E
 from .ddp import GradAllReducer
 
-OP_WORDS = 16
+OP_WORDS = 18
 OP_WEIGHT_PREP, OP_CONV, OP_WGRAD, OP_BN_FWD, OP_BN_BWD, OP_COPY2D, OP_ADD, OP_SEG_CE, OP_COLSUM, OP_JOIN = range(1, 11)
 
 
@@ -123,8 +123,11 @@ class NativeStep:
         row = [code] + [a.id if isinstance(a, _Buf) else (-1 if a is None else int(a)) for a in args]
         assert len(row) <= OP_WORDS
         row = row + [0] * (OP_WORDS - len(row))
-        if code == OP_CONV and len(args) < 15:
-            row[15] = -1                # no neighbourhood plan
+        if code == OP_CONV:
+            if len(args) < 15:
+                row[15] = -1            # no neighbourhood plan
+            if len(args) < 16:
+                row[16] = -1            # no addend
         self._ops.append(row)
 
     def _table(self, level_in, ks, stride, transpose, which):
@@ -190,7 +193,7 @@ class NativeStep:
                  self._plan(conv, level))
         return y, out_level
 
-    def _conv_bwd(self, conv, x, level, dy, need_gin=True):
+    def _conv_bwd(self, conv, x, level, dy, need_gin=True, addend=None):
         """wgrad (side stream next to dgrad, like the facade's _conv_bwd_impl) + dgrad; returns d x"""
         rec = self._conv_info(conv)
         out_level, t_fwd, t_bwd, rev = self._geometry(conv, level)
@@ -206,8 +209,9 @@ class NativeStep:
             return None
         self._need_bwd_operand(rec)
         gin = self._new(level, rec["c_pad"])
+        # addend: d x = dgrad + addend in the convolution's epilogue (lgs_conv_fwd4) instead of a separate add pass
         self._op(OP_CONV, dy, rec["c_out"], None, 0, out_level, rec["w_bwd"], rec["K"], rec["c_pad"], t_bwd, level, rev, None, gin, 0,
-                 self._plan(conv, level))
+                 self._plan(conv, level), addend)
         return gin
 
     def _cbr_fwd(self, conv, bn, x, level, relu, res=None):
@@ -223,7 +227,7 @@ class NativeStep:
         del bb
         return z, out_level, (conv, bn, x, level, y, z, stats, relu, res is not None)
 
-    def _cbr_bwd(self, node, dz, need_gin=True):
+    def _cbr_bwd(self, node, dz, need_gin=True, addend=None):
         conv, bn, x, level, y, z, stats, relu, has_res = node
         out_level = y.level
         c = y.c
@@ -232,7 +236,7 @@ class NativeStep:
         dres = self._new(out_level, c) if has_res else None
         self._op(OP_BN_BWD, y, z if relu else None, dz, out_level, c, self._param(bp["weight"]), stats, 1 if relu else 0, dy, dres,
                  self._grad(bp["weight"]), self._grad(bp["bias"]))
-        return self._conv_bwd(conv, x, level, dy, need_gin), dres
+        return self._conv_bwd(conv, x, level, dy, need_gin, addend), dres
 
     def _add(self, a, b):
         out = self._new(a.level, a.c)
@@ -261,8 +265,13 @@ class NativeStep:
         n1, nd, n2 = nodes
         dh, dres = self._cbr_bwd(n2, dy)
         dxr = self._cbr_bwd(nd, dres)[0] if nd is not None else dres
-        dx1 = self._cbr_bwd(n1, dh)[0]
-        return self._add(dx1, dxr)
+        # d x = dgrad of the block's first convolution + the gradient of the identity / downsample path.  LGS_FUSE_ADDEND=1 adds
+        # it in the convolution's epilogue (lgs_conv_fwd4): 23 fewer launches per step but 0.13 ms SLOWER — the epilogue's extra
+        # row loads lengthen the dgrad kernels, while the separate add pass hides behind the wgrad side stream
+        # (profiles/r2_addend_fusion.txt); off by default
+        if os.environ.get("LGS_FUSE_ADDEND", "0") == "0":
+            return self._add(self._cbr_bwd(n1, dh)[0], dxr)
+        return self._cbr_bwd(n1, dh, addend=dxr)[0]
 
     def _stage_fwd(self, stage, x, level):
         nodes = []

@@ -143,6 +143,7 @@ SHAPES = [
     (96, 0, 128, True),       # two output-channel slices (dgrad of a 128 -> 96 layer)
     (64, 0, 48, False),
     (20, 0, 16, False),       # ragged input width (one partial channel block)
+    (256, 32, 512, False),    # Res16UNet34D block8: six output-channel slices
 ]
 
 
@@ -219,6 +220,51 @@ def test_conv_nb_small_map_split(E, lib, n_target, c_in, c_out):
           f"unique rows max {km.plan_stats[1]}")
     assert not torch.isnan(outs["nb", 0]).any()
     assert e_tb < 3e-5 and e_ref < 1e-4
+
+
+@pytest.mark.parametrize("n_target,c", [(30000, 96), (2200, 256), (450, 128)])
+def test_conv_fwd4_addend(E, lib, n_target, c):
+    """lgs_conv_fwd4: out = conv + addend in the epilogue (large map: plain stores; small maps: the split whose blockIdx.z
+    is 0 adds it) equals lgs_conv_fwd3 followed by an add; with a NULL plan the entry runs the table-driven kernel + lgs_add"""
+    from languagegroundedsemseg_b200 import _lib
+    coords, km = _scene_map(E, lib, n_target, 13, min_rows=0)
+    assert km.plan is not None, km.plan_stats
+    n, K = km.n_out, 27
+    torch.manual_seed(n_target)
+    x = torch.randn(n, c, device="cuda")
+    w = torch.randn(K, c, c, device="cuda") / np.sqrt(K * c)
+    add = torch.randn(n, c, device="cuda")
+    w_fwd, _ = _operands(lib, w)
+    ref = _conv3(lib, x, None, w_fwd, K, c, km, km.plan, 1, None, None) + add
+    for plan in (km.plan, None):
+        out = torch.full((n, c), float("nan"), device="cuda")
+        _lib.check(lib.lgs_conv_fwd4(_lib.ptr(x), c, None, 0, n, _lib.ptr(w_fwd), K, c, _lib.ptr(km.fwd_table), _lib.ptr(plan), n, 1,
+                                     None, _lib.ptr(add), _lib.ptr(out), None, _stream()))
+        assert rel_err(out, ref) < 3e-5, (plan is None, rel_err(out, ref))
+
+
+def test_plan_overflow_falls_back_to_table_driven(E, lib):
+    """a cache too small for a supertile's unique rows (lgs_tune nb_umax) makes the builder flag the plan; the facade then
+    keeps the table-driven kernel — same result, no error"""
+    from languagegroundedsemseg_b200 import scenes
+    assert lib.lgs_tune(b"nb_umax", 64) == 0
+    try:
+        coords, _, _ = scenes.synthetic_voxel_scene(seed=4, target_voxels=9000)
+        c = torch.from_numpy(coords).cuda()
+        st = E.SparseTensor(torch.zeros(c.shape[0], 4, device="cuda"), c)
+        km = st.coordinate_manager.kernel_map(st.coordinate_map_key, st.coordinate_map_key, [3] * 3, [1] * 3)
+        assert km.plan is None and km.plan_stats[0] == 1 and km.plan_stats[1] > 64, km.plan_stats
+        torch.manual_seed(0)
+        x = torch.randn(c.shape[0], 32, device="cuda")
+        w = torch.randn(27, 32, 32, device="cuda") / 30
+        E.set_conv_algo("bx3")
+        y = E.sparse_conv(x, w, None, km)
+        E.set_conv_algo("simt")
+        y_ref = E.sparse_conv(x, w, None, km)
+        E.set_conv_algo("bx3")
+        assert rel_err(y, y_ref) < 1e-4
+    finally:
+        lib.lgs_tune(b"nb_umax", 0)
 
 
 def test_facade_layers_with_plan_vs_oracle(E, lib):
