@@ -544,8 +544,14 @@ def run_engine(args, rank, world, local_rank):
 
     # ---- reduce over ranks ---------------------------------------------------------------------------------
     tot_vox = n_vox
+    per_rank = None
     if world > 1:
         import torch.distributed as dist
+        mine = torch.tensor([n_vox, ms / args.steps, ms_e2e / args.steps], device=dev, dtype=torch.float64)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)                    # each rank's scene size and own step time: slowest-rank gating made visible
+        per_rank = {"voxels": [int(e[0].item()) for e in every], "ms_per_step": [round(e[1].item(), 3) for e in every],
+                    "e2e_ms_per_step": [round(e[2].item(), 3) for e in every]}
         t = torch.tensor([ms, ms_e2e, kmap_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e, kmap_ms = t.tolist()
@@ -567,7 +573,8 @@ def run_engine(args, rank, world, local_rank):
     res = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "warmup_done": warm_done, "ms_per_step": round(ms / args.steps, 3),
-        "step_ms": {"median": round(statistics.median(per_step), 3), "min": round(min(per_step), 3), "max": round(max(per_step), 3)}, "higher_is_better": True, "scaling": "weak",
+        "step_ms": {"median": round(statistics.median(per_step), 3), "min": round(min(per_step), 3), "max": round(max(per_step), 3)},
+        **({"per_rank": per_rank} if per_rank else {}), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.dtype == "f32" else "bf16", "data": "synthetic",
         "config": {"workload": workload_string(args.model, n_vox, args.voxel_size, args.voxels, args.config), "voxels_per_gpu": n_vox, "algo": args.algo,
                    "binding": _lib.binding() + " (Python -> C ABI)",

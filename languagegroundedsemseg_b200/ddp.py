@@ -89,6 +89,23 @@ class GradAllReducer:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(self.bucket_of[i])))
         self._arm()
 
+    def set_bounds(self, bounds):
+        """re-cut the buckets at the given parameter indices (ascending, first 0, last len(params)).  The native step driver
+        aligns them with the points of backward at which whole groups of layers have their gradients, so that a bucket can go
+        out the moment its group is done.  Not with per-parameter hooks (overlap=True: they captured the old bucket ids)."""
+        bounds = sorted(set(int(b) for b in bounds))
+        if self._hooks:
+            raise RuntimeError("set_bounds: this reducer launches its buckets from gradient hooks")
+        if bounds[0] != 0 or bounds[-1] != len(self.params):
+            raise ValueError("set_bounds: bounds must start at 0 and end at len(params)")
+        self.bounds = bounds
+        self.bucket_of = []
+        for b in range(len(bounds) - 1):
+            self.bucket_of += [b] * (bounds[b + 1] - bounds[b])
+        self._pending = [0] * (len(bounds) - 1)
+        self._fired = [False] * (len(bounds) - 1)
+        self._arm()
+
     # -- gradient views ---------------------------------------------------------------------------------------------
     def attach(self):
         """(re)point every parameter's .grad at its slice of the flat buffer"""

@@ -371,6 +371,7 @@ class NativeStep:
                 d = self._add(d, dskip[i + 1])
             d = self._stage_bwd(nb, d)
             d = self._cbr_bwd(nd, d)[0]
+            self.marks[f"encoder_done_{i}"] = len(self._ops)  # gradients of encoder stage i (and of everything after it) are complete
         d = self._add(d, dskip[0])
         self._cbr_bwd(n0, d, need_gin=False)
         self._op(OP_JOIN)
@@ -400,6 +401,15 @@ class NativeStep:
         self._sig = None
         ids = {id(p): i for i, p in enumerate(self.reducer.params)}
         self._enc_last = max(ids[id(p)] for p in self.net.block4.parameters())
+        # all-reduce buckets cut where backward completes whole groups of layers: [decoder + classifier] after the decoder,
+        # [stage 4: conv4p8s2 .. block4 = 56 % of the parameters] and [stage 3] right after their backward, the small rest
+        # (stem, stages 1-2) at the end — instead of three equal-byte buckets of which two could only go out after backward
+        self._stage_first = {}
+        for i, names in enumerate(self.ENC):
+            ps = [p for nm in names for p in getattr(self.net, nm).parameters()]
+            self._stage_first[i] = min(ids[id(p)] for p in ps)
+        if self.reducer.world > 1 and not self.reducer._hooks:
+            self.reducer.set_bounds([0, self._stage_first[2], self._stage_first[3], self._enc_last + 1, len(self.reducer.params)])
         written = set()
         for r in self._layers:
             written.add(id(r["mod"]._parameters["kernel"]))
@@ -512,13 +522,17 @@ class NativeStep:
             loss = loss.detach()
             begin = fwd_end
         if red.world > 1:
-            mid = self.marks["decoder_done"]
-            self.run_range(begin, mid)
-            # buckets that hold only decoder / classifier parameters are complete: send them while the encoder's backward runs
-            for b in range(len(red._pending)):
-                if red.bounds[b] > self._enc_last:
-                    red.reduce_bucket(b)
-            self.run_range(mid, self.n_ops)
+            # a bucket goes out as soon as every parameter in it has its gradient: after the decoder, after encoder stage 4,
+            # after stage 3 (run_range joins the wgrad side stream at the end of each range); the rest with red.wait()
+            pos = begin
+            for mark, first in (("decoder_done", self._enc_last + 1), ("encoder_done_3", self._stage_first[3]),
+                                ("encoder_done_2", self._stage_first[2])):
+                self.run_range(pos, self.marks[mark])
+                pos = self.marks[mark]
+                for b in range(len(red._pending)):
+                    if red.bounds[b] >= first:
+                        red.reduce_bucket(b)
+            self.run_range(pos, self.n_ops)
             red.wait()
         else:
             self.run_range(begin, self.n_ops)

@@ -42,12 +42,23 @@ def _worker(rank, world, port, out_dir):
     if os.environ.get("LGS_TEST_USE_DDP"):
         model = ddp.wrap_ddp(net)                       # stock DistributedDataParallel
         reducer = None
+    elif os.environ.get("LGS_TEST_STAGED"):
+        # the native step driver's protocol: no hooks, buckets re-cut at layer-group boundaries, sent group by group
+        model, reducer = net, ddp.GradAllReducer(net.parameters(), overlap=False)
+        n = len(reducer.params)
+        reducer.set_bounds([0, n // 5, n // 2, n - 7, n])
     else:
         model, reducer = net, ddp.GradAllReducer(net.parameters())   # bench.py's path: one flat all-reduce
     out, _ = model(me_cpu.SparseTensor(torch.from_numpy(feats), torch.from_numpy(coords)))
     loss = torch.nn.functional.cross_entropy(out.F, torch.from_numpy(labels), ignore_index=-1)
     loss.backward()
-    if reducer is not None:
+    if reducer is not None and os.environ.get("LGS_TEST_STAGED"):
+        for first in (n - 7, n // 2):                   # "decoder done", "stage 4 done": buckets at or above `first` go out
+            for b in range(len(reducer._pending)):
+                if reducer.bounds[b] >= first:
+                    reducer.reduce_bucket(b)
+        reducer.wait()                                  # the rest
+    elif reducer is not None:
         reducer()
     torch.save({k: p.grad.clone() for k, p in net.named_parameters()}, os.path.join(out_dir, f"g{rank}.pt"))
     n = torch.tensor([coords.shape[0]], dtype=torch.float64)
@@ -57,12 +68,14 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("use_ddp", [False, True])
+@pytest.mark.parametrize("use_ddp", [False, True, "staged"])
 def test_ddp_gloo_two_ranks(tmp_path, use_ddp, monkeypatch):
-    if use_ddp:
+    monkeypatch.delenv("LGS_TEST_USE_DDP", raising=False)
+    monkeypatch.delenv("LGS_TEST_STAGED", raising=False)
+    if use_ddp == "staged":
+        monkeypatch.setenv("LGS_TEST_STAGED", "1")
+    elif use_ddp:
         monkeypatch.setenv("LGS_TEST_USE_DDP", "1")
-    else:
-        monkeypatch.delenv("LGS_TEST_USE_DDP", raising=False)
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
