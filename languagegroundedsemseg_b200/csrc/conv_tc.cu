@@ -1451,7 +1451,11 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
   LGS_CUDA(cudaMemsetAsync(gw, 0, size_t(K) * c_in * c_out * sizeof(float), stream));
   if (n_out == 0) return LGS_OK;
 
-  int64_t chunks = (148 * 2) / (groups * n_splits * m_slices);   // <= two CTAs' worth of work per SM, one resident at a time (TMEM)
+  // LGS_WGRAD_WAVES (default 4): CTAs' worth of work per SM; more = shorter CTAs (finer interleaving with the training stream's
+  // kernels, which cannot share an SM with a 214 KB wgrad CTA) but more red.add traffic.  Step time 10.86-10.93 ms at 2,
+  // 10.77 at 3 / 4 / 8 on one box (gpurun_out/r2an)
+  static const int wg_waves = getenv("LGS_WGRAD_WAVES") ? std::max(1, atoi(getenv("LGS_WGRAD_WAVES"))) : 4;
+  int64_t chunks = (148 * wg_waves) / (groups * n_splits * m_slices);   // one CTA resident per SM at a time (TMEM)
   const int64_t max_chunks = cdiv(n_out, int64_t(R) * 4);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
@@ -1470,7 +1474,7 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
     int64_t rows = 0, act = 0;
     double best = cost_of(chunks, rows, act);
     int64_t best_rows = p.rows_per_chunk, best_chunks = chunks;
-    const int64_t c_hi = std::min<int64_t>(max_chunks, cdiv(148 * 4, per));   // chunks stay >= 4 tiles tall
+    const int64_t c_hi = std::min<int64_t>(max_chunks, cdiv(148 * 2 * wg_waves, per));   // chunks stay >= 4 tiles tall
     for (int64_t c = 1; c <= c_hi; ++c) {
       const double cost = cost_of(c, rows, act);
       if (cost < best * 0.97) best = cost, best_rows = rows, best_chunks = act;
