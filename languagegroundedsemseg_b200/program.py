@@ -77,6 +77,12 @@ class NativeStep:
         self._ops, self._bufs = [], []
         self._ext_static, self._ext_dynamic, self._keep, self._ext_cache = [], {}, [], {}    # [(slot, getter)], name -> slot, ...
         self._n_ext = 0
+        # The four big level-0 decoder wgrads (block8: 1.4 ms of full-GPU work) are issued after the decoder's backward instead
+        # of next to their dgrads: there they compete with the level-0 dgrads for every SM, later they run under the
+        # latency-bound coarse encoder stages.  10.74 -> 10.63 ms on one box (profiles/r2_wgrad_deferral.txt; deferring level 1
+        # as well, or spreading them over the encoder stages, is slower).  LGS_DEFER_WGRAD=0 switches it off.
+        self._defer_wgrad = os.environ.get("LGS_DEFER_WGRAD", "1") != "0"
+        self._deferred = []
         self._tables = {}             # (level_in, ks, stride, transpose, 'fwd'|'bwd') -> buffer
         self._plans = {}              # level -> buffer (neighbourhood plan of the level's 3^3 same-map kernel map)
         self._layers = []             # (conv module, weight source tensor, K, c_in_padded, c_out, fwd operand, bwd operand)
@@ -204,7 +210,11 @@ class NativeStep:
             self._op(OP_COPY2D, gw, rec["c_pad"] * rec["c_out"], 0, rec["gw"], rec["c_in"] * rec["c_out"], 0, -1, rec["K"],
                      rec["c_in"] * rec["c_out"])
         else:
-            self._op(OP_WGRAD, x, rec["c_pad"], level, dy, rec["c_out"], out_level, t_fwd, rec["K"], rec["gw"], _lib.ALGO_BX3, side)
+            args = (OP_WGRAD, x, rec["c_pad"], level, dy, rec["c_out"], out_level, t_fwd, rec["K"], rec["gw"], _lib.ALGO_BX3, side)
+            if self._defer_wgrad and side and level == 0 and rec["K"] == 27 and rec["c_pad"] >= 64 and "decoder_done" not in self.marks:
+                self._deferred.append(args)
+            else:
+                self._op(*args)
         if not need_gin:
             return None
         self._need_bwd_operand(rec)
@@ -365,6 +375,8 @@ class NativeStep:
             d = self._cbr_bwd(nt, du)[0]
         self._op(OP_JOIN)
         self.marks["decoder_done"] = len(self._ops)          # every decoder / classifier gradient is complete here
+        for args in self._deferred:                           # ... except the deferred level-0 wgrads, issued here
+            self._op(*args)
         for i in (3, 2, 1, 0):
             nd, nb = enc[i]
             if i < 3:
@@ -525,8 +537,10 @@ class NativeStep:
             # a bucket goes out as soon as every parameter in it has its gradient: after the decoder, after encoder stage 4,
             # after stage 3 (run_range joins the wgrad side stream at the end of each range); the rest with red.wait()
             pos = begin
-            for mark, first in (("decoder_done", self._enc_last + 1), ("encoder_done_3", self._stage_first[3]),
-                                ("encoder_done_2", self._stage_first[2])):
+            cps = [("decoder_done", self._enc_last + 1), ("encoder_done_3", self._stage_first[3]), ("encoder_done_2", self._stage_first[2])]
+            if self._deferred:          # the decoder's gradients are complete only after the deferred wgrads: first send at stage 4
+                cps = cps[1:]
+            for mark, first in cps:
                 self.run_range(pos, self.marks[mark])
                 pos = self.marks[mark]
                 for b in range(len(red._pending)):
