@@ -322,6 +322,11 @@ int64_t lgs_program_arena_bytes(const lgs_program* p, const int64_t* level_rows)
 void lgs_program_reset(lgs_program* p);
 int lgs_program_run(lgs_program* p, int32_t op_begin, int32_t op_end, const int64_t* level_rows, void* const* ext,
                     void* d_arena, int64_t arena_bytes, void* d_bn_scratch, void* stream, void* side_stream);
+/* lgs_program_run with flags: LGS_RUN_NO_JOIN (1) = leave the side stream unjoined when the range ends (the caller makes its
+ * collective wait on the side stream itself and runs the last range with flags 0, which joins). */
+#define LGS_RUN_NO_JOIN 1
+int lgs_program_run2(lgs_program* p, int32_t op_begin, int32_t op_end, const int64_t* level_rows, void* const* ext,
+                    void* d_arena, int64_t arena_bytes, void* d_bn_scratch, void* stream, void* side_stream, int32_t flags);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,7 @@ SIGNATURES = {
     "lgs_program_arena_bytes": (_i64, [_p, _p]),
     "lgs_program_reset": (None, [_p]),
     "lgs_program_run": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i64, _p, _p, _p]),
+    "lgs_program_run2": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i64, _p, _p, _p, _i32]),
     "lgs_bn_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "lgs_seg_ce_supported": (C.c_int, [_i32]),
     "lgs_seg_ce": (C.c_int, [_p, _i64, _i32, _p, _i64, _p, _p, _p, _p]),

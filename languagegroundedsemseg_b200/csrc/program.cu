@@ -179,6 +179,11 @@ void lgs_program_reset(lgs_program* p) {
 
 int lgs_program_run(lgs_program* p, int32_t op_begin, int32_t op_end, const int64_t* level_rows, void* const* ext,
                     void* d_arena, int64_t arena_bytes, void* d_bn_scratch, void* stream_, void* side_stream_) {
+  return lgs_program_run2(p, op_begin, op_end, level_rows, ext, d_arena, arena_bytes, d_bn_scratch, stream_, side_stream_, 0);
+}
+
+int lgs_program_run2(lgs_program* p, int32_t op_begin, int32_t op_end, const int64_t* level_rows, void* const* ext,
+                     void* d_arena, int64_t arena_bytes, void* d_bn_scratch, void* stream_, void* side_stream_, int32_t flags) {
   if (!p || !level_rows || !ext || op_begin < 0 || op_end > p->n_ops || op_begin > op_end)
     return fail(LGS_E_INVALID, "lgs_program_run: bad arguments");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_), side = static_cast<cudaStream_t>(side_stream_);
@@ -281,7 +286,7 @@ int lgs_program_run(lgs_program* p, int32_t op_begin, int32_t op_end, const int6
         rc = fail(LGS_E_INVALID, "lgs_program_run: unknown op %lld at %d", (long long)o[0], i);
     }
   }
-  if (forked && !tracing) {     // never leave side-stream work unjoined behind a returning call
+  if (forked && !tracing && !(flags & LGS_RUN_NO_JOIN)) {     // never leave side-stream work unjoined behind a returning call
     cudaEventRecord(p->ev_join, side);
     cudaStreamWaitEvent(stream, p->ev_join, 0);
   }

@@ -497,11 +497,13 @@ class NativeStep:
             self._arena = torch.empty(int(need * 1.1) + 4096, dtype=torch.uint8, device=self.device)
         return keep
 
-    def run_range(self, begin, end):
-        rc = self.lib.lgs_program_run(self._handle, begin, end, ctypes.addressof(self._rows_arr), ctypes.addressof(self._ext_arr),
-                                      self._arena.data_ptr(), self._arena.numel(), self._scratch.data_ptr(),
-                                      0 if self._dry else torch._C._cuda_getCurrentRawStream(self.device.index),
-                                      0 if self._dry else self._side.cuda_stream)
+    def run_range(self, begin, end, join=True):
+        """ops [begin, end); join=False leaves the wgrad side stream unjoined at the end of the range (the caller's collective
+        waits on the side stream instead, so the training stream never stalls at a bucket boundary)"""
+        rc = self.lib.lgs_program_run2(self._handle, begin, end, ctypes.addressof(self._rows_arr), ctypes.addressof(self._ext_arr),
+                                       self._arena.data_ptr(), self._arena.numel(), self._scratch.data_ptr(),
+                                       0 if self._dry else torch._C._cuda_getCurrentRawStream(self.device.index),
+                                       0 if self._dry else self._side.cuda_stream, 0 if join else 1)
         if rc != _lib.OK:
             self._scratch.zero_()
             self.lib.lgs_program_reset(self._handle)
@@ -540,12 +542,18 @@ class NativeStep:
             cps = [("decoder_done", self._enc_last + 1), ("encoder_done_3", self._stage_first[3]), ("encoder_done_2", self._stage_first[2])]
             if self._deferred:          # the decoder's gradients are complete only after the deferred wgrads: first send at stage 4
                 cps = cps[1:]
+            main = torch.cuda.current_stream(self.device)
             for mark, first in cps:
-                self.run_range(pos, self.marks[mark])
+                self.run_range(pos, self.marks[mark], join=False)
                 pos = self.marks[mark]
-                for b in range(len(red._pending)):
-                    if red.bounds[b] >= first:
-                        red.reduce_bucket(b)
+                # the collective must see the wgrads (side stream) AND the BatchNorm / bias gradients (training stream) issued so
+                # far: the side stream waits for the training stream's position, NCCL's stream for the side stream — the training
+                # stream itself waits for nothing
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    for b in range(len(red._pending)):
+                        if red.bounds[b] >= first:
+                            red.reduce_bucket(b)
             self.run_range(pos, self.n_ops)
             red.wait()
         else:
