@@ -64,6 +64,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.numAttrs = g_pdl.load(std::memory_order_relaxed) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
+// zero-fill as a KERNEL (float4 stores; bytes a multiple of 16, 16-byte aligned): a cudaMemsetAsync node between two kernels
+// breaks their programmatic dependency, so the kernel behind it pays the whole launch + drain gap
+int zero_fill_async(void* p, size_t bytes, cudaStream_t stream);
 #define LGS_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                                      \
   do {                                                                                              \
     LGS_CUDA(::lgs::launch_pdl(kernel, dim3(grid), dim3(block), size_t(smem), (stream), __VA_ARGS__)); \

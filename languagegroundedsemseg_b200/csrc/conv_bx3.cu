@@ -637,7 +637,10 @@ int conv_fwd_bx3(const void* in, int c_in, const void* in2, int c_in2, const voi
   q.b_stages = sb;
   const size_t smem = size_t(sa) * A_BYTES + size_t(sb) * q.b_stage_bytes + fixed;
 
-  if (q.k_splits > 1) LGS_CUDA(cudaMemsetAsync(out, 0, size_t(n_out) * c_out * sizeof(float), stream));
+  if (q.k_splits > 1) {
+    const int rz = zero_fill_async(out, size_t(n_out) * c_out * sizeof(float), stream);
+    if (rz != LGS_OK) return rz;
+  }
 
   // tensor map over the BX3 operand viewed as bf16 [K * c_out rows][num_kb * 64], box {64 (= 128 B), n_tile rows}
   CUtensorMap tmap;

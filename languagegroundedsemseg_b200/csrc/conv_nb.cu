@@ -523,7 +523,10 @@ int conv_fwd_nb(const void* in, int c_in, const void* in2, int c_in2, const void
   q.k_per_split = (K + k_splits - 1) / k_splits;
   k_splits = (K + q.k_per_split - 1) / q.k_per_split;
   const unsigned gz = unsigned(q.kb_splits * k_splits);
-  if (gz > 1) LGS_CUDA(cudaMemsetAsync(out, 0, size_t(n_out) * c_out * sizeof(float), stream));
+  if (gz > 1) {
+    const int rz = zero_fill_async(out, size_t(n_out) * c_out * sizeof(float), stream);
+    if (rz != LGS_OK) return rz;
+  }
 
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {cuuint64_t(q.num_kb) * 64, cuuint64_t(K) * cuuint64_t(c_out)};

@@ -285,7 +285,10 @@ int conv_wgrad_stem(const void* in, int c_in, const void* gout, int64_t n_out, i
                     int dtype, cudaStream_t stream) {
   if (dtype != LGS_F32 || K != WS_K || c_in != 4 || c_out != 32 || !table || (reinterpret_cast<uintptr_t>(in) & 15))
     return LGS_E_UNSUPPORTED;
-  LGS_CUDA(cudaMemsetAsync(gw, 0, size_t(K) * c_in * c_out * sizeof(float), stream));
+  {
+    const int rz = zero_fill_async(gw, size_t(K) * c_in * c_out * sizeof(float), stream);
+    if (rz != LGS_OK) return rz;
+  }
   if (n_out == 0) return LGS_OK;
   const int64_t tiles = cdiv(n_out, WS_TILE);
   const unsigned grid = unsigned(std::min<int64_t>(tiles, 148 * 4));

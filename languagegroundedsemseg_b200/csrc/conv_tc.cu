@@ -1448,7 +1448,10 @@ int conv_wgrad_tc(const void* in, int64_t n_in, int c_in, const void* gout, int6
   while (cols < G * p.MC * p.n_cols) cols <<= 1;
   p.tmem_cols = cols;
 
-  LGS_CUDA(cudaMemsetAsync(gw, 0, size_t(K) * c_in * c_out * sizeof(float), stream));
+  {
+    const int rz = zero_fill_async(gw, size_t(K) * c_in * c_out * sizeof(float), stream);
+    if (rz != LGS_OK) return rz;
+  }
   if (n_out == 0) return LGS_OK;
 
   // LGS_WGRAD_WAVES (default 4): CTAs' worth of work per SM; more = shorter CTAs (finer interleaving with the training stream's

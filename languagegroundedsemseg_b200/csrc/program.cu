@@ -18,6 +18,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lgs {
@@ -47,6 +49,11 @@ __global__ void __launch_bounds__(256) copy2d_v4_kernel(const float4* __restrict
   }
 }
 // out = a + b (float4 stream): gradient accumulation where two consumers meet (residual branches, skip connections)
+__global__ void __launch_bounds__(256) zero_v4_kernel(float4* __restrict__ p, int64_t n4) {
+  pdl_grid_sync();
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x)
+    p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
 __global__ void __launch_bounds__(256) add_v4_kernel(const float4* a, const float4* __restrict__ b, float4* out,   // a may alias out
 
                                                      int64_t n4) {
@@ -77,6 +84,21 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g
 }  // namespace lgs
 
 using namespace lgs;
+
+namespace lgs {
+int zero_fill_async(void* p, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return LGS_OK;
+  static const bool use_memset = getenv("LGS_ZERO_MEMSET") != nullptr;      // A/B knob
+  if (use_memset || (bytes & 15) || (reinterpret_cast<uintptr_t>(p) & 15) || !g_pdl.load(std::memory_order_relaxed)) {
+    LGS_CUDA(cudaMemsetAsync(p, 0, bytes, stream));
+    return LGS_OK;
+  }
+  const int64_t n4 = int64_t(bytes >> 4);
+  const unsigned blocks = unsigned(std::min<int64_t>(cdiv(n4, 256 * 2), 148 * 4));
+  LGS_LAUNCH_PDL(zero_v4_kernel, std::max(1u, blocks), 256, 0, stream, static_cast<float4*>(p), n4);
+  return LGS_OK;
+}
+}  // namespace lgs
 
 extern "C" {
 
@@ -115,7 +137,10 @@ int lgs_colsum(const float* d_g, int64_t rows, int32_t c, float* d_out, void* st
   LGS_TRACE("lgs_colsum %p %lld %d %p %p", (const void*)d_g, (long long)rows, (int)c, (const void*)d_out, (const void*)stream_);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (rows < 0 || c < 1 || !d_out) return fail(LGS_E_INVALID, "lgs_colsum: bad arguments");
-  LGS_CUDA(cudaMemsetAsync(d_out, 0, size_t(c) * sizeof(float), stream));
+  {
+    const int rz = zero_fill_async(d_out, size_t(c) * sizeof(float), stream);
+    if (rz != LGS_OK) return rz;
+  }
   if (rows == 0) return LGS_OK;
   const dim3 grid{unsigned((c + 31) / 32), unsigned(std::min<int64_t>(cdiv(rows, 8 * 16), 148 * 4)), 1u}, block{32u, 8u, 1u};
   LGS_LAUNCH_PDL(colsum_kernel, grid, block, 0, stream, d_g, rows, c, d_out);
