@@ -7,6 +7,8 @@
 //   launch 2 (warp per row) loss_i = logsumexp(x_i) - x_i[y_i];  dlogits_i = (softmax(x_i) - onehot(y_i)) / n_valid
 //                           block partial sums -> one fp64 atomic; the last block to finish writes loss = sum / n_valid
 // Labels outside [0, C) other than `ignore` are an error in torch (device assert); here they are treated as ignored.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace lgs {
@@ -48,11 +50,11 @@ seg_ce_kernel(const float* __restrict__ logits, int64_t n, int c, const int64_t*
   pdl_grid_sync();
   __shared__ float wsum[SCE_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t row = int64_t(blockIdx.x) * (SCE_THREADS / 32) + warp;
   const int c4 = c >> 2;
   const float inv_valid = float(1.0 / ws[1]);      // written by the count kernel (stream order)
   float my_loss = 0.f;
-  if (row < n) {
+  // persistent grid: a warp walks rows with the grid's stride (one loss atomic per block instead of one per 8 rows)
+  for (int64_t row = int64_t(blockIdx.x) * (SCE_THREADS / 32) + warp; row < n; row += int64_t(gridDim.x) * (SCE_THREADS / 32)) {
     const int64_t y = __ldg(labels + row);
     const bool valid = y != ignore && y >= 0 && y < c;
     float4* drow = dlogits ? reinterpret_cast<float4*>(dlogits + row * c) : nullptr;
@@ -88,7 +90,7 @@ seg_ce_kernel(const float* __restrict__ logits, int64_t n, int c, const int64_t*
         s += __shfl_xor_sync(0xffffffffu, s, o);
         xy += __shfl_xor_sync(0xffffffffu, xy, o);    // only one lane holds a non-zero value
       }
-      my_loss = __logf(s) + m - xy;
+      my_loss += __logf(s) + m - xy;
       if (drow) {
         const float k = inv_valid / s;
 #pragma unroll
@@ -141,7 +143,8 @@ int lgs_seg_ce(const float* d_logits, int64_t n, int32_t c, const int64_t* d_lab
   if ((reinterpret_cast<uintptr_t>(d_logits) & 15) || (reinterpret_cast<uintptr_t>(d_grad_logits) & 15))
     return fail(LGS_E_UNSUPPORTED, "lgs_seg_ce: logits / gradient rows must be 16-byte aligned");
   LGS_LAUNCH_PDL(seg_ce_count_kernel, 1, 1024, 0, stream, d_labels, n, c, ignore_label, d_ws);
-  LGS_LAUNCH_PDL(seg_ce_kernel, unsigned(cdiv(n, SCE_THREADS / 32)), SCE_THREADS, 0, stream, d_logits, n, c, d_labels,
+  const unsigned sce_grid = unsigned(std::min<int64_t>(cdiv(n, SCE_THREADS / 32), 148 * 8));
+  LGS_LAUNCH_PDL(seg_ce_kernel, sce_grid, SCE_THREADS, 0, stream, d_logits, n, c, d_labels,
              ignore_label, d_ws, d_loss, d_grad_logits);
   return LGS_OK;
 }
