@@ -468,6 +468,11 @@ def run_engine(args, rank, world, local_rank):
         barrier()
 
     # ---- timed region: `value` --------------------------------------------------------------------------
+    # the cyclic garbage collector stays off inside the timed regions (collected right before): a generation-2 pass over the
+    # process's objects is one candidate for the single 50-100 ms host stall seen in about one value leg in fifteen
+    import gc
+    gc.collect()
+    gc.disable()
     l0 = _lib.launch_count()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -506,6 +511,7 @@ def run_engine(args, rank, world, local_rank):
     t1.record()
     barrier()
     clocks_e2e = clk.summary((t_e0, time.time()))
+    gc.enable()
     clk.__exit__()
     ms_e2e = t0.elapsed_time(t1)
 
