@@ -445,11 +445,13 @@ def run_engine(args, rank, world, local_rank):
         resident_step()
     barrier()
     if not args.profile_run:
-        # settle: further UNTIMED batches of 5 steps until two consecutive batches agree within 3 % (max over ranks), at most
-        # 40 batches.  A fresh box pages the image / driver in for the first seconds (one run in three showed a 0.6 s host stall
+        # settle: further UNTIMED batches of 5 steps — at least 8, until four consecutive batches agree within 3 % (max over
+        # ranks), at most 60.  (The single 30-100 ms step seen in about one first timed region in ten — never in the second
+        # one, which starts ~45 steps into the process — points at warm-up that is still going on: allocator pools of the
+        # training / staging / side streams whose reuse depends on event timing.)  A fresh box pages the image / driver in for the first seconds (one run in three showed a 0.6 s host stall
         # inside the first timed region after 10 warm-up steps: 40 ms/step instead of 11); the total goes into "warmup_done" ("warmup" echoes the requested count).
-        prev = None
-        for _ in range(40):
+        prev, stable = None, 0
+        for it in range(60):
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record()
             for _ in range(5):
@@ -462,9 +464,10 @@ def run_engine(args, rank, world, local_rank):
                 import torch.distributed as dist
                 dist.all_reduce(cur, op=dist.ReduceOp.MAX)
             cur = float(cur.item())
-            if prev is not None and abs(cur - prev) <= 0.03 * min(cur, prev):
-                break
+            stable = stable + 1 if (prev is not None and abs(cur - prev) <= 0.03 * min(cur, prev)) else 0
             prev = cur
+            if it >= 7 and stable >= 3:     # at least 40 further steps, the last four batches within 3 % of their neighbours
+                break
         barrier()
 
     # ---- timed region: `value` --------------------------------------------------------------------------
