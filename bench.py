@@ -479,18 +479,24 @@ def run_engine(args, rank, world, local_rank):
     l0 = _lib.launch_count()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]      # per-step diagnostics, created outside the region
+    for m in marks:
+        m.record()                                                                 # cudaEventCreate happens at the first record
+    torch.cuda.synchronize()
     t_w0 = time.time()
+    host_t = [time.perf_counter()]
     ev0.record()
-    marks = []
-    for _ in range(args.steps):
+    for i in range(args.steps):
         loss = resident_step()
-        marks.append(torch.cuda.Event(enable_timing=True))
-        marks[-1].record()
+        marks[i].record()
+        host_t.append(time.perf_counter())
     ev1.record()
     barrier()
     clocks_value = clk.summary((t_w0, time.time()))
     ms = ev0.elapsed_time(ev1)
     per_step = [a.elapsed_time(b) for a, b in zip([ev0] + marks[:-1], marks)]      # diagnostics only: the value is ms / steps
+    host_ms = [1e3 * (b - a) for a, b in zip(host_t[:-1], host_t[1:])]             # host time of each step's issue (no sync)
+    i_max = max(range(len(per_step)), key=per_step.__getitem__)
     launches = _lib.launch_count() - l0
     loss_val = float(loss.item())
     if args.profile_run:
@@ -582,7 +588,9 @@ def run_engine(args, rank, world, local_rank):
     res = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "warmup_done": warm_done, "ms_per_step": round(ms / args.steps, 3),
-        "step_ms": {"median": round(statistics.median(per_step), 3), "min": round(min(per_step), 3), "max": round(max(per_step), 3)},
+        "step_ms": {"median": round(statistics.median(per_step), 3), "min": round(min(per_step), 3), "max": round(max(per_step), 3),
+                    "argmax": i_max, "host_issue_ms_median": round(statistics.median(host_ms), 3),
+                    "host_issue_ms_around_max": [round(h, 2) for h in host_ms[max(0, i_max - 2): i_max + 2]]},
         **({"per_rank": per_rank} if per_rank else {}), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.dtype == "f32" else "bf16", "data": "synthetic",
         "config": {"workload": workload_string(args.model, n_vox, args.voxel_size, args.voxels, args.config), "voxels_per_gpu": n_vox, "algo": args.algo,
