@@ -325,7 +325,7 @@ def run_engine(args, rank, world, local_rank):
     # ONE nvidia-smi poller (rank 0 only: concurrent pollers slow the driver), started now — seconds before the first timed
     # region — because its NVML start-up stalls CUDA calls for a few hundred ms; it then polls every 200 ms through both
     # timed regions and each region reports the samples that fall inside it.
-    clk = ClockSampler(local_rank if rank == 0 else -1)
+    clk = ClockSampler(local_rank if (rank == 0 and os.environ.get("LGS_BENCH_NO_CLOCKS", "0") == "0") else -1)   # knob: diagnose sampler-induced stalls
     clk.__enter__()
     E.set_conv_algo(args.algo)
     fdtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
@@ -368,6 +368,18 @@ def run_engine(args, rank, world, local_rank):
                                 high_priority=os.environ.get("LGS_STAGE_PRIORITY", "0") != "0")
           if not args.no_prefetch else None)
     tickets = {}
+    if pf is not None and os.environ.get("LGS_BENCH_NO_PRERESERVE", "0") == "0":
+        # The staging stream's allocations (coordinate maps, tables, plans of the NEXT batch) are released only after the
+        # training stream's recorded use of them: when that event is still pending the caching allocator finds no cached
+        # block and falls through to cudaMalloc, which waits for the GPU — the 50-100 ms `stage` call behind the occasional
+        # long step (profiles/r2_bench_stage_stall.txt).  One large block cached in the staging stream's pool up front
+        # gives the allocator something to split instead.
+        # Both pools (large blocks and the <= 1 MB small-block pool) of both streams that allocate during a step.
+        for strm in (pf.stream, torch.cuda.current_stream(dev)):
+            with torch.cuda.stream(strm):
+                spare = [torch.empty(1 << 30, dtype=torch.uint8, device=dev)] + \
+                        [torch.empty(512 << 10, dtype=torch.uint8, device=dev) for _ in range(256)]
+            del spare
 
     # the engine's fused softmax cross-entropy (lgs_seg_ce: one pass over the logits) unless LGS_ATEN_CE=1
     crit = _aten_criterion if os.environ.get("LGS_ATEN_CE") else (lambda x, y: lgs_losses.cross_entropy(x, y, ignore_index=-1))
@@ -399,6 +411,8 @@ def run_engine(args, rank, world, local_rank):
 
     prof_mode = {"on": False}     # per-launch CUDA events need the facade's hooks: the profiled steps run module by module
 
+    phases = []              # host ms per step: (get, stage next batch, step + optimiser) — diagnostics of host-side stalls
+
     def staged_step(key, src):
         flush.fill_(0.0)
         native = None if prof_mode["on"] else native_step
@@ -407,9 +421,14 @@ def run_engine(args, rank, world, local_rank):
             return train_step(E.SparseTensor, model, opt, c, f.to(fdtype), lab, reducer, criterion=crit, program=program, native=native, clip=clip)
         if key not in tickets:
             tickets[key] = pf.stage(*src)
+        t0 = time.perf_counter()
         st, lab = pf.get(tickets[key])
+        t1 = time.perf_counter()
         tickets[key] = pf.stage(*src)                        # next step's batch, overlapped with this step
-        return train_step(None, model, opt, None, None, lab, reducer, st=st, criterion=crit, program=program, native=native, clip=clip)
+        t2 = time.perf_counter()
+        out = train_step(None, model, opt, None, None, lab, reducer, st=st, criterion=crit, program=program, native=native, clip=clip)
+        phases.append((1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (time.perf_counter() - t2)))   # get, stage next, run + optimiser
+        return out
 
     def resident_step():
         return staged_step("resident", (d_coords, d_feats, d_labels))
@@ -486,10 +505,14 @@ def run_engine(args, rank, world, local_rank):
     t_w0 = time.time()
     host_t = [time.perf_counter()]
     ev0.record()
+    del phases[:]
+    segs_before = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)       # cudaMalloc calls so far (caching allocator)
     for i in range(args.steps):
         loss = resident_step()
         marks[i].record()
         host_t.append(time.perf_counter())
+    value_phases = list(phases)
+    segs_after = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
     ev1.record()
     barrier()
     clocks_value = clk.summary((t_w0, time.time()))
@@ -590,7 +613,10 @@ def run_engine(args, rank, world, local_rank):
         "warmup": args.warmup, "warmup_done": warm_done, "ms_per_step": round(ms / args.steps, 3),
         "step_ms": {"median": round(statistics.median(per_step), 3), "min": round(min(per_step), 3), "max": round(max(per_step), 3),
                     "argmax": i_max, "host_issue_ms_median": round(statistics.median(host_ms), 3),
-                    "host_issue_ms_around_max": [round(h, 2) for h in host_ms[max(0, i_max - 2): i_max + 2]]},
+                    "host_issue_ms_around_max": [round(h, 2) for h in host_ms[max(0, i_max - 2): i_max + 2]],
+                    "host_phases_ms_at_max(get,stage_next,run+opt)": [round(x, 2) for x in value_phases[i_max]] if i_max < len(value_phases) else None,
+                    "cudaMalloc_segments_during_region": int(segs_after - segs_before),
+                    "host_phases_ms_median": [round(statistics.median(p[j] for p in value_phases), 2) for j in range(3)] if value_phases else None},
         **({"per_rank": per_rank} if per_rank else {}), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.dtype == "f32" else "bf16", "data": "synthetic",
         "config": {"workload": workload_string(args.model, n_vox, args.voxel_size, args.voxels, args.config), "voxels_per_gpu": n_vox, "algo": args.algo,
