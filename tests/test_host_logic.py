@@ -292,3 +292,25 @@ def test_bench_roofline_report_on_synthetic_launch_records():
     assert abs(r["share_of_step"] - 6 * 0.37 / 16.0) < 1e-3
     assert r["all_wgrad"]["share_of_step"] == round(3 * 0.345 / 16.0, 3)
     assert r["traffic"] is None or isinstance(r["traffic"], int)
+
+
+def test_bank_colour_scheme_of_the_neighbourhood_plan():
+    """csrc/nbplan.cu, "Colours": g = (x + 3y + 5z) / step mod 8 is additive, so a translation by any kernel offset shifts the
+    colours of a group of voxels by one constant — eight pairwise different colours stay pairwise different for all 27 offsets
+    (the bank-conflict-free cache reads of conv_nb.cu rest on this) — and every axis-aligned plane carries all eight colours."""
+    import itertools
+    import numpy as np
+    rng = np.random.default_rng(0)
+    colour = lambda c, step: ((c[..., 0] // step) + 3 * (c[..., 1] // step) + 5 * (c[..., 2] // step)) & 7  # noqa: E731
+    for step in (1, 2, 8):
+        pts = rng.integers(-50, 50, size=(4000, 3)) * step
+        g = colour(pts, step)
+        octet = np.stack([pts[np.flatnonzero(g == k)[0]] for k in range(8)])          # eight voxels of eight different colours
+        for off in itertools.product((-1, 0, 1), repeat=3):
+            moved = colour(octet + np.array(off) * step, step)
+            assert len(set(moved.tolist())) == 8
+            assert len(set(((moved - colour(octet, step)) & 7).tolist())) == 1        # one constant shift
+        for axis in range(3):                                                          # planes x / y / z = const
+            plane = pts.copy()
+            plane[:, axis] = 3 * step
+            assert set(colour(plane, step).tolist()) == set(range(8))
