@@ -86,7 +86,23 @@ class ClockSampler:
                 raise RuntimeError('disabled')
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            h = None
+            try:        # the CUDA device's own identity (NVML indices ignore CUDA_VISIBLE_DEVICES): UUID, then PCI bus id
+                props = torch.cuda.get_device_properties(self.index)
+                uuid = str(getattr(props, "uuid", "") or "")
+                if uuid:
+                    h = nv.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            except Exception:
+                h = None
+            if h is None:
+                try:
+                    props = torch.cuda.get_device_properties(self.index)
+                    bus = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+                    h = nv.nvmlDeviceGetHandleByPciBusId(bus)
+                except Exception:
+                    h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self._stop = threading.Event()
             self.t = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
             self.t.start()
