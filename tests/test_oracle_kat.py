@@ -171,3 +171,91 @@ def test_voxelize_oracle_matches_numpy_matmul():
     homo = np.hstack((pts, np.ones((3000, 1), dtype=pts.dtype)))
     ref = np.floor(homo @ M.T[:, :3])        # the reference's expression, lib/voxelizer.py:138-139
     assert (q != ref.astype(np.int32)).sum() <= 2   # only points within an ulp of a voxel face may differ
+
+
+def _densify(coords, feats, lo, size):
+    """[n, 4] (b, x, y, z) sparse rows -> dense [B, C, Z, Y, X] grid (zeros elsewhere), grid origin `lo`"""
+    b = int(coords[:, 0].max()) + 1
+    g = torch.zeros(b, feats.shape[1], size, size, size, dtype=feats.dtype)
+    x, y, z = (torch.from_numpy(coords[:, i] - lo).long() for i in (1, 2, 3))
+    g[torch.from_numpy(coords[:, 0]).long(), :, z, y, x] = feats
+    return g
+
+
+def test_conv3_equals_dense_conv3d_at_active_sites():
+    """An anchor that does not come from this repository's reading of MinkowskiEngine: a stride-1 3x3x3 sparse convolution is
+    torch's DENSE conv3d (cross-correlation, zero padding) sampled at the active voxels, with W[k] at kernel position
+    (kz, ky, kx) = (k // 9, (k // 3) % 3, k % 3) — ME's x-fastest offset enumeration with centred odd kernels (App. A.5).
+    Values, input gradient and weight gradient, fp64."""
+    rng = np.random.default_rng(3)
+    c = random_sparse_coords(rng, 500, extent=9, batches=2)
+    cin, cout = 5, 4
+    f = torch.from_numpy(rng.standard_normal((c.shape[0], cin))).double().requires_grad_(True)
+    conv = _conv(cin, cout, 3, bias=True).double()
+    y = conv(_st(c, f))
+    assert torch.equal(y.C, torch.from_numpy(c))
+    gy = torch.from_numpy(rng.standard_normal(tuple(y.F.shape)))
+    y.F.backward(gy)
+    lo, size = int(c[:, 1:].min()), int(c[:, 1:].max() - c[:, 1:].min()) + 1
+    f2 = f.detach().clone().requires_grad_(True)
+    w = conv.kernel.detach().clone().requires_grad_(True)                       # [27, cin, cout]
+    wd = w.reshape(3, 3, 3, cin, cout).permute(4, 3, 0, 1, 2)                    # [cout, cin, kz, ky, kx]
+    dense = torch.nn.functional.conv3d(_densify(c, f2, lo, size), wd, conv.bias.detach().reshape(-1), padding=1)
+    x_, y_, z_ = (torch.from_numpy(c[:, i] - lo).long() for i in (1, 2, 3))
+    ref = dense[torch.from_numpy(c[:, 0]).long(), :, z_, y_, x_]
+    assert torch.allclose(y.F, ref, rtol=1e-12, atol=1e-12)
+    ref.backward(gy)
+    assert torch.allclose(f.grad, f2.grad, rtol=1e-11, atol=1e-12)
+    assert torch.allclose(conv.kernel.grad, w.grad, rtol=1e-11, atol=1e-12)
+
+
+def test_strided_conv2_equals_dense_conv3d_stride2():
+    """2x2x2 stride-2 down-sampling: coarse voxel = floor(c / 2) * 2, fine voxel at offset (dx, dy, dz) in {0, 1}^3 from it
+    contributes through W[dx + 2 dy + 4 dz] (even kernels are not centred, App. A.5) = dense conv3d with stride 2, no padding,
+    on a grid whose origin is even; sampled at the coarse map's coordinates / 2"""
+    rng = np.random.default_rng(5)
+    c = random_sparse_coords(rng, 400, extent=10, batches=1)
+    c[:, 1:] -= c[:, 1:].min()                                                   # origin 0 (even)
+    cin, cout = 3, 6
+    f = torch.from_numpy(rng.standard_normal((c.shape[0], cin))).double()
+    conv = _conv(cin, cout, 2, stride=2).double()
+    y = conv(_st(c, f))
+    size = int(c[:, 1:].max()) + 2
+    size += size % 2
+    wd = conv.kernel.detach().reshape(2, 2, 2, cin, cout).permute(4, 3, 0, 1, 2)
+    dense = torch.nn.functional.conv3d(_densify(c, f, 0, size), wd, stride=2)
+    oc = y.C.numpy()
+    assert (oc[:, 1:] % 2 == 0).all() and y.tensor_stride == [2, 2, 2]
+    ref = dense[torch.from_numpy(oc[:, 0]).long(), :, torch.from_numpy(oc[:, 3] // 2).long(), torch.from_numpy(oc[:, 2] // 2).long(),
+                torch.from_numpy(oc[:, 1] // 2).long()]
+    assert torch.allclose(y.F.detach(), ref, rtol=1e-12, atol=1e-12)
+    # every non-zero cell of the dense result is an active coarse voxel and vice versa (the coarse map is exactly the support)
+    support = (_densify(c, torch.ones(c.shape[0], 1, dtype=torch.float64), 0, size).reshape(1, 1, size // 2, 2, size // 2, 2, size // 2, 2)
+               .amax((3, 5, 7)) > 0).sum().item()
+    assert support == oc.shape[0]
+
+
+def test_transposed_conv2_equals_dense_conv_transpose3d():
+    """2x2x2 stride-2 up-sampling onto the encoder's fine map: out[p] = in[parent(p)] . W[k(p)], k(p) = p's offset inside its
+    parent, x fastest = dense conv_transpose3d with stride 2 (every fine cell receives exactly one product) sampled at the
+    fine map's voxels"""
+    rng = np.random.default_rng(8)
+    c = random_sparse_coords(rng, 300, extent=8, batches=1)
+    c[:, 1:] -= c[:, 1:].min()
+    cmid, cout = 4, 3
+    x = _st(c, torch.from_numpy(rng.standard_normal((c.shape[0], 2))).double())
+    down = _conv(2, cmid, 2, stride=2).double()
+    up = _conv(cmid, cout, 2, stride=2, transpose=True).double()
+    mid = down(x)
+    y = up(mid)
+    assert torch.equal(y.C, x.C) and y.tensor_stride == [1, 1, 1]                 # lands on the encoder's map, same row order
+    mc = mid.C.numpy()
+    size = int(c[:, 1:].max()) + 2
+    size += size % 2
+    coarse = torch.zeros(1, cmid, size // 2, size // 2, size // 2, dtype=torch.float64)
+    iz, iy, ix = (torch.from_numpy(mc[:, i] // 2).long() for i in (3, 2, 1))
+    coarse[0, :, iz, iy, ix] = mid.F.detach().t()
+    wd = up.kernel.detach().reshape(2, 2, 2, cmid, cout).permute(3, 4, 0, 1, 2)   # [c_in, c_out, kz, ky, kx]
+    dense = torch.nn.functional.conv_transpose3d(coarse, wd, stride=2)
+    ref = dense[0, :, torch.from_numpy(c[:, 3]).long(), torch.from_numpy(c[:, 2]).long(), torch.from_numpy(c[:, 1]).long()].t()
+    assert torch.allclose(y.F.detach(), ref, rtol=1e-12, atol=1e-12)
